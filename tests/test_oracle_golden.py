@@ -1,0 +1,118 @@
+"""CPU: the oracle's env layer against the committed golden vectors, which were
+produced by the reference's own hover.py (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.hover_oracle import HoverConfig, HoverVecOracle
+from oracle.quadx_model import QuadXParams
+
+SCENARIOS = ["fly_quiet", "fly_noisy", "floor", "dome"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"hover_ref_{name}.npz"))
+
+
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_oracle_reproduces_reference_hover(golden_dir, name):
+    g = _load(golden_dir, name)
+    orc = HoverVecOracle(
+        1, QuadXParams(), HoverConfig(), seed=int(g["seed"]), env_id0=int(g["env_id"]),
+        auto_reset=False, noise=bool(g["noise"]), vision_mode="raster",
+    )
+    ep = -1
+    for k in range(g["actions"].shape[0]):
+        if g["episode_start"][k]:
+            ep += 1
+            obs = orc.reset()
+            np.testing.assert_allclose(obs[0], g["reset_obs"][ep], rtol=0, atol=1e-12)
+        obs, r, te, tr, _ = orc.step(g["actions"][k][None])
+        np.testing.assert_allclose(obs[0], g["obs"][k], rtol=0, atol=1e-12, err_msg=f"obs step {k}")
+        assert abs(r[0] - g["reward"][k]) < 1e-11, k
+        assert bool(te[0]) == bool(g["terminated"][k]) and bool(tr[0]) == bool(g["truncated"][k]), k
+        np.testing.assert_allclose(orc.st.aviary_state()[0], g["state"][k], rtol=0, atol=1e-12)
+
+
+def test_episode_length_signature(golden_dir):
+    """The reference's TensorBoard runs start at ep_len 32 (floor rule) and
+    saturate at 402 (time limit) -- hover.py:275-276,283-290,356."""
+    floor = _load(golden_dir, "floor")
+    assert int(np.argmax(floor["terminated"])) + 1 == 32
+    assert floor["reward"][31] < -99.0 and floor["reward"][30] > -10.0
+    fly = _load(golden_dir, "fly_quiet")
+    assert int(np.argmax(fly["truncated"])) + 1 == 402
+    assert not fly["terminated"].any()
+    # sticky flags freeze the physics after the episode ended (hover.py:347-348)
+    np.testing.assert_array_equal(fly["state"][402], fly["state"][407])
+
+
+def test_prev_action_survives_reset(golden_dir):
+    """hover.py:31,357: prev_action is not cleared by reset(), so the first
+    smoothness penalty of an episode is taken against the previous episode's
+    last action."""
+    g = _load(golden_dir, "fly_noisy")
+    k = int(np.where(g["episode_start"])[0][1])
+    a_prev, a = g["actions"][k - 1], g["actions"][k]
+    orc = HoverVecOracle(1, seed=int(g["seed"]), env_id0=int(g["env_id"]), auto_reset=False, noise=True, vision_mode="raster")
+    orc.reset()
+    for j in range(k):
+        orc.step(g["actions"][j][None])
+    orc.reset()
+    _, r, _, _, _ = orc.step(a[None])
+    assert abs(r[0] - g["reward"][k]) < 1e-11
+    assert np.linalg.norm(a - a_prev) > 1e-3  # the quirk is actually exercised
+
+
+def test_auto_reset_matches_manual_reset():
+    """SB3 VecEnv semantics: on done the returned obs is the first obs of the next
+    episode and the terminal obs is reported separately."""
+    a = np.tile(np.array([[0.0, 0.0, 0.0, -1.0]]), (3, 1))
+    auto = HoverVecOracle(3, seed=5, auto_reset=True, noise=True)
+    man = HoverVecOracle(3, seed=5, auto_reset=False, noise=True)
+    auto.reset()
+    man.reset()
+    for k in range(40):
+        o1, r1, te1, tr1, info = auto.step(a)
+        o2, r2, te2, tr2, _ = man.step(a)
+        np.testing.assert_array_equal(r1, r2)
+        np.testing.assert_array_equal(te1, te2)
+        if te1.any():
+            assert k == 31
+            np.testing.assert_array_equal(info["terminal_obs"], o2)
+            o2 = man.reset()
+            np.testing.assert_array_equal(o1, o2)
+        else:
+            np.testing.assert_array_equal(o1, o2)
+    assert auto.n_done == 3 and auto.sum_len == 96
+
+
+def test_analytic_vision_close_to_rasterised():
+    """Bound of the analytic-vs-pixel error of the three vision features over
+    random in-dome poses; these are the tolerances the GPU parity
+    tests use for obs[7:16]."""
+    from oracle import vision
+    from oracle.hover_oracle import detect_rectangle
+    from oracle.quadx_model import euler_to_quat
+
+    p = QuadXParams()
+    rng = np.random.default_rng(1)
+    n = 400
+    pos = rng.uniform(-2, 2, (n, 3))
+    pos[:, 2] = rng.uniform(0.01, 2.5, n)
+    rpy = rng.uniform(-0.5, 0.5, (n, 3))
+    q = euler_to_quat(rpy)
+    v, c, a, r = vision.analytic_features(pos, q, p)
+    V = np.zeros(n, bool)
+    C = np.zeros((n, 2))
+    A = np.zeros(n)
+    R = np.zeros(n)
+    for i in range(n):
+        V[i], C[i], A[i], R[i] = detect_rectangle(vision.render_rgba(pos[i], q[i], p))
+    assert (V != v).mean() <= 0.01
+    both = V & v
+    assert both.sum() > 200
+    assert np.abs(C - c)[both].max() * 64 <= 1.5  # pixels
+    assert (np.abs(A - a)[both] / A[both]).max() <= 0.10
+    assert np.abs(R - r)[both].max() <= 0.35  # one pixel row/column on a ~5 px high quad
