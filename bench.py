@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the QuadX hover step (physics + reward + obs) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+
+One "step" = one pass of the hot path (QuadXHoverEnv.step for every env: 12
+physics sub-steps, 6 control updates, reward, termination, auto-reset, obs)
+over one batch of E envs per GPU.  Prints ONE JSON line (rank 0).  See
+DESIGN.md "Measurement" for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_ENV_STEP = 358  # 128+128 state, 16 action, 80 obs, 4 reward, 2 flags
+ACT_BYTES, OUT_BYTES = 16, 80 + 4 + 1 + 1
+HOVER_THR = (0.1 * 9.81 / 4.0) ** 0.5
+METRIC = "env-steps/sec (physics+reward+obs), QuadX hover"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-envs", type=int, default=8192, help="envs of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the configs[1] (4096 envs) side measurements")
+    return ap.parse_args()
+
+
+def workload_config(envs_per_gpu: int, n_gpus: int) -> dict:
+    return {
+        "workload": "hover (hover.py QuadXHoverEnv), %d envs/GPU x %d GPU, physics+reward+obs+auto-reset step" % (envs_per_gpu, n_gpus),
+        "baseline_config": "configs[3] shard size generalised to N=1 (1 Mi envs on one GPU); configs[1] (4096 envs) reported under 'hover_4096'",
+        "envs_per_gpu": envs_per_gpu,
+        "n_envs_total": envs_per_gpu * n_gpus,
+        "sub_steps_per_env_step": 12,
+        "spawn": "pos (0,0,1) level at rest, motors at hover throttle; reference reset protocol (10 idle Aviary.step) on auto-reset",
+        "actions": "U(-1,1)*0.3 rates, thrust a3 = hover + 0.3*U(-1,1); 8 pre-generated device batches cycled",
+        "motor_noise": "2 % (cf2x.yaml:5), Philox seed 1234",
+        "l2_policy": "working set per step (state 176 B r+w + outputs, x envs) exceeds the 126 MB L2 when envs/GPU >= 2^19; no flush needed at the default size",
+        "sharding": "contiguous env ranges, Philox key = global env id, no data-path collective",
+    }
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- CPU arm
+def cpu_run(n_envs: int, steps: int, warmup: int, budget_s: float = 25.0) -> dict:
+    """Time the CPU oracle (port of the reference path) on a bounded sample of the
+    same workload.  Uses the threaded C port when it is built, else numpy."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (8, n_envs, 4))
+    acts[..., :3] *= 0.3
+    acts[..., 3] = (2 * HOVER_THR - 1) + 0.3 * acts[..., 3]
+    try:
+        from oracle import c_oracle
+
+        sim = c_oracle.COracle(n_envs, seed=1234, start_pos=(0, 0, 1.0), spawn_throttle=HOVER_THR)
+        kind_detail, cores = "oracle/quadx_oracle.c (float64, all host threads)", sim.threads
+        step = lambda a: sim.step(a)  # noqa: E731
+        sim.reset()
+    except Exception:
+        from oracle.hover_oracle import HoverConfig, HoverVecOracle
+
+        sim = HoverVecOracle(n_envs, cfg=HoverConfig(start_pos=(0, 0, 1.0), spawn_throttle=HOVER_THR), seed=1234, noise=True)
+        kind_detail, cores = "oracle/hover_oracle.py (numpy float64, vectorised over envs)", 1
+        step = lambda a: sim.step(a)  # noqa: E731
+        sim.reset()
+    for k in range(warmup):
+        step(acts[k % 8])
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(steps):
+        step(acts[k % 8])
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * done / dt, "unit": UNIT, "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{n_envs} envs x {done} steps of the same hover workload, {kind_detail}", "seconds": dt, "steps_done": done,
+            "ms_per_step": 1e3 * dt / done}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = args.steps
+    r = cpu_run(args.cpu_envs, steps, min(args.warmup, 2), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_done"],
+        "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.envs, args.gpus),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "PyFlyt/pybullet are not installable here (no network); the reference arm is the CPU oracle port of the same path",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------- ours
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import fpv_drone_rl_agent_b200 as pkg
+    from fpv_drone_rl_agent_b200 import _lib
+
+    E = args.envs
+    cfg = pkg.default_config()
+    cfg.update(start_pos=[0, 0, 1.0], spawn_throttle=HOVER_THR, auto_reset=1, noise=1)
+    sim = pkg.QuadXSim(E, cfg, seed=1234, env_id0=rank * E, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(rank)
+    acts = torch.rand(8, E, 4, generator=g) * 2 - 1
+    acts[..., :3] *= 0.3
+    acts[..., 3] = (2 * HOVER_THR - 1) + 0.3 * acts[..., 3]
+    acts_pinned = acts.pin_memory()
+    acts = acts.to(dev)
+    obs = torch.zeros(E, 20, device=dev)
+    rew = torch.zeros(E, device=dev)
+    te = torch.zeros(E, dtype=torch.uint8, device=dev)
+    tr = torch.zeros(E, dtype=torch.uint8, device=dev)
+    sim.reset(obs)
+    for k in range(args.warmup):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    torch.cuda.synchronize()
+    launches0 = _lib.lib().qx_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t0 = time.perf_counter()
+    ev[0].record()
+    for k in range(args.steps):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    launches = _lib.lib().qx_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    value = E * world * args.steps / (max_ms * 1e-3)
+
+    # ---- e2e: the C-ABI host-buffer call, H2D + kernel + D2H inside the timed region
+    h_obs = torch.zeros(E, 20).pin_memory()
+    h_rew = torch.zeros(E).pin_memory()
+    h_te = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    h_tr = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    import ctypes as C
+
+    L = _lib.lib()
+    vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def host_step(k):
+        _lib.check(L.qx_step_host(sim._h, vp(acts_pinned[k % 8]), vp(h_obs), vp(h_rew), vp(h_te), vp(h_tr), None))
+
+    for k in range(3):
+        host_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0 = time.perf_counter()
+    for k in range(e2e_steps):
+        host_step(k)
+    e1 = time.perf_counter()
+    te2e = torch.tensor([e1 - e0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+    e2e_value = E * world * e2e_steps / float(te2e.item())
+
+    line = None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        kern_ms = statistics.mean(per)
+        achieved = E * ALG_BYTES_PER_ENV_STEP / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("envs") == E:
+                traffic = tj.get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(E, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * ACT_BYTES, "d2h_bytes_per_step": E * OUT_BYTES,
+                    "steps": e2e_steps, "api": "qx_step_host (C-ABI, pinned host buffers, synchronous)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "qx::quadx_step_kernel<false>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
+                         "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_small:
+            line["hover_4096"] = small_config(pkg, dev)
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_run(args.cpu_envs, 40, 2, budget_s=20.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
+    sim.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def small_config(pkg, dev) -> dict:
+    """BASELINE.json configs[1]: 4096 envs on one GPU -- latency-bound; reported
+    for per-step launches, a CUDA graph of 64 steps and step_k (K = 64)."""
+    import torch
+
+    n, K = 4096, 64
+    cfg = pkg.default_config()
+    cfg.update(start_pos=[0, 0, 1.0], spawn_throttle=HOVER_THR, auto_reset=1, noise=1)
+    sim = pkg.QuadXSim(n, cfg, seed=1234, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    a = torch.rand(K, n, 4, generator=g) * 2 - 1
+    a[..., :3] *= 0.3
+    a[..., 3] = (2 * HOVER_THR - 1) + 0.3 * a[..., 3]
+    a = a.to(dev)
+    obs = torch.zeros(K, n, 20, device=dev)
+    rew = torch.zeros(K, n, device=dev)
+    te = torch.zeros(K, n, dtype=torch.uint8, device=dev)
+    tr = torch.zeros(K, n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sim.reset(obs[0])
+    out = {"envs": n, "note": "L2 flushed (256 MB memset) before each timed block; 64 env steps per block"}
+
+    def timed(fn, reps=5):
+        best = []
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            best.append(s.elapsed_time(e))
+        return statistics.median(best)
+
+    def per_step():
+        for k in range(K):
+            sim.step(a[k], obs[k], rew[k], te[k], tr[k])
+
+    per_step()
+    ms = timed(per_step)
+    out["per_step_launch"] = {"env_steps_per_s": n * K / (ms * 1e-3), "us_per_step": 1e3 * ms / K}
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        per_step()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            per_step()
+    torch.cuda.synchronize()
+    ms = timed(graph.replay)
+    out["cuda_graph"] = {"env_steps_per_s": n * K / (ms * 1e-3), "us_per_step": 1e3 * ms / K}
+    ms = timed(lambda: sim.step_k(a, obs, rew, te, tr))
+    out["step_k64"] = {"env_steps_per_s": n * K / (ms * 1e-3), "us_per_step": 1e3 * ms / K, "alg_bytes_per_env_step": 102}
+    sim.close()
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -1,0 +1,538 @@
+// qx_kernels.cu -- K1: the fused env-step kernel (one thread per env) and the
+// C-ABI of include/quadx_b200.h.  sm_100a only.
+//
+// One launch of quadx_step_kernel does, per env, what the reference does in
+// QuadXHoverEnv.step (hover.py:334-358): scale the action, run 6 Aviary.step()
+// = 12 physics sub-steps with the rate PID every 2nd, build the 20-D
+// observation, compute reward / termination / truncation, and -- with
+// auto_reset -- the whole of reset() (hover.py:72-113, incl. its 10 idle
+// Aviary.step()) for the envs that finished.  The 44 carried words are read
+// once as 11 coalesced float4 loads, live in registers across the sub-steps,
+// and are written back once.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/quadx_b200.h"
+#include "qx_model.cuh"
+
+namespace qx {
+
+constexpr int kBlock = 128;
+
+struct Stats {
+  double sum_ret;
+  unsigned long long sum_len;
+  unsigned long long n_done;
+};
+
+struct StepArgs {
+  float4* state;
+  const float* actions;     // [k, n, act_dim]
+  void* obs;                // [k, n, obs_stride]
+  float* reward;            // [k, n]
+  uint8_t* terminated;      // [k, n]
+  uint8_t* truncated;       // [k, n]
+  float* terminal_obs;      // [n, obs_dim] or null
+  const uint8_t* mask;      // reset only
+  Stats* stats;
+  int64_t n;
+  int64_t obs_stride;
+  int32_t k;
+  int32_t obs_bf16;
+};
+
+template <int DIM>
+__device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int64_t row, int64_t stride, bool bf16) {
+  static_assert(DIM % 4 == 0, "obs rows are written as 16-byte / 8-byte vectors");
+  if (bf16) {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + row * stride;
+    if ((stride & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < DIM; j += 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[j], o[j + 1]), b = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t*>(&a);
+        v.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p + j) = v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) p[j] = __float2bfloat16_rn(o[j]);
+    }
+  } else {
+    float* p = reinterpret_cast<float*>(base) + row * stride;
+    if ((stride & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < DIM; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) p[j] = o[j];
+    }
+  }
+}
+
+// RESET_ONLY: qx_reset (masked reset, no step).  Otherwise k agent steps.
+template <bool RESET_ONLY>
+__global__ void __launch_bounds__(kBlock) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= a.n) return;
+  if (RESET_ONLY && a.mask && !a.mask[i]) return;
+  Env e;
+  load_env(e, a.state, a.n, i);
+  const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
+  const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i) >> 32));
+
+  for (int kk = 0; kk < (RESET_ONLY ? 1 : a.k); ++kk) {
+    const int64_t row = (int64_t)kk * a.n + i;
+    float act[4] = {0.f, 0.f, 0.f, 0.f};
+    float sp[4] = {0.f, 0.f, 0.f, 0.f};
+    int phase = RESET_ONLY ? 1 : 0;  // 0: the agent step, 1: reset (idle steps + first obs)
+    int nsub;
+    if (RESET_ONLY) {
+      respawn(e, c, k0, k1);
+      nsub = c.n_sub_reset;
+    } else {
+      if (c.task == QX_TASK_HOVER) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.actions) + row);
+        act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+        sp[0] = act[0] * c.act_scale[0];  // hover.py:337-341
+        sp[1] = act[1] * c.act_scale[1];
+        sp[2] = act[2] * c.act_scale[2];
+        sp[3] = 0.5f * (act[3] + 1.f);
+      } else {
+        act[0] = __ldg(a.actions + row);  // yaw.py:105-122: roll = pitch = 0, throttle = -1
+        sp[2] = act[0] * c.act_scale[2];
+      }
+      nsub = (e.flags & (F_TERM | F_TRUNC)) ? 0 : c.n_sub_step;  // hover.py:347-348
+    }
+    const bool live = RESET_ONLY || nsub > 0 || c.n_sub_step == 0;
+    float obs[QX_OBS_DIM_HOVER];
+
+    while (true) {
+      // ---- Aviary.step() x ratio: control on every ctrl_every-th sub-step
+      float pwm[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t stream = phase ? STREAM_RESET : STREAM_STEP;
+      for (int j = 0, cc = 0; j < nsub; ++j) {
+        if (cc == 0) control_update(e, c, sp, pwm);
+        if (++cc == c.ctrl_every) cc = 0;
+        physics_substep(e, c, pwm, (uint32_t)j, stream, k0, k1);
+      }
+      // ---- compute_attitude / compute_state, hover.py:224-272
+      float er, ep, ey;
+      if (phase == 0 && !live) {
+        er = e.peul[0]; ep = e.peul[1]; ey = e.peul[2];  // frozen after the episode ended
+      } else {
+        quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, er, ep, ey);
+      }
+      if (phase == 1) { e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey; }  // hover.py:112
+      const float two_pi = 6.28318530718f, pi = 3.14159265359f;
+      float d0 = er - e.peul[0] + pi, d1 = ep - e.peul[1] + pi, d2 = ey - e.peul[2] + pi;
+      d0 = d0 - two_pi * floorf(d0 * (1.f / two_pi)) - pi;  // hover.py:229 (python floor-mod)
+      d1 = d1 - two_pi * floorf(d1 * (1.f / two_pi)) - pi;
+      d2 = d2 - two_pi * floorf(d2 * (1.f / two_pi)) - pi;
+      bool vis;
+      float cx, cy, area, ratio;
+      vision(e, c, vis, cx, cy, area, ratio);
+      if (c.task == QX_TASK_HOVER) {
+        obs[0] = d0 * c.inv_agent_dt; obs[1] = d1 * c.inv_agent_dt; obs[2] = d2 * c.inv_agent_dt;
+        euler_to_quat(er, ep, ey, obs[3], obs[4], obs[5], obs[6]);  // hover.py:233
+        obs[7] = cx; obs[8] = cy; obs[9] = e.pcx; obs[10] = e.pcy;
+        obs[11] = area; obs[12] = e.parea; obs[13] = vis ? 1.f : 0.f; obs[14] = ratio; obs[15] = e.pratio;
+        obs[16] = act[0]; obs[17] = act[1]; obs[18] = act[2]; obs[19] = act[3];
+      }
+      e.pcx = cx; e.pcy = cy; e.parea = area; e.pratio = ratio;  // hover.py:270-272
+      if (phase == 1) break;
+
+      // ---- compute_term_trunc_reward, hover.py:274-332
+      float reward = -0.1f;  // hover.py:343
+      uint32_t fl = e.flags;
+      if (e.step_count > c.max_steps) fl |= F_TRUNC;  // hover.py:275-276
+      if (live) {
+        fl &= ~(F_LOWZ);
+        if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB;
+        if (e.spz < c.floor_thr) fl |= F_LOWZ;
+      }
+      if (fl & F_OOB) { reward = -100.f; fl |= F_TERM; }  // hover.py:278-281
+      if (e.step_count > c.floor_grace && !c.render && (fl & F_LOWZ)) {  // hover.py:283-290
+        reward = -100.f; fl |= F_TERM | F_ONFLOOR;
+      }
+      const float target_reward =
+          vis ? -(sqrtf(cx * cx + cy * cy) + fabsf(area - c.target_area) + fabsf(ratio - c.target_ratio)) : -2.0f;
+      reward -= 0.01f * e.swb[2] * e.swb[2];                        // hover.py:322-324
+      reward += target_reward - sqrtf(er * er + ep * ep);          // hover.py:326-327
+      const float a0 = act[0] - e.pa[0], a1 = act[1] - e.pa[1], a2 = act[2] - e.pa[2], a3 = act[3] - e.pa[3];
+      reward -= 0.2f * sqrtf(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
+      reward += 1.0f;                                               // hover.py:332
+      e.flags = fl;
+      e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;  // hover.py:354
+      e.step_count += 1;                               // hover.py:356
+      e.pa[0] = act[0]; e.pa[1] = act[1]; e.pa[2] = act[2]; e.pa[3] = act[3];  // hover.py:357
+      e.rng_ctr += 1u;
+      e.ep_ret += reward;
+      const bool term = fl & F_TERM, trunc = fl & F_TRUNC;
+      a.reward[row] = reward;
+      a.terminated[row] = term ? 1 : 0;
+      a.truncated[row] = trunc ? 1 : 0;
+      if (!(c.auto_reset && (term || trunc))) break;
+      // ---- SB3 VecEnv auto-reset + Monitor episode statistics
+      atomicAdd(&a.stats->sum_ret, (double)e.ep_ret);
+      atomicAdd(&a.stats->sum_len, (unsigned long long)e.step_count);
+      atomicAdd(&a.stats->n_done, 1ull);
+      if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, QX_OBS_DIM_HOVER, false);
+      respawn(e, c, k0, k1);
+      act[0] = act[1] = act[2] = act[3] = 0.f;  // hover.py:101
+      sp[0] = sp[1] = sp[2] = sp[3] = 0.f;      // set_mode(0): zero setpoint
+      phase = 1;
+      nsub = c.n_sub_reset;
+    }
+    if (a.obs) write_obs(obs, a.obs, row, a.obs_stride, a.obs_bf16 != 0);
+  }
+  store_env(e, a.state, a.n, i);
+}
+
+}  // namespace qx
+
+// ===========================================================================
+// host side / C-ABI
+// ===========================================================================
+struct QxHandle {
+  QxConfig cfg;
+  qx::DevConfig dev;
+  int64_t n;
+  int device;
+  float4* state;
+  qx::Stats* stats;
+  // staging for the *_host calls
+  cudaStream_t stream;
+  float* h_act; float* d_act;
+  float* h_obs; float* d_obs;
+  float* h_rew; float* d_rew;
+  uint8_t* h_flags; uint8_t* d_flags;  // [2n] terminated | truncated, then [n] mask
+  float* h_tobs; float* d_tobs;
+  bool staging;
+};
+
+static thread_local char g_err[512] = "";
+static int64_t g_launches = 0;
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define QX_CUDA(call)                                                             \
+  do {                                                                            \
+    cudaError_t _e = (call);                                                      \
+    if (_e != cudaSuccess) return fail(QX_ECUDA, #call ": %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" const char* qx_last_error(void) { return g_err; }
+extern "C" int32_t qx_version(void) { return QX_VERSION; }
+extern "C" int64_t qx_launch_count(void) { return g_launches; }
+extern "C" int64_t qx_sizeof_config(void) { return (int64_t)sizeof(QxConfig); }
+
+extern "C" int qx_default_config(int32_t task, QxConfig* c) {
+  if (!c || (task != QX_TASK_HOVER && task != QX_TASK_YAW)) return fail(QX_EINVAL, "qx_default_config: bad arguments");
+  memset(c, 0, sizeof(*c));
+  c->task = task;
+  c->mass = 0.1f;
+  c->inertia[0] = 3e-5f; c->inertia[1] = 3e-5f; c->inertia[2] = 5e-5f;
+  const float mx[4] = {0.028f, -0.028f, 0.028f, -0.028f}, my[4] = {-0.028f, 0.028f, 0.028f, -0.028f};
+  const float ts[4] = {-1.f, -1.f, 1.f, 1.f};
+  const float map[16] = {-1, -1, -1, 1, 1, 1, -1, 1, 1, -1, 1, 1, -1, 1, 1, 1};
+  memcpy(c->motor_x, mx, sizeof(mx)); memcpy(c->motor_y, my, sizeof(my));
+  memcpy(c->torque_sign, ts, sizeof(ts)); memcpy(c->motor_map, map, sizeof(map));
+  c->total_thrust = 4.0f; c->thrust_coef = 3.16e-10f; c->torque_coef = 7.94e-12f; c->noise_ratio = 0.02f; c->tau = 0.01f;
+  c->drag_coef_xyz = 1.5f; c->drag_area_xyz = 3.0e-4f; c->drag_coef_pqr = 1.0e-4f; c->air_density = 1.225f;
+  const float kp[3] = {2.0e-2f, 2.0e-2f, 4.0e-2f}, ki[3] = {2.5e-7f, 2.5e-7f, 1.35e-4f}, kd[3] = {5.0e-5f, 5.0e-5f, 0.f};
+  for (int a = 0; a < 3; ++a) { c->rate_kp[a] = kp[a]; c->rate_ki[a] = ki[a]; c->rate_kd[a] = kd[a]; c->rate_lim[a] = 1.0f; }
+  c->pwm_idle = 0.05f; c->physics_hz = 240.f; c->control_hz = 120.f; c->gravity = 9.81f;
+  c->state_stale = 1; c->gyro = 1; c->max_coord_vel = 100.f; c->floor_z = 0.01f;
+  c->cam_tilt_up_deg = 25.f; c->cam_fov_deg = 90.f; c->cam_res = 128.f; c->cam_near = 0.1f; c->vis_margin_px = 0.5f;
+  const float panel[12] = {4.98f, -1, 5, 4.98f, 1, 5, 4.98f, 1, 7, 4.98f, -1, 7};
+  memcpy(c->panel, panel, sizeof(panel));
+  c->aviary_steps_per_step = task == QX_TASK_HOVER ? 6 : 1;
+  c->max_steps = 400; c->floor_grace_steps = 30; c->reset_idle_steps = task == QX_TASK_HOVER ? 10 : 0;
+  c->agent_dt = 0.025f; c->flight_dome_size = 3.0f; c->floor_threshold = 0.1f;
+  c->target_area = 0.013f; c->target_ratio = 1.53f;
+  c->action_scale[0] = 30.f; c->action_scale[1] = 30.f; c->action_scale[2] = -30.f;
+  c->spawn_yaw_noise = task == QX_TASK_YAW ? 3.14159265f : 0.f;
+  c->render = 0; c->auto_reset = 1; c->noise = 1;
+  return QX_OK;
+}
+
+static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevConfig* d) {
+  memset(d, 0, sizeof(*d));
+  if (s.task != QX_TASK_HOVER) return fail(QX_EINVAL, "qx_create: only QX_TASK_HOVER is implemented in this build");
+  if (!(s.physics_hz > 0) || !(s.control_hz > 0) || s.control_hz > s.physics_hz) return fail(QX_EINVAL, "qx_create: bad rates");
+  const int per = (int)(s.physics_hz / s.control_hz);
+  d->task = s.task;
+  d->ctrl_every = per;
+  d->n_sub_step = s.aviary_steps_per_step * per;
+  d->n_sub_reset = s.reset_idle_steps * per;
+  d->max_steps = s.max_steps; d->floor_grace = s.floor_grace_steps; d->render = s.render; d->auto_reset = s.auto_reset;
+  d->noise = (s.noise && s.noise_ratio != 0.f) ? 1 : 0;
+  d->state_stale = s.state_stale; d->gyro = s.gyro;
+  d->obs_dim = QX_OBS_DIM_HOVER; d->act_dim = QX_ACT_DIM_HOVER;
+  const double h = 1.0 / s.physics_hz, T = 1.0 / s.control_hz;
+  d->h = (float)h; d->lag_alpha = (float)(h / s.tau); d->noise_ratio = s.noise_ratio;
+  d->thrust_k = (float)(s.total_thrust / 4.0); d->pwm_idle = s.pwm_idle;
+  const double max_rpm2 = s.total_thrust / (4.0 * s.thrust_coef);
+  for (int m = 0; m < 4; ++m) {
+    d->torque_k[m] = (float)(s.torque_sign[m] * s.torque_coef * max_rpm2);
+    d->mx[m] = s.motor_x[m]; d->my[m] = s.motor_y[m];
+  }
+  memcpy(d->map, s.motor_map, sizeof(d->map));
+  d->drag_c = (float)(0.5 * s.air_density * s.drag_coef_xyz * s.drag_area_xyz); d->drag_pqr = s.drag_coef_pqr;
+  for (int a = 0; a < 3; ++a) {
+    d->kp[a] = s.rate_kp[a]; d->kiT[a] = (float)(s.rate_ki[a] * T); d->kd_T[a] = (float)(s.rate_kd[a] / T); d->lim[a] = s.rate_lim[a];
+    d->I[a] = s.inertia[a]; d->invI[a] = (float)(1.0 / s.inertia[a]);
+    d->cam_off[a] = s.cam_offset[a]; d->act_scale[a] = s.action_scale[a];
+    d->start_pos[a] = s.start_pos[a]; d->start_rpy[a] = s.start_rpy[a];
+  }
+  d->inv_mass = (float)(1.0 / s.mass); d->g = s.gravity; d->vmax = s.max_coord_vel; d->floor_z = s.floor_z;
+  const double tilt = s.cam_tilt_up_deg * M_PI / 180.0;
+  d->cam_sd = (float)sin(tilt); d->cam_cd = (float)cos(tilt);
+  d->inv_tan = (float)(1.0 / tan(0.5 * s.cam_fov_deg * M_PI / 180.0));
+  d->res = s.cam_res; d->half_res = 0.5f * s.cam_res; d->inv_half_res = 2.0f / s.cam_res; d->inv_res2 = 1.0f / (s.cam_res * s.cam_res);
+  d->cam_near = s.cam_near; d->margin = s.vis_margin_px;
+  memcpy(d->panel, s.panel, sizeof(d->panel));
+  d->inv_agent_dt = 1.0f / s.agent_dt; d->dome2 = s.flight_dome_size * s.flight_dome_size; d->floor_thr = s.floor_threshold;
+  d->target_area = s.target_area; d->target_ratio = s.target_ratio;
+  d->spawn_thr = s.spawn_throttle; d->spawn_pos_noise = s.spawn_pos_noise; d->spawn_yaw_noise = s.spawn_yaw_noise;
+  d->seed_lo = (uint32_t)seed; d->seed_hi = (uint32_t)(seed >> 32);
+  d->env_lo = (uint32_t)env_id0; d->env_hi = (uint32_t)(env_id0 >> 32);
+  return QX_OK;
+}
+
+extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uint64_t env_id0, int device, QxHandle** out) {
+  if (!cfg || !out || n_envs <= 0) return fail(QX_EINVAL, "qx_create: bad arguments");
+  int ndev = 0;
+  QX_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(QX_EINVAL, "qx_create: no such device");
+  cudaDeviceProp prop;
+  QX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(QX_EARCH, "qx_create: this library is built for sm_100a (B200) only");
+  QxHandle* h = new (std::nothrow) QxHandle();
+  if (!h) return fail(QX_ENOMEM, "qx_create: out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg; h->n = n_envs; h->device = device;
+  int rc = derive(*cfg, seed, env_id0, &h->dev);
+  if (rc) { delete h; return rc; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * 11 * n_envs);
+  if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
+  if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * 11 * n_envs);
+  if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(qx::Stats));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    cudaFree(h->state); cudaFree(h->stats); delete h;
+    return fail(QX_ECUDA, "qx_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return QX_OK;
+}
+
+extern "C" int qx_destroy(QxHandle* h) {
+  if (!h) return QX_OK;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  cudaFree(h->state); cudaFree(h->stats);
+  if (h->staging) {
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_tobs);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_flags); cudaFree(h->d_tobs);
+  }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaSetDevice(prev);
+  delete h;
+  return QX_OK;
+}
+
+extern "C" int64_t qx_num_envs(const QxHandle* h) { return h ? h->n : 0; }
+extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0; }
+extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
+extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
+
+static int launch(QxHandle* h, bool reset_only, const qx::StepArgs& a, cudaStream_t s) {
+  const unsigned grid = (unsigned)((h->n + qx::kBlock - 1) / qx::kBlock);
+  if (reset_only)
+    qx::quadx_step_kernel<true><<<grid, qx::kBlock, 0, s>>>(h->dev, a);
+  else
+    qx::quadx_step_kernel<false><<<grid, qx::kBlock, 0, s>>>(h->dev, a);
+  ++g_launches;
+  QX_CUDA(cudaGetLastError());
+  return QX_OK;
+}
+
+extern "C" int qx_reset(QxHandle* h, const uint8_t* mask_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride, void* stream) {
+  if (!h) return fail(QX_EINVAL, "qx_reset: null handle");
+  if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_reset: obs_stride < obs_dim");
+  qx::StepArgs a{};
+  a.state = h->state; a.mask = mask_dev; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
+  a.stats = h->stats; a.n = h->n; a.k = 1;
+  return launch(h, true, a, (cudaStream_t)stream);
+}
+
+extern "C" int qx_step_k(QxHandle* h, int32_t k, const float* actions_dev, float* obs_dev, float* reward_dev,
+                         uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream) {
+  if (!h || k <= 0 || !actions_dev || !reward_dev || !terminated_dev || !truncated_dev)
+    return fail(QX_EINVAL, "qx_step_k: bad arguments");
+  qx::StepArgs a{};
+  a.state = h->state; a.actions = actions_dev; a.obs = obs_dev; a.obs_stride = h->dev.obs_dim; a.reward = reward_dev;
+  a.terminated = terminated_dev; a.truncated = truncated_dev; a.stats = h->stats; a.n = h->n; a.k = k;
+  return launch(h, false, a, (cudaStream_t)stream);
+}
+
+extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
+                       float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
+  if (!h || !actions_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(QX_EINVAL, "qx_step: bad arguments");
+  if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step: obs_stride < obs_dim");
+  qx::StepArgs a{};
+  a.state = h->state; a.actions = actions_dev; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
+  a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev; a.terminal_obs = terminal_obs_dev;
+  a.stats = h->stats; a.n = h->n; a.k = 1;
+  return launch(h, false, a, (cudaStream_t)stream);
+}
+
+static int ensure_staging(QxHandle* h) {
+  if (h->staging) return QX_OK;
+  const int64_t n = h->n;
+  const int od = h->dev.obs_dim, ad = h->dev.act_dim;
+  QX_CUDA(cudaMallocHost(&h->h_act, sizeof(float) * n * ad)); QX_CUDA(cudaMalloc(&h->d_act, sizeof(float) * n * ad));
+  QX_CUDA(cudaMallocHost(&h->h_obs, sizeof(float) * n * od)); QX_CUDA(cudaMalloc(&h->d_obs, sizeof(float) * n * od));
+  QX_CUDA(cudaMallocHost(&h->h_rew, sizeof(float) * n)); QX_CUDA(cudaMalloc(&h->d_rew, sizeof(float) * n));
+  QX_CUDA(cudaMallocHost(&h->h_flags, 3 * n)); QX_CUDA(cudaMalloc(&h->d_flags, 3 * n));
+  QX_CUDA(cudaMallocHost(&h->h_tobs, sizeof(float) * n * od)); QX_CUDA(cudaMalloc(&h->d_tobs, sizeof(float) * n * od));
+  h->staging = true;
+  return QX_OK;
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+extern "C" int qx_reset_host(QxHandle* h, const uint8_t* mask_host, float* obs_host) {
+  if (!h) return fail(QX_EINVAL, "qx_reset_host: null handle");
+  DeviceGuard g(h->device);
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const int64_t n = h->n;
+  const int od = h->dev.obs_dim;
+  uint8_t* dmask = nullptr;
+  if (mask_host) {
+    memcpy(h->h_flags + 2 * n, mask_host, n);
+    QX_CUDA(cudaMemcpyAsync(h->d_flags + 2 * n, h->h_flags + 2 * n, n, cudaMemcpyHostToDevice, h->stream));
+    dmask = h->d_flags + 2 * n;
+  }
+  rc = qx_reset(h, dmask, h->d_obs, QX_OBS_F32, od, h->stream);
+  if (rc) return rc;
+  if (obs_host) QX_CUDA(cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->stream));
+  QX_CUDA(cudaStreamSynchronize(h->stream));
+  if (obs_host) {
+    if (!mask_host) memcpy(obs_host, h->h_obs, sizeof(float) * n * od);
+    else
+      for (int64_t i = 0; i < n; ++i)
+        if (mask_host[i]) memcpy(obs_host + i * od, h->h_obs + i * od, sizeof(float) * od);
+  }
+  return QX_OK;
+}
+
+static bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Pinned caller buffers are used in place (one DMA each way); pageable ones go
+// through the handle's pinned staging area.
+extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
+                            uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
+  if (!h || !actions_host) return fail(QX_EINVAL, "qx_step_host: bad arguments");
+  DeviceGuard g(h->device);
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  const int64_t n = h->n;
+  const int od = h->dev.obs_dim, ad = h->dev.act_dim;
+  const float* src = actions_host;
+  if (!is_pinned(actions_host)) { memcpy(h->h_act, actions_host, sizeof(float) * n * ad); src = h->h_act; }
+  QX_CUDA(cudaMemcpyAsync(h->d_act, src, sizeof(float) * n * ad, cudaMemcpyHostToDevice, h->stream));
+  rc = qx_step(h, h->d_act, h->d_obs, QX_OBS_F32, od, h->d_rew, h->d_flags, h->d_flags + n,
+               terminal_obs_host ? h->d_tobs : nullptr, h->stream);
+  if (rc) return rc;
+  const bool p_obs = is_pinned(obs_host), p_rew = is_pinned(reward_host), p_te = is_pinned(terminated_host),
+             p_tr = is_pinned(truncated_host);
+  if (obs_host) QX_CUDA(cudaMemcpyAsync(p_obs ? obs_host : h->h_obs, h->d_obs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->stream));
+  if (reward_host) QX_CUDA(cudaMemcpyAsync(p_rew ? reward_host : h->h_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  QX_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * n, cudaMemcpyDeviceToHost, h->stream));
+  if (p_te) QX_CUDA(cudaMemcpyAsync(terminated_host, h->d_flags, n, cudaMemcpyDeviceToHost, h->stream));
+  if (p_tr) QX_CUDA(cudaMemcpyAsync(truncated_host, h->d_flags + n, n, cudaMemcpyDeviceToHost, h->stream));
+  if (terminal_obs_host) QX_CUDA(cudaMemcpyAsync(h->h_tobs, h->d_tobs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->stream));
+  QX_CUDA(cudaStreamSynchronize(h->stream));
+  if (obs_host && !p_obs) memcpy(obs_host, h->h_obs, sizeof(float) * n * od);
+  if (reward_host && !p_rew) memcpy(reward_host, h->h_rew, sizeof(float) * n);
+  if (terminated_host && !p_te) memcpy(terminated_host, h->h_flags, n);
+  if (truncated_host && !p_tr) memcpy(truncated_host, h->h_flags + n, n);
+  if (terminal_obs_host) {
+    for (int64_t i = 0; i < n; ++i)
+      if (h->h_flags[i] || h->h_flags[n + i]) memcpy(terminal_obs_host + i * od, h->h_tobs + i * od, sizeof(float) * od);
+  }
+  return QX_OK;
+}
+
+extern "C" int qx_get_state(QxHandle* h, void* planes_host) {
+  if (!h || !planes_host) return fail(QX_EINVAL, "qx_get_state: bad arguments");
+  DeviceGuard g(h->device);
+  // device layout: 11 planes of n float4; host layout: 44 planes of n words
+  const int64_t n = h->n;
+  float4* tmp = (float4*)malloc(sizeof(float4) * 11 * n);
+  if (!tmp) return fail(QX_ENOMEM, "qx_get_state: out of host memory");
+  cudaError_t e = cudaMemcpy(tmp, h->state, sizeof(float4) * 11 * n, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(tmp); return fail(QX_ECUDA, "qx_get_state: %s", cudaGetErrorString(e)); }
+  float* out = (float*)planes_host;
+  for (int p = 0; p < 11; ++p)
+    for (int64_t i = 0; i < n; ++i) {
+      const float4 v = tmp[p * n + i];
+      out[(4 * p + 0) * n + i] = v.x; out[(4 * p + 1) * n + i] = v.y; out[(4 * p + 2) * n + i] = v.z; out[(4 * p + 3) * n + i] = v.w;
+    }
+  free(tmp);
+  return QX_OK;
+}
+
+extern "C" int qx_set_state(QxHandle* h, const void* planes_host) {
+  if (!h || !planes_host) return fail(QX_EINVAL, "qx_set_state: bad arguments");
+  DeviceGuard g(h->device);
+  const int64_t n = h->n;
+  float4* tmp = (float4*)malloc(sizeof(float4) * 11 * n);
+  if (!tmp) return fail(QX_ENOMEM, "qx_set_state: out of host memory");
+  const float* in = (const float*)planes_host;
+  for (int p = 0; p < 11; ++p)
+    for (int64_t i = 0; i < n; ++i)
+      tmp[p * n + i] = make_float4(in[(4 * p + 0) * n + i], in[(4 * p + 1) * n + i], in[(4 * p + 2) * n + i], in[(4 * p + 3) * n + i]);
+  cudaError_t e = cudaMemcpy(h->state, tmp, sizeof(float4) * 11 * n, cudaMemcpyHostToDevice);
+  free(tmp);
+  if (e != cudaSuccess) return fail(QX_ECUDA, "qx_set_state: %s", cudaGetErrorString(e));
+  return QX_OK;
+}
+
+extern "C" int qx_episode_stats(QxHandle* h, double* sum_return, int64_t* sum_length, int64_t* n_episodes, int32_t clear) {
+  if (!h) return fail(QX_EINVAL, "qx_episode_stats: null handle");
+  DeviceGuard g(h->device);
+  qx::Stats s;
+  QX_CUDA(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
+  if (clear) QX_CUDA(cudaMemset(h->stats, 0, sizeof(s)));
+  if (sum_return) *sum_return = s.sum_ret;
+  if (sum_length) *sum_length = (int64_t)s.sum_len;
+  if (n_episodes) *n_episodes = (int64_t)s.n_done;
+  return QX_OK;
+}

@@ -1,0 +1,384 @@
+// qx_model.cuh -- fp32 device model of one QuadX drone + the hover / yaw env layer.
+//
+// Everything here runs in registers of ONE thread per env.  What is computed
+// follows, step by step,
+//   * /root/reference/simulation/hover.py:224-358 (obs, reward, termination, step)
+//   * hover.py:72-113 (reset), yaw.py:57-149 (yaw task)
+//   * the PyFlyt 0.21.0 mode-0 QuadX model and pybullet's multibody integrator
+//     as restated in SURVEY.md section 9 (third-party, parity unpinned),
+//     parameterised by cf2x.yaml:1-19 and cf2x.urdf:10-68.
+// It is written from that description for this hardware, not translated from
+// the CPU oracle: single precision, MUFU intrinsics, no libm slow paths inside
+// the sub-step loop, Philox counters instead of a stateful generator.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qx {
+
+// ---------------------------------------------------------------------------
+// kernel-side constants, derived once on the host from QxConfig
+// ---------------------------------------------------------------------------
+struct DevConfig {
+  int32_t task, n_sub_step, n_sub_reset, ctrl_every, max_steps, floor_grace, render, auto_reset, noise,
+      state_stale, gyro, obs_dim, act_dim;
+  float h, lag_alpha, noise_ratio, thrust_k, pwm_idle;
+  float torque_k[4], mx[4], my[4], map[16];
+  float drag_c, drag_pqr, kp[3], kiT[3], kd_T[3], lim[3];
+  float inv_mass, g, I[3], invI[3], vmax, floor_z;
+  float cam_sd, cam_cd, inv_tan, res, half_res, inv_half_res, inv_res2, cam_near, cam_off[3], margin, panel[12];
+  float inv_agent_dt, dome2, floor_thr, target_area, target_ratio, act_scale[3];
+  float start_pos[3], start_rpy[3], spawn_thr, spawn_pos_noise, spawn_yaw_noise;
+  uint32_t seed_lo, seed_hi, env_lo, env_hi;  // env id of local env 0
+};
+
+enum : uint32_t {
+  F_CONTACT = 1u,
+  F_TERM = 2u,
+  F_TRUNC = 4u,
+  F_OOB = 8u,
+  F_ONFLOOR = 16u,
+  F_LOWZ = 32u,
+};
+enum : uint32_t { STREAM_STEP = 0, STREAM_RESET = 1, STREAM_SPAWN = 2 };
+
+// The 44 carried words of one env (QX_STATE_WORDS); plane p, lane l = word 4p+l.
+struct Env {
+  float px, py, pz;           // world position
+  float qx, qy, qz, qw;       // body->world quaternion (x,y,z,w)
+  float vx, vy, vz;           // world linear velocity
+  float wx, wy, wz;           // world angular velocity
+  float thr[4];               // motor throttle (PyFlyt Motors.throttle)
+  float pi[3], pe[3];         // rate PID integral, previous error
+  float swb[3], svb[3];       // Aviary.state rows 0 and 2 (body rates / velocity snapshot)
+  float peul[3];              // previous_ang_pos, hover.py:354
+  float pa[4];                // prev_action, hover.py:357
+  float pcx, pcy, parea, pratio;  // hover.py:270-272
+  int32_t step_count;         // hover.py:356
+  uint32_t rng_ctr;           // env steps since creation (Philox counter word 2)
+  float ep_ret;               // Monitor: running episode return
+  uint32_t flags;
+  // transient (not stored): pose part of the Aviary.state snapshot
+  float sqx, sqy, sqz, sqw, spx, spy, spz;
+};
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void load_env(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  float4 a = ldg4(st + 0 * n + i), b = ldg4(st + 1 * n + i), c = ldg4(st + 2 * n + i), d = ldg4(st + 3 * n + i);
+  float4 f = ldg4(st + 4 * n + i), g = ldg4(st + 5 * n + i), h = ldg4(st + 6 * n + i), k = ldg4(st + 7 * n + i);
+  float4 l = ldg4(st + 8 * n + i), m = ldg4(st + 9 * n + i), o = ldg4(st + 10 * n + i);
+  e.px = a.x; e.py = a.y; e.pz = a.z; e.qx = a.w;
+  e.qy = b.x; e.qz = b.y; e.qw = b.z; e.vx = b.w;
+  e.vy = c.x; e.vz = c.y; e.wx = c.z; e.wy = c.w;
+  e.wz = d.x; e.thr[0] = d.y; e.thr[1] = d.z; e.thr[2] = d.w;
+  e.thr[3] = f.x; e.pi[0] = f.y; e.pi[1] = f.z; e.pi[2] = f.w;
+  e.pe[0] = g.x; e.pe[1] = g.y; e.pe[2] = g.z; e.swb[0] = g.w;
+  e.swb[1] = h.x; e.swb[2] = h.y; e.svb[0] = h.z; e.svb[1] = h.w;
+  e.svb[2] = k.x; e.peul[0] = k.y; e.peul[1] = k.z; e.peul[2] = k.w;
+  e.pa[0] = l.x; e.pa[1] = l.y; e.pa[2] = l.z; e.pa[3] = l.w;
+  e.pcx = m.x; e.pcy = m.y; e.parea = m.z; e.pratio = m.w;
+  e.step_count = __float_as_int(o.x); e.rng_ctr = __float_as_uint(o.y); e.ep_ret = o.z; e.flags = __float_as_uint(o.w);
+  e.sqx = e.qx; e.sqy = e.qy; e.sqz = e.qz; e.sqw = e.qw; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
+}
+
+__device__ __forceinline__ void store_env(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
+  st[0 * n + i] = make_float4(e.px, e.py, e.pz, e.qx);
+  st[1 * n + i] = make_float4(e.qy, e.qz, e.qw, e.vx);
+  st[2 * n + i] = make_float4(e.vy, e.vz, e.wx, e.wy);
+  st[3 * n + i] = make_float4(e.wz, e.thr[0], e.thr[1], e.thr[2]);
+  st[4 * n + i] = make_float4(e.thr[3], e.pi[0], e.pi[1], e.pi[2]);
+  st[5 * n + i] = make_float4(e.pe[0], e.pe[1], e.pe[2], e.swb[0]);
+  st[6 * n + i] = make_float4(e.swb[1], e.swb[2], e.svb[0], e.svb[1]);
+  st[7 * n + i] = make_float4(e.svb[2], e.peul[0], e.peul[1], e.peul[2]);
+  st[8 * n + i] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
+  st[9 * n + i] = make_float4(e.pcx, e.pcy, e.parea, e.pratio);
+  st[10 * n + i] = make_float4(__int_as_float(e.step_count), __uint_as_float(e.rng_ctr), e.ep_ret, __uint_as_float(e.flags));
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10: same integer stream as oracle/quadx_model.py:philox4x32_10
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// ((x >> 9) + 0.5) * 2^-23 without an int->float conversion
+__device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
+
+// 4 x N(0,1): two Box-Muller pairs (cos, sin, cos, sin) like oracle normal4()
+__device__ __forceinline__ void normal4(uint4 b, float n[4]) {
+  const float ra = sqrtf(-2.0f * __logf(u01(b.x)));
+  const float rb = sqrtf(-2.0f * __logf(u01(b.z)));
+  float sa, ca, sb, cb;
+  // 2*pi*u in (0, 2pi): within the accurate range of the MUFU sin/cos
+  __sincosf(6.28318530718f * u01(b.y) - 3.14159265359f, &sa, &ca);
+  __sincosf(6.28318530718f * u01(b.w) - 3.14159265359f, &sb, &cb);
+  // shifted by -pi to centre the argument: sin(t-pi) = -sin t, cos(t-pi) = -cos t
+  n[0] = -ra * ca; n[1] = -ra * sa; n[2] = -rb * cb; n[3] = -rb * sb;
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ---------------------------------------------------------------------------
+// PyFlyt QuadX.update_control, mode 0: rate PID -> motor mix -> saturation
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const float sp[4], float pwm[4]) {
+  float cmd[4];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float err = sp[a] - e.swb[a];
+    e.pi[a] = clampf(fmaf(c.kiT[a], err, e.pi[a]), -c.lim[a], c.lim[a]);
+    const float d = c.kd_T[a] * (err - e.pe[a]);
+    cmd[a] = clampf(fmaf(c.kp[a], err, e.pi[a]) + d, -c.lim[a], c.lim[a]);
+    e.pe[a] = err;
+  }
+  cmd[3] = sp[3];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    pwm[m] = c.map[4 * m + 0] * cmd[0] + c.map[4 * m + 1] * cmd[1] + c.map[4 * m + 2] * cmd[2] + c.map[4 * m + 3] * cmd[3];
+  const float high = fmaxf(fmaxf(pwm[0], pwm[1]), fmaxf(pwm[2], pwm[3]));
+  if (high > 1.0f) {
+    const float inv = __frcp_rn(high);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pwm[m] *= inv;
+  }
+  const float low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
+  if (low < c.pwm_idle) {
+    const float k = (c.pwm_idle - low) * __frcp_rn(1.0f - low);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pwm[m] = fmaf(1.0f - pwm[m], k, pwm[m]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one 1/physics_hz sub-step: Motors.physics_update + drag + update_state +
+// pybullet.stepSimulation (free flight) + the declared floor stand-in
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float pwm[4], uint32_t sub,
+                                                uint32_t stream, uint32_t k0, uint32_t k1) {
+  // motors: first-order lag, multiplicative noise
+  float nz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c.noise) normal4(philox4x32_10(make_uint4(sub, stream, e.rng_ctr, 0u), k0, k1), nz);
+  float fz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    float t = fmaf(c.lag_alpha, pwm[m] - e.thr[m], e.thr[m]);
+    t = fmaf(nz[m] * c.noise_ratio, t, t);
+    e.thr[m] = t;
+    const float rr = fabsf(t) * t;        // rpm |rpm| / max_rpm^2
+    const float f = c.thrust_k * rr;      // kf rpm^2
+    fz += f;
+    tx = fmaf(c.my[m], f, tx);            // r x F = (y F, -x F, 0)
+    ty = fmaf(-c.mx[m], f, ty);
+    tz = fmaf(c.torque_k[m], rr, tz);
+  }
+  // drag from the (stale) snapshot, body frame
+  const float fbx = -c.drag_c * fabsf(e.svb[0]) * e.svb[0];
+  const float fby = -c.drag_c * fabsf(e.svb[1]) * e.svb[1];
+  const float fbz = fz - c.drag_c * fabsf(e.svb[2]) * e.svb[2];
+  if (!(e.flags & F_CONTACT)) {
+    tx -= c.drag_pqr * fabsf(e.swb[0]) * e.swb[0];
+    ty -= c.drag_pqr * fabsf(e.swb[1]) * e.swb[1];
+    tz -= c.drag_pqr * fabsf(e.swb[2]) * e.swb[2];
+  }
+  // rotation matrix of the current attitude
+  const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
+  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
+  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
+  // body-frame velocities of the current state
+  const float wbx = r00 * e.wx + r10 * e.wy + r20 * e.wz;
+  const float wby = r01 * e.wx + r11 * e.wy + r21 * e.wz;
+  const float wbz = r02 * e.wx + r12 * e.wy + r22 * e.wz;
+  if (c.state_stale) {  // QuadX.update_state runs before stepSimulation
+    e.swb[0] = wbx; e.swb[1] = wby; e.swb[2] = wbz;
+    e.svb[0] = r00 * e.vx + r10 * e.vy + r20 * e.vz;
+    e.svb[1] = r01 * e.vx + r11 * e.vy + r21 * e.vz;
+    e.svb[2] = r02 * e.vx + r12 * e.vy + r22 * e.vz;
+    e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
+  }
+  // semi-implicit Euler on the floating base
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (c.gyro) {
+    const float lx = c.I[0] * wbx, ly = c.I[1] * wby, lz = c.I[2] * wbz;
+    gx = wby * lz - wbz * ly; gy = wbz * lx - wbx * lz; gz = wbx * ly - wby * lx;
+  }
+  const float ax = (tx - gx) * c.invI[0], ay = (ty - gy) * c.invI[1], az = (tz - gz) * c.invI[2];
+  e.wx = clampf(fmaf(c.h, r00 * ax + r01 * ay + r02 * az, e.wx), -c.vmax, c.vmax);
+  e.wy = clampf(fmaf(c.h, r10 * ax + r11 * ay + r12 * az, e.wy), -c.vmax, c.vmax);
+  e.wz = clampf(fmaf(c.h, r20 * ax + r21 * ay + r22 * az, e.wz), -c.vmax, c.vmax);
+  const float hm = c.h * c.inv_mass;
+  e.vx = clampf(fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx), -c.vmax, c.vmax);
+  e.vy = clampf(fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy), -c.vmax, c.vmax);
+  e.vz = clampf(fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.h * c.g, -c.vmax, c.vmax);
+  e.px = fmaf(c.h, e.vx, e.px);
+  e.py = fmaf(c.h, e.vy, e.py);
+  e.pz = fmaf(c.h, e.vz, e.pz);
+  // q <- exp(h w / 2) q, series in s = |w|^2 (no sqrt / sin / cos), then renormalise
+  const float hh = 0.5f * c.h;
+  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * hh * hh;  // (theta/2)^2
+  const float kq = hh * (1.f + s * (-1.f / 6.f + s * (1.f / 120.f + s * (-1.f / 5040.f))));
+  const float dw = 1.f + s * (-0.5f + s * (1.f / 24.f + s * (-1.f / 720.f + s * (1.f / 40320.f))));
+  const float dx = e.wx * kq, dy = e.wy * kq, dz = e.wz * kq;
+  const float nx = dw * x + dx * w + dy * z - dz * y;
+  const float ny = dw * y - dx * z + dy * w + dz * x;
+  const float nzq = dw * z + dx * y - dy * x + dz * w;
+  const float nw = dw * w - dx * x - dy * y - dz * z;
+  const float inv = rsqrtf(nx * nx + ny * ny + nzq * nzq + nw * nw);
+  e.qx = nx * inv; e.qy = ny * inv; e.qz = nzq * inv; e.qw = nw * inv;
+  // floor stand-in: sticky plane at floor_z
+  if (e.pz < c.floor_z) {
+    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vx = 0.f; e.vy = 0.f; e.wx = 0.f; e.wy = 0.f;
+    e.flags |= F_CONTACT;
+  } else {
+    e.flags &= ~F_CONTACT;
+  }
+  if (!c.state_stale) {
+    const float X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
+    const float a00 = 1.f - 2.f * (Y * Y + Z * Z), a01 = 2.f * (X * Y - W * Z), a02 = 2.f * (X * Z + W * Y);
+    const float a10 = 2.f * (X * Y + W * Z), a11 = 1.f - 2.f * (X * X + Z * Z), a12 = 2.f * (Y * Z - W * X);
+    const float a20 = 2.f * (X * Z - W * Y), a21 = 2.f * (Y * Z + W * X), a22 = 1.f - 2.f * (X * X + Y * Y);
+    e.swb[0] = a00 * e.wx + a10 * e.wy + a20 * e.wz;
+    e.swb[1] = a01 * e.wx + a11 * e.wy + a21 * e.wz;
+    e.swb[2] = a02 * e.wx + a12 * e.wy + a22 * e.wz;
+    e.svb[0] = a00 * e.vx + a10 * e.vy + a20 * e.vz;
+    e.svb[1] = a01 * e.vx + a11 * e.vy + a21 * e.vz;
+    e.svb[2] = a02 * e.vx + a12 * e.vy + a22 * e.vz;
+    e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
+  }
+}
+
+// pybullet.getEulerFromQuaternion (ZYX, with its gimbal guard)
+__device__ __forceinline__ void quat_to_euler(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
+  const float sarg = -2.f * (x * z - w * y);
+  if (sarg <= -0.99999f) {
+    roll = 0.f; pitch = -1.57079632679f; yaw = 2.f * atan2f(x, -y);
+  } else if (sarg >= 0.99999f) {
+    roll = 0.f; pitch = 1.57079632679f; yaw = 2.f * atan2f(-x, y);
+  } else {
+    roll = atan2f(2.f * (y * z + w * x), w * w - x * x - y * y + z * z);
+    pitch = asinf(sarg);
+    yaw = atan2f(2.f * (x * y + w * z), w * w + x * x - y * y - z * z);
+  }
+}
+
+// pybullet.getQuaternionFromEuler, hover.py:233
+__device__ __forceinline__ void euler_to_quat(float roll, float pitch, float yaw, float& x, float& y, float& z, float& w) {
+  float sr, cr, sp, cp, sy, cy;
+  __sincosf(0.5f * roll, &sr, &cr);
+  __sincosf(0.5f * pitch, &sp, &cp);
+  __sincosf(0.5f * yaw, &sy, &cy);
+  x = sr * cp * cy - cr * sp * sy;
+  y = cr * sp * cy + sr * cp * sy;
+  z = cr * cp * sy - sr * sp * cy;
+  w = cr * cp * cy + sr * sp * sy;
+}
+
+// ---------------------------------------------------------------------------
+// Camera: analytic stand-in for Camera.capture_image + detect_rectangle
+// (hover.py:157-222, 241-248).  The four corners of the red face are projected
+// through the PyFlyt FPV camera (body Euler angles with the pitch offset by the
+// tilt; FOV 90, 128x128) and the features are taken on the pixel lattice the
+// way cv2.findContours / contourArea / boundingRect would report them.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& vis, float& cx, float& cy, float& area,
+                                       float& ratio) {
+  const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
+  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
+  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
+  // sin / cos of the roll Euler angle = (r21, r22) / cos(pitch)
+  float sph = 0.f, cph = 1.f;
+  if (fabsf(r20) < 0.99999f) {
+    const float inv = rsqrtf(r21 * r21 + r22 * r22);
+    sph = r21 * inv; cph = r22 * inv;
+  }
+  // camera axes in the body frame: Rx(-roll) Ry(-tilt) Rx(roll) applied to x, z
+  const float sd = c.cam_sd, cd = c.cam_cd;
+  const float fx = cd, fy = sd * sph, fzz = sd * cph;
+  const float ux = -sd * cph, uy = sph * cph * (cd - 1.f), uz = fmaf(sph, sph, cd * cph * cph);
+  // right = fwd x up
+  const float rx = fy * uz - fzz * uy, ry = fzz * ux - fx * uz, rz = fx * uy - fy * ux;
+  float pxs[4], pys[4];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float dx = c.panel[3 * k + 0] - e.px, dy = c.panel[3 * k + 1] - e.py, dz = c.panel[3 * k + 2] - e.pz;
+    const float bx = r00 * dx + r10 * dy + r20 * dz - c.cam_off[0];
+    const float by = r01 * dx + r11 * dy + r21 * dz - c.cam_off[1];
+    const float bz = r02 * dx + r12 * dy + r22 * dz - c.cam_off[2];
+    const float depth = fx * bx + fy * by + fzz * bz;
+    ok = ok && (depth > c.cam_near);
+    const float k1 = c.inv_tan * __frcp_rn(fmaxf(depth, 1e-9f));
+    pxs[k] = fmaf((rx * bx + ry * by + rz * bz) * k1, c.half_res, c.half_res);
+    pys[k] = fmaf(-(ux * bx + uy * by + uz * bz) * k1, c.half_res, c.half_res);
+  }
+  const float xmin = fminf(fminf(pxs[0], pxs[1]), fminf(pxs[2], pxs[3]));
+  const float xmax = fmaxf(fmaxf(pxs[0], pxs[1]), fmaxf(pxs[2], pxs[3]));
+  const float ymin = fminf(fminf(pys[0], pys[1]), fminf(pys[2], pys[3]));
+  const float ymax = fmaxf(fmaxf(pys[0], pys[1]), fmaxf(pys[2], pys[3]));
+  ok = ok && xmin >= c.margin && ymin >= c.margin && xmax <= c.res - c.margin && ymax <= c.res - c.margin;
+  float a2 = 0.f, per = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int kn = (k + 1) & 3;
+    a2 += pxs[k] * pys[kn] - pxs[kn] * pys[k];
+    const float ex = pxs[kn] - pxs[k], ey = pys[kn] - pys[k];
+    per += sqrtf(ex * ex + ey * ey);
+  }
+  const float wpx = floorf(xmax - 0.5f) - ceilf(xmin - 0.5f) + 1.f;
+  const float hpx = floorf(ymax - 0.5f) - ceilf(ymin - 0.5f) + 1.f;
+  ok = ok && wpx >= 2.f && hpx >= 2.f;
+  vis = ok;
+  cx = ok ? fmaf(0.25f * (pxs[0] + pxs[1] + pxs[2] + pxs[3]) - 0.5f, c.inv_half_res, -1.f) : 0.f;
+  cy = ok ? fmaf(0.25f * (pys[0] + pys[1] + pys[2] + pys[3]) - 0.5f, c.inv_half_res, -1.f) : 0.f;
+  area = ok ? fmaxf(0.5f * fabsf(a2) - 0.5f * per + 1.f, 0.f) * c.inv_res2 : 0.f;
+  ratio = ok ? __fdividef(wpx, hpx) : 0.f;
+}
+
+// Aviary(start_pos, start_orn) + Aviary.reset() + the env bookkeeping of
+// hover.py:98-107.  prev_action is deliberately left alone (hover.py:31,357).
+__device__ __forceinline__ void respawn(Env& e, const DevConfig& c, uint32_t k0, uint32_t k1) {
+  float px = c.start_pos[0], py = c.start_pos[1], pz = c.start_pos[2], yaw = c.start_rpy[2];
+  if (c.spawn_pos_noise != 0.f || c.spawn_yaw_noise != 0.f) {
+    const uint4 b = philox4x32_10(make_uint4(0u, STREAM_SPAWN, e.rng_ctr, 0u), k0, k1);
+    px = fmaf(c.spawn_pos_noise, 2.f * u01(b.x) - 1.f, px);
+    py = fmaf(c.spawn_pos_noise, 2.f * u01(b.y) - 1.f, py);
+    pz = fmaf(c.spawn_pos_noise, 2.f * u01(b.z) - 1.f, pz);
+    yaw = fmaf(c.spawn_yaw_noise, 2.f * u01(b.w) - 1.f, yaw);
+  }
+  pz = fmaxf(pz, c.floor_z);
+  e.px = px; e.py = py; e.pz = pz;
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(0.5f * c.start_rpy[0], &sr, &cr);
+  sincosf(0.5f * c.start_rpy[1], &sp, &cp);
+  sincosf(0.5f * yaw, &sy, &cy);
+  e.qx = sr * cp * cy - cr * sp * sy;
+  e.qy = cr * sp * cy + sr * cp * sy;
+  e.qz = cr * cp * sy - sr * sp * cy;
+  e.qw = cr * cp * cy + sr * sp * sy;
+  e.vx = e.vy = e.vz = 0.f;
+  e.wx = e.wy = e.wz = 0.f;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) e.thr[m] = c.spawn_thr;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { e.pi[a] = 0.f; e.pe[a] = 0.f; e.swb[a] = 0.f; e.svb[a] = 0.f; }
+  e.sqx = e.qx; e.sqy = e.qy; e.sqz = e.qz; e.sqw = e.qw; e.spx = px; e.spy = py; e.spz = pz;
+  e.flags = (pz <= c.floor_z) ? F_CONTACT : 0u;
+  e.step_count = 0;
+  e.pcx = e.pcy = e.parea = e.pratio = 0.f;
+  e.ep_ret = 0.f;
+}
+
+}  // namespace qx

@@ -146,8 +146,9 @@ def rng_key(seed: int, env_ids: np.ndarray) -> np.ndarray:
 
 
 def u01(x: np.ndarray) -> np.ndarray:
-    """uint32 -> (0,1): ((x >> 8) + 0.5) * 2^-24 -- exact in fp32 and fp64."""
-    return ((x >> np.uint32(8)).astype(np.float64) + 0.5) * (1.0 / 16777216.0)
+    """uint32 -> (0,1): ((x >> 9) + 0.5) * 2^-23 -- exact in fp32 and fp64 (on
+    the GPU: bit-cast (x >> 9) | 0x3f800000 and subtract 1 - 2^-24, no I2F)."""
+    return ((x >> np.uint32(9)).astype(np.float64) + 0.5) * (1.0 / 8388608.0)
 
 
 def normal4(bits: np.ndarray) -> np.ndarray:

@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol that
+include/quadx_b200.h declares (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from fpv_drone_rl_agent_b200 import _lib
+
+    return _lib
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:qx|ppo)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    names = _declared("quadx_b200.h")
+    assert len(names) >= 15
+    L = ctypes.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/quadx_b200.h but not exported"
+    assert sorted(built.EXPORTED) == names
+
+
+def test_config_layout_and_defaults(built):
+    from oracle.hover_oracle import HoverConfig
+    from oracle.quadx_model import QuadXParams
+
+    L = built.lib()
+    assert L.qx_version() == 1
+    assert L.qx_sizeof_config() == ctypes.sizeof(built.QxConfig)
+    c = built.default_config(built.QX_TASK_HOVER)
+    p, h = QuadXParams(), HoverConfig()
+    f = lambda x: pytest.approx(x, rel=1e-6)  # noqa: E731
+    assert c.mass == f(p.mass) and list(c.inertia) == f(list(p.inertia))
+    assert list(c.motor_x) == f([m[0] for m in p.motor_xy]) and list(c.motor_y) == f([m[1] for m in p.motor_xy])
+    assert list(c.motor_map) == f([v for row in p.motor_map for v in row]) and list(c.torque_sign) == f(list(p.torque_sign))
+    assert c.total_thrust == f(p.total_thrust) and c.thrust_coef == f(p.thrust_coef) and c.torque_coef == f(p.torque_coef)
+    assert c.noise_ratio == f(p.noise_ratio) and c.tau == f(p.tau)
+    assert c.drag_coef_xyz == f(p.drag_coef_xyz) and c.drag_area_xyz == f(p.drag_area_xyz) and c.drag_coef_pqr == f(p.drag_coef_pqr)
+    assert list(c.rate_kp) == f(list(p.rate_kp)) and list(c.rate_ki) == f(list(p.rate_ki)) and list(c.rate_kd) == f(list(p.rate_kd))
+    assert c.physics_hz == p.physics_hz and c.control_hz == p.control_hz and c.gravity == f(p.gravity)
+    assert bool(c.state_stale) == p.state_stale and bool(c.gyro) == p.gyro and c.floor_z == f(p.floor_z)
+    assert c.cam_tilt_up_deg == p.cam_tilt_up_deg and c.cam_fov_deg == p.cam_fov_deg and c.cam_res == p.cam_res
+    from oracle import vision
+
+    assert list(c.panel) == f(list(vision.panel_front_face().ravel())) and c.vis_margin_px == vision.VIS_MARGIN_PX
+    assert c.aviary_steps_per_step == h.env_step_ratio and c.max_steps == h.max_steps and c.reset_idle_steps == h.reset_idle_steps
+    assert c.floor_grace_steps == h.floor_grace_steps and c.agent_dt == f(h.agent_dt)
+    assert c.flight_dome_size == h.flight_dome_size and c.floor_threshold == f(h.floor_threshold)
+    assert c.target_area == f(h.target_area) and c.target_ratio == f(h.target_ratio) and list(c.action_scale) == list(h.action_scale)
+
+
+def test_no_gpu_means_loud_failure(built):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fpv_drone_rl_agent_b200 import QuadXSim
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        QuadXSim(4)
+    # the raw C-ABI refuses too, with an error string
+    h = ctypes.c_void_p()
+    cfg = built.default_config()
+    rc = built.lib().qx_create(ctypes.byref(cfg), 4, 0, 0, 0, ctypes.byref(h))
+    assert rc < 0 and built.lib().qx_last_error()
