@@ -22,12 +22,29 @@
 
 namespace qx {
 
-constexpr int kBlock = 128;
+#ifndef QX_BLOCK
+#define QX_BLOCK 128
+#endif
+#ifndef QX_MIN_BLOCKS
+#define QX_MIN_BLOCKS 4
+#endif
+constexpr int kBlock = QX_BLOCK;
 
 struct Stats {
   double sum_ret;
   unsigned long long sum_len;
   unsigned long long n_done;
+};
+
+// Envs that finished in a step and must be re-created before the next one.
+// Filled by the step kernel, drained by the reset kernel launched right after
+// it on the same stream, so that reset work (20 idle sub-steps, hover.py:109)
+// runs in full warps instead of diverging inside the step kernel.
+struct ResetQueue {
+  unsigned int count;
+  unsigned int ticket;
+  unsigned int pad[2];
+  unsigned int idx[1];  // [n_envs]
 };
 
 struct StepArgs {
@@ -40,6 +57,7 @@ struct StepArgs {
   float* terminal_obs;      // [n, obs_dim] or null
   const uint8_t* mask;      // reset only
   Stats* stats;
+  ResetQueue* queue;        // deferred-reset mode (MODE_STEP_DEFER / MODE_RESET_QUEUE)
   int64_t n;
   int64_t obs_stride;
   int32_t k;
@@ -76,18 +94,47 @@ __device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int
   }
 }
 
-// RESET_ONLY: qx_reset (masked reset, no step).  Otherwise k agent steps.
-template <bool RESET_ONLY>
-__global__ void __launch_bounds__(kBlock) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= a.n) return;
-  if (RESET_ONLY && a.mask && !a.mask[i]) return;
+// MODE_STEP_INLINE : k agent steps, finished envs reset inside the same thread (qx_step_k)
+// MODE_STEP_DEFER  : one agent step, finished envs are queued for MODE_RESET_QUEUE (qx_step)
+// MODE_RESET_MASK  : qx_reset (masked reset, no step)
+// MODE_RESET_QUEUE : reset of the envs queued by the preceding MODE_STEP_DEFER launch
+enum { MODE_STEP_INLINE = 0, MODE_STEP_DEFER = 1, MODE_RESET_MASK = 2, MODE_RESET_QUEUE = 3 };
+
+template <int MODE>
+__device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, int64_t i);
+
+constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
+  if (MODE == MODE_RESET_QUEUE) {
+    // Every block reads the count before any block can zero it: the zeroing
+    // block is the last one to take a ticket, after its own __syncthreads.
+    const unsigned int cnt = *reinterpret_cast<volatile unsigned int*>(&a.queue->count);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&a.queue->ticket, 1u) == gridDim.x - 1) { a.queue->count = 0u; a.queue->ticket = 0u; }
+    }
+    for (unsigned int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock)
+      run_env<MODE>(c, a, (int64_t)a.queue->idx[t]);
+  } else {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.n) return;
+    if (MODE == MODE_RESET_MASK && a.mask && !a.mask[i]) return;
+    run_env<MODE>(c, a, i);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
+  constexpr bool RESET_ONLY = MODE == MODE_RESET_MASK || MODE == MODE_RESET_QUEUE;
   Env e;
   load_env(e, a.state, a.n, i);
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
   const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i) >> 32));
 
-  for (int kk = 0; kk < (RESET_ONLY ? 1 : a.k); ++kk) {
+  for (int kk = 0; kk < ((RESET_ONLY || MODE == MODE_STEP_DEFER) ? 1 : a.k); ++kk) {
     const int64_t row = (int64_t)kk * a.n + i;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     float sp[4] = {0.f, 0.f, 0.f, 0.f};
@@ -112,15 +159,24 @@ __global__ void __launch_bounds__(kBlock) quadx_step_kernel(const __grid_constan
     }
     const bool live = RESET_ONLY || nsub > 0 || c.n_sub_step == 0;
     float obs[QX_OBS_DIM_HOVER];
+    bool deferred = false;
 
     while (true) {
       // ---- Aviary.step() x ratio: control on every ctrl_every-th sub-step
       float pwm[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t stream = phase ? STREAM_RESET : STREAM_STEP;
+      uint4 bits = make_uint4(0u, 0u, 0u, 0u);
       for (int j = 0, cc = 0; j < nsub; ++j) {
         if (cc == 0) control_update(e, c, sp, pwm);
         if (++cc == c.ctrl_every) cc = 0;
-        physics_substep(e, c, pwm, (uint32_t)j, stream, k0, k1);
+        float nz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c.noise) {  // one Philox4x32-10 call feeds two sub-steps
+          if ((j & 1) == 0) bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
+          normal4((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, nz);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) nz[m] *= c.noise_ratio;
+        }
+        physics_substep(e, c, pwm, nz);
       }
       // ---- compute_attitude / compute_state, hover.py:224-272
       float er, ep, ey;
@@ -162,11 +218,11 @@ __global__ void __launch_bounds__(kBlock) quadx_step_kernel(const __grid_constan
         reward = -100.f; fl |= F_TERM | F_ONFLOOR;
       }
       const float target_reward =
-          vis ? -(sqrtf(cx * cx + cy * cy) + fabsf(area - c.target_area) + fabsf(ratio - c.target_ratio)) : -2.0f;
+          vis ? -(fsqrt(cx * cx + cy * cy) + fabsf(area - c.target_area) + fabsf(ratio - c.target_ratio)) : -2.0f;
       reward -= 0.01f * e.swb[2] * e.swb[2];                        // hover.py:322-324
-      reward += target_reward - sqrtf(er * er + ep * ep);          // hover.py:326-327
+      reward += target_reward - fsqrt(er * er + ep * ep);          // hover.py:326-327
       const float a0 = act[0] - e.pa[0], a1 = act[1] - e.pa[1], a2 = act[2] - e.pa[2], a3 = act[3] - e.pa[3];
-      reward -= 0.2f * sqrtf(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
+      reward -= 0.2f * fsqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
       reward += 1.0f;                                               // hover.py:332
       e.flags = fl;
       e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;  // hover.py:354
@@ -184,13 +240,18 @@ __global__ void __launch_bounds__(kBlock) quadx_step_kernel(const __grid_constan
       atomicAdd(&a.stats->sum_len, (unsigned long long)e.step_count);
       atomicAdd(&a.stats->n_done, 1ull);
       if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, QX_OBS_DIM_HOVER, false);
+      if (MODE == MODE_STEP_DEFER) {  // hand the env to the reset kernel; it writes the next obs
+        a.queue->idx[atomicAdd(&a.queue->count, 1u)] = (unsigned int)i;
+        deferred = true;
+        break;
+      }
       respawn(e, c, k0, k1);
       act[0] = act[1] = act[2] = act[3] = 0.f;  // hover.py:101
       sp[0] = sp[1] = sp[2] = sp[3] = 0.f;      // set_mode(0): zero setpoint
       phase = 1;
       nsub = c.n_sub_reset;
     }
-    if (a.obs) write_obs(obs, a.obs, row, a.obs_stride, a.obs_bf16 != 0);
+    if (a.obs && !deferred) write_obs(obs, a.obs, RESET_ONLY ? i : row, a.obs_stride, a.obs_bf16 != 0);
   }
   store_env(e, a.state, a.n, i);
 }
@@ -207,6 +268,7 @@ struct QxHandle {
   int device;
   float4* state;
   qx::Stats* stats;
+  qx::ResetQueue* queue;
   // staging for the *_host calls
   cudaStream_t stream;
   float* h_act; float* d_act;
@@ -328,12 +390,14 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   cudaSetDevice(device);
   cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * 11 * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
+  if (e == cudaSuccess) e = cudaMalloc(&h->queue, sizeof(qx::ResetQueue) + sizeof(unsigned int) * n_envs);
+  if (e == cudaSuccess) e = cudaMemset(h->queue, 0, sizeof(qx::ResetQueue));
   if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * 11 * n_envs);
   if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
-    cudaFree(h->state); cudaFree(h->stats); delete h;
+    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue); delete h;
     return fail(QX_ECUDA, "qx_create: %s", cudaGetErrorString(e));
   }
   *out = h;
@@ -345,7 +409,7 @@ extern "C" int qx_destroy(QxHandle* h) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->stats);
+  cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue);
   if (h->staging) {
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_tobs);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_flags); cudaFree(h->d_tobs);
@@ -361,12 +425,18 @@ extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0
 extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
 extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
 
-static int launch(QxHandle* h, bool reset_only, const qx::StepArgs& a, cudaStream_t s) {
+static int launch(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((h->n + qx::kBlock - 1) / qx::kBlock);
-  if (reset_only)
-    qx::quadx_step_kernel<true><<<grid, qx::kBlock, 0, s>>>(h->dev, a);
-  else
-    qx::quadx_step_kernel<false><<<grid, qx::kBlock, 0, s>>>(h->dev, a);
+  switch (mode) {
+    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    default: {
+      const unsigned g = grid < (unsigned)qx::kResetQueueBlocks ? grid : (unsigned)qx::kResetQueueBlocks;
+      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE><<<g, qx::kBlock, 0, s>>>(h->dev, a);
+      break;
+    }
+  }
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;
@@ -378,7 +448,7 @@ extern "C" int qx_reset(QxHandle* h, const uint8_t* mask_dev, void* obs_dev, int
   qx::StepArgs a{};
   a.state = h->state; a.mask = mask_dev; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
   a.stats = h->stats; a.n = h->n; a.k = 1;
-  return launch(h, true, a, (cudaStream_t)stream);
+  return launch(h, qx::MODE_RESET_MASK, a, (cudaStream_t)stream);
 }
 
 extern "C" int qx_step_k(QxHandle* h, int32_t k, const float* actions_dev, float* obs_dev, float* reward_dev,
@@ -388,7 +458,7 @@ extern "C" int qx_step_k(QxHandle* h, int32_t k, const float* actions_dev, float
   qx::StepArgs a{};
   a.state = h->state; a.actions = actions_dev; a.obs = obs_dev; a.obs_stride = h->dev.obs_dim; a.reward = reward_dev;
   a.terminated = terminated_dev; a.truncated = truncated_dev; a.stats = h->stats; a.n = h->n; a.k = k;
-  return launch(h, false, a, (cudaStream_t)stream);
+  return launch(h, qx::MODE_STEP_INLINE, a, (cudaStream_t)stream);
 }
 
 extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
@@ -399,7 +469,12 @@ extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int
   a.state = h->state; a.actions = actions_dev; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
   a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev; a.terminal_obs = terminal_obs_dev;
   a.stats = h->stats; a.n = h->n; a.k = 1;
-  return launch(h, false, a, (cudaStream_t)stream);
+  if (!h->cfg.auto_reset) return launch(h, qx::MODE_STEP_INLINE, a, (cudaStream_t)stream);
+  // two launches: the step proper, then the reset of whatever finished, in full warps
+  a.queue = h->queue;
+  int rc = launch(h, qx::MODE_STEP_DEFER, a, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch(h, qx::MODE_RESET_QUEUE, a, (cudaStream_t)stream);
 }
 
 static int ensure_staging(QxHandle* h) {

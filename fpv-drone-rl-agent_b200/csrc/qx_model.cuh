@@ -47,7 +47,7 @@ struct Env {
   float px, py, pz;           // world position
   float qx, qy, qz, qw;       // body->world quaternion (x,y,z,w)
   float vx, vy, vz;           // world linear velocity
-  float wx, wy, wz;           // world angular velocity
+  float wx, wy, wz;           // BODY-frame angular velocity (see physics_substep)
   float thr[4];               // motor throttle (PyFlyt Motors.throttle)
   float pi[3], pe[3];         // rate PID integral, previous error
   float swb[3], svb[3];       // Aviary.state rows 0 and 2 (body rates / velocity snapshot)
@@ -111,19 +111,26 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
-// ((x >> 9) + 0.5) * 2^-23 without an int->float conversion
-__device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
+// MUFU-only approximations (1-2 ulp): no Newton refinement, no slow paths
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float frsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// 4 x N(0,1): two Box-Muller pairs (cos, sin, cos, sin) like oracle normal4()
-__device__ __forceinline__ void normal4(uint4 b, float n[4]) {
-  const float ra = sqrtf(-2.0f * __logf(u01(b.x)));
-  const float rb = sqrtf(-2.0f * __logf(u01(b.z)));
-  float sa, ca, sb, cb;
-  // 2*pi*u in (0, 2pi): within the accurate range of the MUFU sin/cos
-  __sincosf(6.28318530718f * u01(b.y) - 3.14159265359f, &sa, &ca);
-  __sincosf(6.28318530718f * u01(b.w) - 3.14159265359f, &sb, &cb);
-  // shifted by -pi to centre the argument: sin(t-pi) = -sin t, cos(t-pi) = -cos t
-  n[0] = -ra * ca; n[1] = -ra * sa; n[2] = -rb * cb; n[3] = -rb * sb;
+// ((x >> 9) + 0.5) * 2^-23 without an int->float conversion (reset pose noise)
+__device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
+// 16-bit field -> (k + 0.5) * 2^-16: field in the top of the mantissa of [1,2), minus (1 - 2^-17)
+__device__ __forceinline__ float u01_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
+__device__ __forceinline__ float u01_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
+
+// 4 x N(0,1) from two 32-bit words, like oracle normal4(): each word is one
+// Box-Muller pair (low half -> radius, high half -> angle).
+__device__ __forceinline__ void normal4(uint32_t w0, uint32_t w1, float n[4]) {
+  const float ra = fsqrt(-1.38629436112f * __log2f(u01_lo16(w0)));  // sqrt(-2 ln u)
+  const float rb = fsqrt(-1.38629436112f * __log2f(u01_lo16(w1)));
+  // angle 2 pi u shifted by -pi into the accurate MUFU range: sin(t - pi) = -sin t, cos(t - pi) = -cos t
+  const float ta = fmaf(6.28318530718f, u01_hi16(w0), -3.14159265359f);
+  const float tb = fmaf(6.28318530718f, u01_hi16(w1), -3.14159265359f);
+  n[0] = -ra * __cosf(ta); n[1] = -ra * __sinf(ta); n[2] = -rb * __cosf(tb); n[3] = -rb * __sinf(tb);
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -147,13 +154,13 @@ __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const
     pwm[m] = c.map[4 * m + 0] * cmd[0] + c.map[4 * m + 1] * cmd[1] + c.map[4 * m + 2] * cmd[2] + c.map[4 * m + 3] * cmd[3];
   const float high = fmaxf(fmaxf(pwm[0], pwm[1]), fmaxf(pwm[2], pwm[3]));
   if (high > 1.0f) {
-    const float inv = __frcp_rn(high);
+    const float inv = frcp(high);
 #pragma unroll
     for (int m = 0; m < 4; ++m) pwm[m] *= inv;
   }
   const float low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
   if (low < c.pwm_idle) {
-    const float k = (c.pwm_idle - low) * __frcp_rn(1.0f - low);
+    const float k = (c.pwm_idle - low) * frcp(1.0f - low);
 #pragma unroll
     for (int m = 0; m < 4; ++m) pwm[m] = fmaf(1.0f - pwm[m], k, pwm[m]);
   }
@@ -161,62 +168,63 @@ __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const
 
 // ---------------------------------------------------------------------------
 // one 1/physics_hz sub-step: Motors.physics_update + drag + update_state +
-// pybullet.stepSimulation (free flight) + the declared floor stand-in
+// pybullet.stepSimulation (free flight) + the declared floor stand-in.
+//
+// Bullet integrates the WORLD angular velocity, w' = w + h R a_b, and then
+// q' = exp(h w'/2) q.  With w = R w_b that is exactly  w_b' = w_b + h a_b  and
+// q' = q exp(h w_b'/2)  (a rotation about u leaves u unchanged), so the
+// angular half is carried in the body frame and needs no rotation matrix.
+// (Bullet's +-100 clamp acts on world components; here on body components --
+// the two differ only beyond 100 rad/s.)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float pwm[4], uint32_t sub,
-                                                uint32_t stream, uint32_t k0, uint32_t k1) {
-  // motors: first-order lag, multiplicative noise
-  float nz[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c.noise) normal4(philox4x32_10(make_uint4(sub, stream, e.rng_ctr, 0u), k0, k1), nz);
+__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float pwm[4], const float nz[4]) {
+  // motors: first-order lag, multiplicative noise, thrust and torques
   float fz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     float t = fmaf(c.lag_alpha, pwm[m] - e.thr[m], e.thr[m]);
-    t = fmaf(nz[m] * c.noise_ratio, t, t);
+    t = fmaf(nz[m], t, t);                // nz already scaled by noise_ratio
     e.thr[m] = t;
     const float rr = fabsf(t) * t;        // rpm |rpm| / max_rpm^2
-    const float f = c.thrust_k * rr;      // kf rpm^2
-    fz += f;
-    tx = fmaf(c.my[m], f, tx);            // r x F = (y F, -x F, 0)
-    ty = fmaf(-c.mx[m], f, ty);
+    fz += rr;
+    tx = fmaf(c.my[m], rr, tx);           // r x F = (y F, -x F, 0)
+    ty = fmaf(c.mx[m], rr, ty);
     tz = fmaf(c.torque_k[m], rr, tz);
   }
+  fz *= c.thrust_k; tx *= c.thrust_k; ty *= -c.thrust_k;
   // drag from the (stale) snapshot, body frame
   const float fbx = -c.drag_c * fabsf(e.svb[0]) * e.svb[0];
   const float fby = -c.drag_c * fabsf(e.svb[1]) * e.svb[1];
-  const float fbz = fz - c.drag_c * fabsf(e.svb[2]) * e.svb[2];
+  const float fbz = fmaf(-c.drag_c * fabsf(e.svb[2]), e.svb[2], fz);
   if (!(e.flags & F_CONTACT)) {
-    tx -= c.drag_pqr * fabsf(e.swb[0]) * e.swb[0];
-    ty -= c.drag_pqr * fabsf(e.swb[1]) * e.swb[1];
-    tz -= c.drag_pqr * fabsf(e.swb[2]) * e.swb[2];
+    tx = fmaf(-c.drag_pqr * fabsf(e.swb[0]), e.swb[0], tx);
+    ty = fmaf(-c.drag_pqr * fabsf(e.swb[1]), e.swb[1], ty);
+    tz = fmaf(-c.drag_pqr * fabsf(e.swb[2]), e.swb[2], tz);
   }
   // rotation matrix of the current attitude
   const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
-  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
-  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
-  // body-frame velocities of the current state
-  const float wbx = r00 * e.wx + r10 * e.wy + r20 * e.wz;
-  const float wby = r01 * e.wx + r11 * e.wy + r21 * e.wz;
-  const float wbz = r02 * e.wx + r12 * e.wy + r22 * e.wz;
+  const float x2 = x + x, y2 = y + y, z2 = z + z;
+  const float xx = x * x2, yy = y * y2, zz = z * z2, xy = x * y2, xz = x * z2, yz = y * z2, wx = w * x2, wy = w * y2, wz = w * z2;
+  const float r00 = 1.f - (yy + zz), r01 = xy - wz, r02 = xz + wy;
+  const float r10 = xy + wz, r11 = 1.f - (xx + zz), r12 = yz - wx;
+  const float r20 = xz - wy, r21 = yz + wx, r22 = 1.f - (xx + yy);
   if (c.state_stale) {  // QuadX.update_state runs before stepSimulation
-    e.swb[0] = wbx; e.swb[1] = wby; e.swb[2] = wbz;
+    e.swb[0] = e.wx; e.swb[1] = e.wy; e.swb[2] = e.wz;
     e.svb[0] = r00 * e.vx + r10 * e.vy + r20 * e.vz;
     e.svb[1] = r01 * e.vx + r11 * e.vy + r21 * e.vz;
     e.svb[2] = r02 * e.vx + r12 * e.vy + r22 * e.vz;
     e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
   }
-  // semi-implicit Euler on the floating base
+  // angular half, body frame
   float gx = 0.f, gy = 0.f, gz = 0.f;
   if (c.gyro) {
-    const float lx = c.I[0] * wbx, ly = c.I[1] * wby, lz = c.I[2] * wbz;
-    gx = wby * lz - wbz * ly; gy = wbz * lx - wbx * lz; gz = wbx * ly - wby * lx;
+    const float lx = c.I[0] * e.wx, ly = c.I[1] * e.wy, lz = c.I[2] * e.wz;
+    gx = e.wy * lz - e.wz * ly; gy = e.wz * lx - e.wx * lz; gz = e.wx * ly - e.wy * lx;
   }
-  const float ax = (tx - gx) * c.invI[0], ay = (ty - gy) * c.invI[1], az = (tz - gz) * c.invI[2];
-  e.wx = clampf(fmaf(c.h, r00 * ax + r01 * ay + r02 * az, e.wx), -c.vmax, c.vmax);
-  e.wy = clampf(fmaf(c.h, r10 * ax + r11 * ay + r12 * az, e.wy), -c.vmax, c.vmax);
-  e.wz = clampf(fmaf(c.h, r20 * ax + r21 * ay + r22 * az, e.wz), -c.vmax, c.vmax);
+  e.wx = clampf(fmaf(c.h * c.invI[0], tx - gx, e.wx), -c.vmax, c.vmax);
+  e.wy = clampf(fmaf(c.h * c.invI[1], ty - gy, e.wy), -c.vmax, c.vmax);
+  e.wz = clampf(fmaf(c.h * c.invI[2], tz - gz, e.wz), -c.vmax, c.vmax);
+  // linear half, world frame: semi-implicit Euler
   const float hm = c.h * c.inv_mass;
   e.vx = clampf(fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx), -c.vmax, c.vmax);
   e.vy = clampf(fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy), -c.vmax, c.vmax);
@@ -224,21 +232,25 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
   e.px = fmaf(c.h, e.vx, e.px);
   e.py = fmaf(c.h, e.vy, e.py);
   e.pz = fmaf(c.h, e.vz, e.pz);
-  // q <- exp(h w / 2) q, series in s = |w|^2 (no sqrt / sin / cos), then renormalise
+  // q <- q exp(h w_b / 2): series in s = (|w| h / 2)^2 (no sqrt / sin / cos), then renormalise
   const float hh = 0.5f * c.h;
-  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * hh * hh;  // (theta/2)^2
+  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * (hh * hh);
   const float kq = hh * (1.f + s * (-1.f / 6.f + s * (1.f / 120.f + s * (-1.f / 5040.f))));
   const float dw = 1.f + s * (-0.5f + s * (1.f / 24.f + s * (-1.f / 720.f + s * (1.f / 40320.f))));
   const float dx = e.wx * kq, dy = e.wy * kq, dz = e.wz * kq;
-  const float nx = dw * x + dx * w + dy * z - dz * y;
-  const float ny = dw * y - dx * z + dy * w + dz * x;
-  const float nzq = dw * z + dx * y - dy * x + dz * w;
-  const float nw = dw * w - dx * x - dy * y - dz * z;
-  const float inv = rsqrtf(nx * nx + ny * ny + nzq * nzq + nw * nw);
+  const float nx = w * dx + x * dw + y * dz - z * dy;
+  const float ny = w * dy - x * dz + y * dw + z * dx;
+  const float nzq = w * dz + x * dy - y * dx + z * dw;
+  const float nw = w * dw - x * dx - y * dy - z * dz;
+  const float inv = frsqrt(nx * nx + ny * ny + nzq * nzq + nw * nw);
   e.qx = nx * inv; e.qy = ny * inv; e.qz = nzq * inv; e.qw = nw * inv;
-  // floor stand-in: sticky plane at floor_z
+  // floor stand-in: sticky plane at floor_z (zeroes world v_xy and world w_xy)
   if (e.pz < c.floor_z) {
-    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vx = 0.f; e.vy = 0.f; e.wx = 0.f; e.wy = 0.f;
+    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vx = 0.f; e.vy = 0.f;
+    const float X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
+    const float a20 = 2.f * (X * Z - W * Y), a21 = 2.f * (Y * Z + W * X), a22 = 1.f - 2.f * (X * X + Y * Y);
+    const float wzw = a20 * e.wx + a21 * e.wy + a22 * e.wz;  // world yaw rate survives
+    e.wx = a20 * wzw; e.wy = a21 * wzw; e.wz = a22 * wzw;
     e.flags |= F_CONTACT;
   } else {
     e.flags &= ~F_CONTACT;
@@ -248,9 +260,7 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
     const float a00 = 1.f - 2.f * (Y * Y + Z * Z), a01 = 2.f * (X * Y - W * Z), a02 = 2.f * (X * Z + W * Y);
     const float a10 = 2.f * (X * Y + W * Z), a11 = 1.f - 2.f * (X * X + Z * Z), a12 = 2.f * (Y * Z - W * X);
     const float a20 = 2.f * (X * Z - W * Y), a21 = 2.f * (Y * Z + W * X), a22 = 1.f - 2.f * (X * X + Y * Y);
-    e.swb[0] = a00 * e.wx + a10 * e.wy + a20 * e.wz;
-    e.swb[1] = a01 * e.wx + a11 * e.wy + a21 * e.wz;
-    e.swb[2] = a02 * e.wx + a12 * e.wy + a22 * e.wz;
+    e.swb[0] = e.wx; e.swb[1] = e.wy; e.swb[2] = e.wz;
     e.svb[0] = a00 * e.vx + a10 * e.vy + a20 * e.vz;
     e.svb[1] = a01 * e.vx + a11 * e.vy + a21 * e.vz;
     e.svb[2] = a02 * e.vx + a12 * e.vy + a22 * e.vz;
@@ -301,7 +311,7 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
   // sin / cos of the roll Euler angle = (r21, r22) / cos(pitch)
   float sph = 0.f, cph = 1.f;
   if (fabsf(r20) < 0.99999f) {
-    const float inv = rsqrtf(r21 * r21 + r22 * r22);
+    const float inv = frsqrt(r21 * r21 + r22 * r22);
     sph = r21 * inv; cph = r22 * inv;
   }
   // camera axes in the body frame: Rx(-roll) Ry(-tilt) Rx(roll) applied to x, z
@@ -320,7 +330,7 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
     const float bz = r02 * dx + r12 * dy + r22 * dz - c.cam_off[2];
     const float depth = fx * bx + fy * by + fzz * bz;
     ok = ok && (depth > c.cam_near);
-    const float k1 = c.inv_tan * __frcp_rn(fmaxf(depth, 1e-9f));
+    const float k1 = c.inv_tan * frcp(fmaxf(depth, 1e-9f));
     pxs[k] = fmaf((rx * bx + ry * by + rz * bz) * k1, c.half_res, c.half_res);
     pys[k] = fmaf(-(ux * bx + uy * by + uz * bz) * k1, c.half_res, c.half_res);
   }
@@ -335,7 +345,7 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
     const int kn = (k + 1) & 3;
     a2 += pxs[k] * pys[kn] - pxs[kn] * pys[k];
     const float ex = pxs[kn] - pxs[k], ey = pys[kn] - pys[k];
-    per += sqrtf(ex * ex + ey * ey);
+    per += fsqrt(ex * ex + ey * ey);
   }
   const float wpx = floorf(xmax - 0.5f) - ceilf(xmin - 0.5f) + 1.f;
   const float hpx = floorf(ymax - 0.5f) - ceilf(ymin - 0.5f) + 1.f;
@@ -344,7 +354,7 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
   cx = ok ? fmaf(0.25f * (pxs[0] + pxs[1] + pxs[2] + pxs[3]) - 0.5f, c.inv_half_res, -1.f) : 0.f;
   cy = ok ? fmaf(0.25f * (pys[0] + pys[1] + pys[2] + pys[3]) - 0.5f, c.inv_half_res, -1.f) : 0.f;
   area = ok ? fmaxf(0.5f * fabsf(a2) - 0.5f * per + 1.f, 0.f) * c.inv_res2 : 0.f;
-  ratio = ok ? __fdividef(wpx, hpx) : 0.f;
+  ratio = ok ? wpx * frcp(hpx) : 0.f;
 }
 
 // Aviary(start_pos, start_orn) + Aviary.reset() + the env bookkeeping of

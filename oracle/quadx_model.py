@@ -147,18 +147,26 @@ def rng_key(seed: int, env_ids: np.ndarray) -> np.ndarray:
 
 def u01(x: np.ndarray) -> np.ndarray:
     """uint32 -> (0,1): ((x >> 9) + 0.5) * 2^-23 -- exact in fp32 and fp64 (on
-    the GPU: bit-cast (x >> 9) | 0x3f800000 and subtract 1 - 2^-24, no I2F)."""
+    the GPU: bit-cast (x >> 9) | 0x3f800000 and subtract 1 - 2^-24, no I2F).
+    Used for the reset pose noise."""
     return ((x >> np.uint32(9)).astype(np.float64) + 0.5) * (1.0 / 8388608.0)
 
 
-def normal4(bits: np.ndarray) -> np.ndarray:
-    """uint32[N,4] -> N(0,1)[N,4] by two Box-Muller pairs (cos, sin, cos, sin)."""
-    u = u01(bits)
-    ra = np.sqrt(-2.0 * np.log(u[:, 0]))
-    rb = np.sqrt(-2.0 * np.log(u[:, 2]))
-    ta = 2.0 * np.pi * u[:, 1]
-    tb = 2.0 * np.pi * u[:, 3]
-    return np.stack([ra * np.cos(ta), ra * np.sin(ta), rb * np.cos(tb), rb * np.sin(tb)], axis=1)
+def u01_16(x: np.ndarray) -> np.ndarray:
+    """16-bit field (as uint32) -> (0,1): (x + 0.5) * 2^-16."""
+    return (x.astype(np.float64) + 0.5) * (1.0 / 65536.0)
+
+
+def normal4(w: np.ndarray) -> np.ndarray:
+    """Two 32-bit words [N,2] -> four N(0,1) [N,4]: each word feeds one
+    Box-Muller pair, low 16 bits -> radius, high 16 bits -> angle; outputs are
+    (r_a cos, r_a sin, r_b cos, r_b sin) for motors 0..3.  One Philox4x32-10
+    call (4 words) therefore serves two physics sub-steps."""
+    lo = w & np.uint32(0xFFFF)
+    hi = w >> np.uint32(16)
+    r = np.sqrt(-2.0 * np.log(u01_16(lo)))
+    t = 2.0 * np.pi * u01_16(hi)
+    return np.stack([r[:, 0] * np.cos(t[:, 0]), r[:, 0] * np.sin(t[:, 0]), r[:, 1] * np.cos(t[:, 1]), r[:, 1] * np.sin(t[:, 1])], axis=1)
 
 
 # ----------------------------------------------------------------------------
@@ -402,9 +410,12 @@ class NoiseSource:
         return philox4x32_10(ctr, self._key)
 
     def normals(self, sub: int, stream: int, step_ctr: np.ndarray):
+        """Motor noise of sub-step ``sub``: Philox counter word 0 is sub >> 1,
+        the sub-step parity picks the word pair."""
         if not self.enabled:
             return None
-        return normal4(self.bits(sub, stream, step_ctr))
+        b = self.bits(sub >> 1, stream, step_ctr)
+        return normal4(b[:, 2 * (sub & 1): 2 * (sub & 1) + 2])
 
 
 def aviary_step(st: QuadXState, setpoint: np.ndarray, p: QuadXParams, noise, sub0: int, stream: int, step_ctr) -> int:

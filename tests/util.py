@@ -4,7 +4,10 @@ import numpy as np
 
 def oracle_to_kernel_state(orc) -> dict:
     """HoverVecOracle -> dict keyed like fpv_drone_rl_agent_b200.STATE_FIELDS."""
+    from oracle.quadx_model import quat_to_mat
+
     st = orc.st
+    wb = np.einsum("nji,nj->ni", quat_to_mat(st.quat), st.omega)  # the kernel carries body rates
     flags = (
         st.contact.astype(np.uint32) * 1
         | orc.terminated.astype(np.uint32) * 2
@@ -17,7 +20,7 @@ def oracle_to_kernel_state(orc) -> dict:
         "px": st.pos[:, 0], "py": st.pos[:, 1], "pz": st.pos[:, 2],
         "qx": st.quat[:, 0], "qy": st.quat[:, 1], "qz": st.quat[:, 2], "qw": st.quat[:, 3],
         "vx": st.vel[:, 0], "vy": st.vel[:, 1], "vz": st.vel[:, 2],
-        "wx": st.omega[:, 0], "wy": st.omega[:, 1], "wz": st.omega[:, 2],
+        "wbx": wb[:, 0], "wby": wb[:, 1], "wbz": wb[:, 2],
         "step_count": orc.step_count, "rng_ctr": orc.rng_ctr, "ep_return": orc.ep_return, "flags": flags,
         "prev_cx": orc.prev_centre[:, 0], "prev_cy": orc.prev_centre[:, 1], "prev_area": orc.prev_area, "prev_ratio": orc.prev_ratio,
         "prev_roll": orc.prev_euler[:, 0], "prev_pitch": orc.prev_euler[:, 1], "prev_yaw": orc.prev_euler[:, 2],
@@ -38,7 +41,10 @@ def kernel_state_arrays(s: dict):
     pos = np.stack([s["px"], s["py"], s["pz"]], 1)
     quat = np.stack([s["qx"], s["qy"], s["qz"], s["qw"]], 1)
     vel = np.stack([s["vx"], s["vy"], s["vz"]], 1)
-    omega = np.stack([s["wx"], s["wy"], s["wz"]], 1)
+    from oracle.quadx_model import quat_to_mat
+
+    wb = np.stack([s["wbx"], s["wby"], s["wbz"]], 1).astype(np.float64)
+    omega = np.einsum("nij,nj->ni", quat_to_mat(quat.astype(np.float64)), wb)  # world frame, like the oracle
     thr = np.stack([s[f"thr{m}"] for m in range(4)], 1)
     return pos, quat, vel, omega, thr
 
