@@ -53,6 +53,13 @@ class QxConfig(C.Structure):
         return self
 
 
+class PpoPolicy(C.Structure):
+    """Mirror of ``struct PpoPolicy`` in include/ppo_b200.h."""
+
+    _fields_ = [("w1", C.c_void_p), ("w2p", C.c_void_p), ("w2v", C.c_void_p), ("w3", C.c_void_p), ("b1", C.c_void_p),
+                ("b2", C.c_void_p), ("b3", C.c_void_p), ("log_std", C.c_void_p), ("obs_dim", i32), ("act_dim", i32)]
+
+
 _lib = None
 
 
@@ -74,6 +81,9 @@ def lib() -> C.CDLL:
         "qx_destroy": (C.c_int, [vp]),
         "qx_reset": (C.c_int, [vp, u8p, vp, i32, i64, vp]),
         "qx_step": (C.c_int, [vp, f32p, vp, i32, i64, f32p, u8p, u8p, f32p, vp]),
+        "qx_step_begin": (C.c_int, [vp, f32p, vp, i32, i64, f32p, u8p, u8p, f32p, vp]),
+        "qx_step_end": (C.c_int, [vp, vp, i32, i64, vp]),
+        "qx_done_queue": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "qx_step_k": (C.c_int, [vp, i32, f32p, f32p, f32p, u8p, u8p, vp]),
         "qx_reset_host": (C.c_int, [vp, u8p, f32p]),
         "qx_step_host": (C.c_int, [vp, f32p, f32p, f32p, u8p, u8p, f32p]),
@@ -88,6 +98,14 @@ def lib() -> C.CDLL:
         "qx_sizeof_config": (i64, []),
         "qx_last_error": (C.c_char_p, []),
         "qx_version": (i32, []),
+        # include/ppo_b200.h
+        "ppo_policy_forward": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, vp, f32, u64, u64, u64, vp, i32, vp, vp, vp, vp, vp, vp]),
+        "ppo_bootstrap_truncated": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, vp, f32, vp, vp, vp, vp, f32, vp, vp]),
+        "ppo_gae": (C.c_int, [vp, vp, vp, vp, i32, i64, f32, f32, vp, vp, vp]),
+        "ppo_running_stats_update": (C.c_int, [vp, i64, i64, i32, vp, f32, vp, vp, vp, vp]),
+        "ppo_running_stats_scratch_bytes": (i64, [i32]),
+        "ppo_reward_normalize": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp]),
+        "ppo_test_gemm": (C.c_int, [vp, vp, vp, i32, i32, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
@@ -99,10 +117,12 @@ def lib() -> C.CDLL:
 
 
 EXPORTED = [
-    "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_k", "qx_reset_host", "qx_step_host",
+    "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
     "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
+PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
+                "ppo_reward_normalize", "ppo_test_gemm"]
 
 
 class QxError(RuntimeError):

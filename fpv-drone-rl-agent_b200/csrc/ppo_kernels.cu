@@ -1,0 +1,527 @@
+// ppo_kernels.cu -- on-device PPO rollout kernels for sm_100a (C-ABI: include/ppo_b200.h).
+//   K2  actor-critic MLP forward on tcgen05 tensor cores + Gaussian sampling + log-prob
+//   K3  GAE / returns reverse scan
+//   K4  VecNormalize running statistics (obs and discounted-return) + reward normalisation
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "../../include/ppo_b200.h"
+#include "../../include/quadx_b200.h"
+#include "qx_model.cuh"
+#include "tc05.cuh"
+
+namespace ppo {
+
+using namespace tc05;
+
+// ---------------------------------------------------------------------------
+// test hook: one 128 x n x k GEMM through the same staging / descriptor / TMEM
+// helpers the policy kernel uses
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) test_gemm_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                        float* __restrict__ D, int n, int k) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * k * 2;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  stage_weight(sA, A, 128, k, tid, 128);
+  stage_weight(sB, B, n, k, tid, 128);
+  fence_async_smem();
+  uint32_t ncols = 32;
+  while ((int)ncols < n) ncols <<= 1;
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, n);
+    const uint32_t lboA = 128 * 16, lboB = n * 16;
+    for (int ks = 0; ks < k / 16; ++ks)
+      mma_bf16(tbase, make_desc(smem_u32(sA) + ks * 2 * lboA, lboA, 128), make_desc(smem_u32(sB) + ks * 2 * lboB, lboB, 128), idesc, ks > 0);
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tbase + ((warp * 32u) << 16) + c0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)tid * n + c0 + j] = __uint_as_float(r[j]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, ncols);
+}
+
+
+// ---------------------------------------------------------------------------
+// K2: ActorCriticPolicy.forward.  One CTA = 128 threads = one tile of 128 rows
+// (thread == row), persistent over tiles.  All weights stay resident in shared
+// memory in the interleaved K-major layout; per tile
+//   L1  X[128x32]  . W1^T [32x256]        -> TMEM cols [0,256)   (pi | vf)
+//   L2  H1p[128x128] . W2p^T, H1v . W2v^T -> TMEM cols [0,128), [128,256)
+//   L3  [H2p|H2v][128x256] . W3^T [256x16] -> TMEM cols [0,16)   (mean0..3, value)
+// with the bias + tanh + bf16 epilogues run by the same 128 threads straight
+// out of TMEM (tcgen05.ld 32x32b: thread t of warp w owns accumulator row
+// 32w + t) into the next layer's A operand in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int kHid = PPO_HIDDEN, kIn = PPO_IN_PAD, kHead = PPO_HEAD_PAD;
+constexpr uint32_t kSmW1 = 0;                                  // [4][256][16 B]
+constexpr uint32_t kSmW2p = kSmW1 + 2 * kHid * kIn * 2;        // [16][128][16 B]
+constexpr uint32_t kSmW2v = kSmW2p + kHid * kHid * 2;
+constexpr uint32_t kSmW3 = kSmW2v + kHid * kHid * 2;           // [32][16][16 B]
+constexpr uint32_t kSmX = kSmW3 + kHead * 2 * kHid * 2;        // [4][128][16 B]
+constexpr uint32_t kSmH = kSmX + 128 * kIn * 2;                // [32][128][16 B]
+constexpr uint32_t kSmB1 = kSmH + 128 * 2 * kHid * 2;          // 256 f32
+constexpr uint32_t kSmB2 = kSmB1 + 2 * kHid * 4;
+constexpr uint32_t kSmB3 = kSmB2 + 2 * kHid * 4;               // 16 f32
+constexpr uint32_t kSmNorm = kSmB3 + kHead * 4;                // mean[32], inv_std[32]
+constexpr uint32_t kSmTotal = kSmNorm + 2 * kIn * 4;
+
+struct FwdArgs {
+  PpoPolicy p;
+  const float* obs;
+  int64_t obs_stride, n;
+  const float* obs_mean;
+  const float* obs_inv_std;
+  float obs_clip;
+  uint32_t seed_lo, seed_hi;
+  uint64_t row0, step;
+  int32_t deterministic;
+  float* actions;
+  float* env_actions;
+  float* values;
+  float* log_probs;
+  float* obs_norm_out;            // [n, obs_dim] normalised obs as the policy saw them (what PPO stores)
+  const uint64_t* step_base;      // device counter added to `step` (CUDA-graph replays)
+  // gather / bootstrap mode: rows are taken from idx[0 .. *count) and, for rows that were truncated but not
+  // terminated, reward[row] += gamma * V(obs[row])   (SB3 collect_rollouts time-limit bootstrap)
+  const uint32_t* gather_idx;
+  const uint32_t* gather_count;
+  float* boot_reward;
+  const uint8_t* boot_te;
+  const uint8_t* boot_tr;
+  float boot_gamma;
+};
+
+__device__ __forceinline__ uint32_t tanh_pack_bf16x2(float lo, float hi) {
+#ifdef PPO_TANH_BF16X2
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  uint32_t u = *reinterpret_cast<uint32_t*>(&v), r;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(u));
+  return r;
+#else
+  float a, b;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(lo));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(hi));
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+#endif
+}
+
+// bias + tanh + bf16 of 256 accumulator columns of this thread's row -> sH chunks
+__device__ __forceinline__ void hidden_epilogue(uint32_t trow, const float* __restrict__ bias, uint8_t* sH, uint32_t row) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < 2 * kHid; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(trow + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 v;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q), b1 = *reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4);
+      v.x = tanh_pack_bf16x2(__uint_as_float(r[8 * q + 0]) + b0.x, __uint_as_float(r[8 * q + 1]) + b0.y);
+      v.y = tanh_pack_bf16x2(__uint_as_float(r[8 * q + 2]) + b0.z, __uint_as_float(r[8 * q + 3]) + b0.w);
+      v.z = tanh_pack_bf16x2(__uint_as_float(r[8 * q + 4]) + b1.x, __uint_as_float(r[8 * q + 5]) + b1.y);
+      v.w = tanh_pack_bf16x2(__uint_as_float(r[8 * q + 6]) + b1.z, __uint_as_float(r[8 * q + 7]) + b1.w);
+      *reinterpret_cast<uint4*>(sH + chunk_off(row, (uint32_t)(c0 >> 3) + q, 128)) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) policy_forward_kernel(const FwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const int obs_dim = a.p.obs_dim, act_dim = a.p.act_dim;
+  // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barrier
+  stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, 128);
+  stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, 128);
+  stage_weight(smem + kSmW2v, (const __nv_bfloat16*)a.p.w2v, kHid, kHid, tid, 128);
+  stage_weight(smem + kSmW3, (const __nv_bfloat16*)a.p.w3, kHead, 2 * kHid, tid, 128);
+  float* sB1 = reinterpret_cast<float*>(smem + kSmB1);
+  float* sB2 = reinterpret_cast<float*>(smem + kSmB2);
+  float* sB3 = reinterpret_cast<float*>(smem + kSmB3);
+  float* sMean = reinterpret_cast<float*>(smem + kSmNorm);
+  float* sInv = sMean + kIn;
+  for (int j = tid; j < 2 * kHid; j += 128) { sB1[j] = a.p.b1[j]; sB2[j] = a.p.b2[j]; }
+  if (tid < kHead) sB3[tid] = a.p.b3[tid];
+  if (tid < kIn) {
+    sMean[tid] = (a.obs_mean && (int)tid < obs_dim) ? a.obs_mean[tid] : 0.f;
+    sInv[tid] = (a.obs_inv_std && (int)tid < obs_dim) ? a.obs_inv_std[tid] : 1.f;
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t trow = tbase + ((warp * 32u) << 16);
+  const uint32_t sX = smem_u32(smem + kSmX), sH = smem_u32(smem + kSmH);
+  const uint32_t sW1 = smem_u32(smem + kSmW1), sW2p = smem_u32(smem + kSmW2p), sW2v = smem_u32(smem + kSmW2v), sW3 = smem_u32(smem + kSmW3);
+  constexpr uint32_t LBO_ACT = 128 * 16, LBO_W1 = 2 * kHid * 16, LBO_W2 = kHid * 16, LBO_W3 = kHead * 16;
+  uint32_t phase = 0;
+  const int64_t n_rows = a.gather_idx ? (int64_t)*a.gather_count : a.n;
+  const int64_t n_tiles = (n_rows + 127) / 128;
+  const float clipv = a.obs_clip > 0.f ? a.obs_clip : 3.0e38f;
+  const uint64_t step = a.step + (a.step_base ? *a.step_base : 0ull);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool valid = tile * 128 + tid < n_rows;
+    const int64_t row = !valid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + tid] : tile * 128 + tid);
+    // ---- X tile: normalise (VecNormalize.normalize_obs), bf16, interleaved K-major
+    {
+      float x[kIn];
+#pragma unroll
+      for (int j = 0; j < kIn; ++j) x[j] = 0.f;
+      if (valid) {
+        const float* src = a.obs + row * a.obs_stride;
+        if (obs_dim == 20 && (a.obs_stride & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 20; j += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + j));
+            x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kIn; ++j)
+            if (j < obs_dim) x[j] = __ldg(src + j);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kIn / 8; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int j = 8 * q + 2 * h;
+          const float v0 = fminf(fmaxf((x[j] - sMean[j]) * sInv[j], -clipv), clipv);
+          const float v1 = fminf(fmaxf((x[j + 1] - sMean[j + 1]) * sInv[j + 1], -clipv), clipv);
+          x[j] = v0; x[j + 1] = v1;
+          __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+          w[h] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        *reinterpret_cast<uint4*>(smem + kSmX + chunk_off(tid, q, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      if (a.obs_norm_out && valid) {
+        float* dst = a.obs_norm_out + row * obs_dim;
+        if (obs_dim == 20) {
+#pragma unroll
+          for (int j = 0; j < 20; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kIn; ++j)
+            if (j < obs_dim) dst[j] = x[j];
+        }
+      }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- L1
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, 2 * kHid);
+#pragma unroll
+      for (int ks = 0; ks < kIn / 16; ++ks)
+        mma_bf16(tbase, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + ks * 2 * LBO_W1, LBO_W1, 128), idesc, ks > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(trow, sB1, smem + kSmH, tid);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- L2 (two independent 128x128x128 chains)
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, kHid);
+#pragma unroll
+      for (int ks = 0; ks < kHid / 16; ++ks)
+        mma_bf16(tbase, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2p + ks * 2 * LBO_W2, LBO_W2, 128), idesc, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < kHid / 16; ++ks)
+        mma_bf16(tbase + kHid, make_desc(sH + (16 + ks * 2) * LBO_ACT, LBO_ACT, 128), make_desc(sW2v + ks * 2 * LBO_W2, LBO_W2, 128), idesc, ks > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(trow, sB2, smem + kSmH, tid);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    // ---- L3 (action_net + value_net as one 128x16x256 GEMM)
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, kHead);
+#pragma unroll
+      for (int ks = 0; ks < 2 * kHid / 16; ++ks)
+        mma_bf16(tbase, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + ks * 2 * LBO_W3, LBO_W3, 128), idesc, ks > 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase); phase ^= 1;
+    fence_after_sync();
+    {
+      uint32_t r[16];
+      tmem_ld16(trow, r);
+      tmem_ld_wait();
+      if (valid) {
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, act[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < act_dim) mean[j] = __uint_as_float(r[j]) + sB3[j];
+        float value = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j == act_dim) value = __uint_as_float(r[j]) + sB3[j];
+        float logp = 0.f;
+        if (!a.deterministic) {
+          const uint64_t gid = a.row0 + (uint64_t)row;
+          const uint4 b = qx::philox4x32_10(make_uint4(0u, 3u, (uint32_t)step, (uint32_t)(step >> 32)),
+                                            a.seed_lo ^ (uint32_t)gid, a.seed_hi ^ (uint32_t)(gid >> 32));
+          const float ra = sqrtf(-2.f * __logf(qx::u01(b.x))), rb = sqrtf(-2.f * __logf(qx::u01(b.z)));
+          float s0, c0, s1, c1;
+          __sincosf(6.28318530718f * qx::u01(b.y) - 3.14159265359f, &s0, &c0);
+          __sincosf(6.28318530718f * qx::u01(b.w) - 3.14159265359f, &s1, &c1);
+          nz[0] = -ra * c0; nz[1] = -ra * s0; nz[2] = -rb * c1; nz[3] = -rb * s1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < act_dim) {
+            const float ls = __ldg(a.p.log_std + j);
+            act[j] = fmaf(__expf(ls), nz[j], mean[j]);
+            logp += -0.5f * nz[j] * nz[j] - ls - 0.91893853320467f;
+          }
+        if (act_dim == 4) {
+          if (a.actions) *reinterpret_cast<float4*>(a.actions + row * 4) = make_float4(act[0], act[1], act[2], act[3]);
+          if (a.env_actions)
+            *reinterpret_cast<float4*>(a.env_actions + row * 4) =
+                make_float4(qx::clampf(act[0], -1.f, 1.f), qx::clampf(act[1], -1.f, 1.f), qx::clampf(act[2], -1.f, 1.f), qx::clampf(act[3], -1.f, 1.f));
+        } else {
+          for (int j = 0; j < act_dim; ++j) {
+            if (a.actions) a.actions[row * act_dim + j] = act[j];
+            if (a.env_actions) a.env_actions[row * act_dim + j] = qx::clampf(act[j], -1.f, 1.f);
+          }
+        }
+        if (a.values) a.values[row] = value;
+        if (a.log_probs) a.log_probs[row] = logp;
+        if (a.boot_reward && a.boot_tr[row] && !a.boot_te[row]) a.boot_reward[row] = fmaf(a.boot_gamma, value, a.boot_reward[row]);
+      }
+    }
+    fence_before_sync();
+    __syncthreads();  // TMEM cols [0,16) and sX are reused by the next tile
+  }
+  if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
+// ---------------------------------------------------------------------------
+// K3: GAE(lambda) -- RolloutBuffer.compute_returns_and_advantage.  One thread per
+// env walks its column of the [T, n] buffers backwards (coalesced across envs):
+//   delta_t = r_t + gamma V_{t+1} (1 - d_t) - V_t ;  A_t = delta_t + gamma lam (1 - d_t) A_{t+1}
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+                                                  const float* __restrict__ last_val, int T, int64_t n, float gamma, float lam,
+                                                  float* __restrict__ adv, float* __restrict__ ret) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float next_v = last_val[i], gae = 0.f;
+  // software pipeline: the loads of step t-1 are issued before the arithmetic of step t
+  float r = rew[(int64_t)(T - 1) * n + i], v = val[(int64_t)(T - 1) * n + i];
+  uint8_t d = done[(int64_t)(T - 1) * n + i];
+  for (int t = T - 1; t >= 0; --t) {
+    float r2 = 0.f, v2 = 0.f;
+    uint8_t d2 = 0;
+    if (t > 0) { r2 = rew[(int64_t)(t - 1) * n + i]; v2 = val[(int64_t)(t - 1) * n + i]; d2 = done[(int64_t)(t - 1) * n + i]; }
+    const float nnt = d ? 0.f : 1.f;
+    const float delta = fmaf(gamma * next_v, nnt, r) - v;
+    gae = fmaf(gamma * lam * nnt, gae, delta);
+    adv[(int64_t)t * n + i] = gae;
+    ret[(int64_t)t * n + i] = gae + v;
+    next_v = v;
+    r = r2; v = v2; d = d2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: VecNormalize running statistics.  Stage 1: per-block fp64 sums of x and
+// x^2 per column; stage 2 (one block): batch moments -> parallel-Welford merge
+// into {mean[dim], var[dim], count} and refresh the fp32 mean / inv_std.
+// ---------------------------------------------------------------------------
+constexpr int kStatBlocks = 296, kStatThreads = 256, kStatMaxDim = 32;
+
+__global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float* __restrict__ x, int64_t stride, int64_t n, int dim, double* __restrict__ part) {
+  __shared__ double sh[kStatThreads / 32][2 * kStatMaxDim];
+  double s[kStatMaxDim], q[kStatMaxDim];
+  for (int j = 0; j < kStatMaxDim; ++j) { s[j] = 0.0; q[j] = 0.0; }
+  for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStatThreads) {
+    const float* row = x + i * stride;
+#pragma unroll
+    for (int j = 0; j < kStatMaxDim; ++j)
+      if (j < dim) { const double v = (double)row[j]; s[j] += v; q[j] += v * v; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < kStatMaxDim; ++j)
+    if (j < dim) {
+      double a = s[j], b = q[j];
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      if (lane == 0) { sh[w][j] = a; sh[w][kStatMaxDim + j] = b; }
+    }
+  __syncthreads();
+  if (threadIdx.x < 2 * kStatMaxDim) {
+    double a = 0.0;
+    for (int k = 0; k < kStatThreads / 32; ++k) a += sh[k][threadIdx.x];
+    part[(size_t)blockIdx.x * 2 * kStatMaxDim + threadIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(64) stats_merge_kernel(const double* __restrict__ part, int nblocks, int64_t n, int dim, double* __restrict__ stats, float eps,
+                                                         float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
+  const int j = threadIdx.x;
+  const bool on = j < dim;
+  double new_mean = 0.0, new_var = 1.0, tot = 0.0;
+  if (on) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; ++b) { s += part[(size_t)b * 2 * kStatMaxDim + j]; q += part[(size_t)b * 2 * kStatMaxDim + kStatMaxDim + j]; }
+    const double bc = (double)n, bm = s / bc, bv = fmax(q / bc - bm * bm, 0.0);
+    const double mean = stats[j], var = stats[dim + j], count = stats[2 * dim];
+    const double delta = bm - mean;
+    tot = count + bc;
+    new_mean = mean + delta * bc / tot;
+    new_var = (var * count + bv * bc + delta * delta * count * bc / tot) / tot;
+  }
+  __syncthreads();  // every thread has read the old count before thread 0 replaces it
+  if (!on) return;
+  stats[j] = new_mean;
+  stats[dim + j] = new_var;
+  if (j == 0) stats[2 * dim] = tot;
+  if (mean_f32) mean_f32[j] = (float)new_mean;
+  if (inv_std_f32) inv_std_f32[j] = (float)(1.0 / sqrt(new_var + (double)eps));
+}
+
+__global__ void __launch_bounds__(256) returns_acc_kernel(const float* __restrict__ r, float* __restrict__ acc, int64_t n, float gamma) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] = fmaf(acc[i], gamma, r[i]);
+}
+
+__global__ void __launch_bounds__(256) reward_norm_kernel(const float* __restrict__ r, const uint8_t* __restrict__ te, const uint8_t* __restrict__ tr, float* __restrict__ acc,
+                                                          int64_t n, float clip, float eps, const double* __restrict__ ret_stats, float* __restrict__ out,
+                                                          uint8_t* __restrict__ done_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float inv = ret_stats ? (float)(1.0 / sqrt(ret_stats[1] + (double)eps)) : 1.f;
+  out[i] = fminf(fmaxf(r[i] * inv, -clip), clip);
+  const uint8_t d = te[i] | tr[i];
+  if (d && acc) acc[i] = 0.f;
+  if (done_out) done_out[i] = d;
+}
+
+}  // namespace ppo
+
+static int pfail(int code, const char* msg) {
+  fprintf(stderr, "libquadx_b200/ppo: %s\n", msg);
+  return code;
+}
+
+extern "C" int ppo_test_gemm(const void* a, const void* b, float* d, int32_t n, int32_t k, void* stream) {
+  if (!a || !b || !d || n < 16 || n > 256 || n % 16 || k < 16 || k % 16) return pfail(QX_EINVAL, "ppo_test_gemm: bad arguments");
+  const size_t smem = (size_t)(128 + n) * k * 2;
+  if (smem > 200 * 1024) return pfail(QX_EINVAL, "ppo_test_gemm: tile too large");
+  cudaFuncSetAttribute(ppo::test_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ppo::test_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, d, n, k);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_test_gemm: launch failed");
+}
+
+static int launch_forward(ppo::FwdArgs& a, int64_t max_rows, void* stream) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(ppo::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppo::kSmTotal) != cudaSuccess)
+      return pfail(QX_ECUDA, "ppo_policy_forward: cannot reserve shared memory");
+  }
+  const int64_t tiles = (max_rows + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  ppo::policy_forward_kernel<<<grid, 128, ppo::kSmTotal, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_policy_forward: launch failed");
+}
+
+static bool policy_ok(const PpoPolicy* p) {
+  return p && p->w1 && p->w2p && p->w2v && p->w3 && p->b1 && p->b2 && p->b3 && p->log_std && p->obs_dim >= 1 && p->obs_dim <= PPO_IN_PAD &&
+         p->act_dim >= 1 && p->act_dim <= 4;
+}
+
+extern "C" int ppo_policy_forward(const PpoPolicy* p, const float* obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                                  const float* obs_inv_std, float obs_clip, uint64_t seed, uint64_t row0, uint64_t step,
+                                  const uint64_t* step_base_dev, int32_t deterministic, float* actions, float* env_actions, float* values,
+                                  float* log_probs, float* obs_norm_out, void* stream) {
+  if (!policy_ok(p) || !obs || n <= 0 || obs_stride < p->obs_dim) return pfail(QX_EINVAL, "ppo_policy_forward: bad arguments");
+  ppo::FwdArgs a{};
+  a.p = *p; a.obs = obs; a.obs_stride = obs_stride; a.n = n; a.obs_mean = obs_mean; a.obs_inv_std = obs_inv_std; a.obs_clip = obs_clip;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.row0 = row0; a.step = step; a.step_base = step_base_dev;
+  a.deterministic = deterministic; a.actions = actions; a.env_actions = env_actions; a.values = values; a.log_probs = log_probs;
+  a.obs_norm_out = obs_norm_out;
+  return launch_forward(a, n, stream);
+}
+
+extern "C" int ppo_bootstrap_truncated(const PpoPolicy* p, const float* terminal_obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                                       const float* obs_inv_std, float obs_clip, const uint32_t* done_count_dev, const uint32_t* done_idx_dev,
+                                       const uint8_t* terminated, const uint8_t* truncated, float gamma, float* reward_inout, void* stream) {
+  if (!policy_ok(p) || !terminal_obs || n <= 0 || !done_count_dev || !done_idx_dev || !terminated || !truncated || !reward_inout)
+    return pfail(QX_EINVAL, "ppo_bootstrap_truncated: bad arguments");
+  ppo::FwdArgs a{};
+  a.p = *p; a.obs = terminal_obs; a.obs_stride = obs_stride; a.n = n; a.obs_mean = obs_mean; a.obs_inv_std = obs_inv_std; a.obs_clip = obs_clip;
+  a.deterministic = 1; a.gather_idx = done_idx_dev; a.gather_count = done_count_dev; a.boot_reward = reward_inout; a.boot_te = terminated;
+  a.boot_tr = truncated; a.boot_gamma = gamma;
+  return launch_forward(a, n, stream);
+}
+
+extern "C" int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int32_t T, int64_t n,
+                       float gamma, float lam, float* advantages, float* returns, void* stream) {
+  if (!rewards || !values || !dones || !last_values || !advantages || !returns || T <= 0 || n <= 0) return pfail(QX_EINVAL, "ppo_gae: bad arguments");
+  ppo::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_gae: launch failed");
+}
+
+extern "C" int64_t ppo_running_stats_scratch_bytes(int32_t dim) { (void)dim; return (int64_t)ppo::kStatBlocks * 2 * ppo::kStatMaxDim * sizeof(double); }
+
+extern "C" int ppo_running_stats_update(const float* x, int64_t stride, int64_t n, int32_t dim, double* stats, float eps, float* mean_f32,
+                                        float* inv_std_f32, void* scratch, void* stream) {
+  if (!x || !stats || !scratch || n <= 0 || dim < 1 || dim > ppo::kStatMaxDim || stride < dim) return pfail(QX_EINVAL, "ppo_running_stats_update: bad arguments");
+  int64_t want = (n + ppo::kStatThreads - 1) / ppo::kStatThreads;
+  const int blocks = (int)(want < ppo::kStatBlocks ? want : ppo::kStatBlocks);
+  ppo::stats_partial_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(x, stride, n, dim, (double*)scratch);
+  ppo::stats_merge_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, dim, stats, eps, mean_f32, inv_std_f32);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_running_stats_update: launch failed");
+}
+
+extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                                    float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream) {
+  if (!reward || !terminated || !truncated || !returns_acc || !ret_stats || !reward_out || !scratch || n <= 0)
+    return pfail(QX_EINVAL, "ppo_reward_normalize: bad arguments");
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  ppo::returns_acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma);
+  int rc = ppo_running_stats_update(returns_acc, 1, n, 1, ret_stats, eps, nullptr, nullptr, scratch, stream);
+  if (rc) return rc;
+  ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_reward_normalize: launch failed");
+}

@@ -461,8 +461,8 @@ extern "C" int qx_step_k(QxHandle* h, int32_t k, const float* actions_dev, float
   return launch(h, qx::MODE_STEP_INLINE, a, (cudaStream_t)stream);
 }
 
-extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
-                       float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
+extern "C" int qx_step_begin(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
+                             float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
   if (!h || !actions_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(QX_EINVAL, "qx_step: bad arguments");
   if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step: obs_stride < obs_dim");
   qx::StepArgs a{};
@@ -470,11 +470,33 @@ extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int
   a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev; a.terminal_obs = terminal_obs_dev;
   a.stats = h->stats; a.n = h->n; a.k = 1;
   if (!h->cfg.auto_reset) return launch(h, qx::MODE_STEP_INLINE, a, (cudaStream_t)stream);
-  // two launches: the step proper, then the reset of whatever finished, in full warps
   a.queue = h->queue;
-  int rc = launch(h, qx::MODE_STEP_DEFER, a, (cudaStream_t)stream);
-  if (rc) return rc;
+  return launch(h, qx::MODE_STEP_DEFER, a, (cudaStream_t)stream);
+}
+
+extern "C" int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_t obs_stride, void* stream) {
+  if (!h) return fail(QX_EINVAL, "qx_step_end: null handle");
+  if (!h->cfg.auto_reset) return QX_OK;
+  if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step_end: obs_stride < obs_dim");
+  qx::StepArgs a{};
+  a.state = h->state; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
+  a.stats = h->stats; a.queue = h->queue; a.n = h->n; a.k = 1;
   return launch(h, qx::MODE_RESET_QUEUE, a, (cudaStream_t)stream);
+}
+
+// two launches: the step proper, then the reset of whatever finished, in full warps
+extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
+                       float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
+  int rc = qx_step_begin(h, actions_dev, obs_dev, obs_dtype, obs_stride, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, stream);
+  if (rc) return rc;
+  return qx_step_end(h, obs_dev, obs_dtype, obs_stride, stream);
+}
+
+extern "C" int qx_done_queue(QxHandle* h, const uint32_t** count_dev, const uint32_t** idx_dev) {
+  if (!h || !count_dev || !idx_dev) return fail(QX_EINVAL, "qx_done_queue: bad arguments");
+  *count_dev = &h->queue->count;
+  *idx_dev = h->queue->idx;
+  return QX_OK;
 }
 
 static int ensure_staging(QxHandle* h) {

@@ -1,0 +1,374 @@
+"""On-device PPO for the batched hover env: what ``train_hover.py:40-63`` does with
+stable-baselines3 (vec env -> VecNormalize -> MlpPolicy [128,128] -> learn ->
+checkpoints), with the rollout half (policy forward, sampling, reward /
+observation normalisation, GAE) on the hand-written kernels of
+``include/ppo_b200.h`` and no host round trip per env step.
+
+The update half (loss, backward, Adam) is plain PyTorch: library GEMMs on a
+39 k-parameter network; its only collective is one all-reduce of the flattened
+gradient per optimiser step (``torch.distributed``, NCCL).
+
+Hyper-parameter names and defaults follow SB3 PPO / VecNormalize.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _lib
+from ._lib import PpoPolicy, check
+from .hover_env import QuadXSim
+
+HID, IN_PAD, HEAD_PAD = 128, 32, 16
+
+
+def _p(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class ActorCritic(nn.Module):
+    """SB3 ``MlpPolicy`` with ``net_arch=[128, 128]`` (train_hover.py:57): separate
+    tanh MLPs for the actor and the critic, state-independent ``log_std``,
+    orthogonal init (gain sqrt 2; 0.01 on the action head; 1 on the value head)."""
+
+    def __init__(self, obs_dim: int = 20, act_dim: int = 4, log_std_init: float = 0.0):
+        super().__init__()
+        assert obs_dim <= IN_PAD and act_dim <= 4
+        self.obs_dim, self.act_dim = obs_dim, act_dim
+        self.pi1, self.pi2, self.mu = nn.Linear(obs_dim, HID), nn.Linear(HID, HID), nn.Linear(HID, act_dim)
+        self.vf1, self.vf2, self.v = nn.Linear(obs_dim, HID), nn.Linear(HID, HID), nn.Linear(HID, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+        for lin, gain in ((self.pi1, math.sqrt(2)), (self.pi2, math.sqrt(2)), (self.vf1, math.sqrt(2)), (self.vf2, math.sqrt(2)),
+                          (self.mu, 0.01), (self.v, 1.0)):
+            nn.init.orthogonal_(lin.weight, gain=gain)
+            nn.init.zeros_(lin.bias)
+
+    def forward(self, obs: torch.Tensor):
+        hp = torch.tanh(self.pi2(torch.tanh(self.pi1(obs))))
+        hv = torch.tanh(self.vf2(torch.tanh(self.vf1(obs))))
+        return self.mu(hp), self.v(hv).squeeze(-1)
+
+    def evaluate_actions(self, obs: torch.Tensor, actions: torch.Tensor):
+        mean, value = self(obs)
+        std = self.log_std.exp()
+        z = (actions - mean) / std
+        logp = (-0.5 * z * z - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum().expand_as(logp)
+        return value, logp, entropy
+
+
+class PackedPolicy:
+    """bf16 copy of an ``ActorCritic`` in the layout of ``struct PpoPolicy``."""
+
+    def __init__(self, model: ActorCritic, device):
+        self.model, self.device = model, torch.device(device)
+        d = self.device
+        self.w1 = torch.zeros(2 * HID, IN_PAD, dtype=torch.bfloat16, device=d)
+        self.w2p = torch.zeros(HID, HID, dtype=torch.bfloat16, device=d)
+        self.w2v = torch.zeros(HID, HID, dtype=torch.bfloat16, device=d)
+        self.w3 = torch.zeros(HEAD_PAD, 2 * HID, dtype=torch.bfloat16, device=d)
+        self.b1 = torch.zeros(2 * HID, device=d)
+        self.b2 = torch.zeros(2 * HID, device=d)
+        self.b3 = torch.zeros(HEAD_PAD, device=d)
+        self.log_std = torch.zeros(4, device=d)
+        self.struct = PpoPolicy(self.w1.data_ptr(), self.w2p.data_ptr(), self.w2v.data_ptr(), self.w3.data_ptr(), self.b1.data_ptr(),
+                                self.b2.data_ptr(), self.b3.data_ptr(), self.log_std.data_ptr(), model.obs_dim, model.act_dim)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        """Re-pack after an optimiser step (a handful of tiny copies, stream-ordered)."""
+        m, od, ad = self.model, self.model.obs_dim, self.model.act_dim
+        self.w1[:HID, :od].copy_(m.pi1.weight)
+        self.w1[HID:, :od].copy_(m.vf1.weight)
+        self.w2p.copy_(m.pi2.weight)
+        self.w2v.copy_(m.vf2.weight)
+        self.w3[:ad, :HID].copy_(m.mu.weight)
+        self.w3[ad, HID:].copy_(m.v.weight[0])
+        self.b1[:HID].copy_(m.pi1.bias)
+        self.b1[HID:].copy_(m.vf1.bias)
+        self.b2[:HID].copy_(m.pi2.bias)
+        self.b2[HID:].copy_(m.vf2.bias)
+        self.b3[:ad].copy_(m.mu.bias)
+        self.b3[ad].copy_(m.v.bias[0])
+        self.log_std[:ad].copy_(m.log_std)
+
+
+class RunningStats:
+    """VecNormalize ``RunningMeanStd`` kept on the device: {mean[dim], var[dim], count} in fp64."""
+
+    def __init__(self, dim: int, device, eps: float = 1e-8):
+        self.dim, self.eps, self.device = dim, eps, torch.device(device)
+        self.stats = torch.zeros(2 * dim + 1, dtype=torch.float64, device=device)
+        self.stats[dim:2 * dim] = 1.0
+        self.stats[2 * dim] = 1e-4  # RunningMeanStd(epsilon=1e-4)
+        self.mean = torch.zeros(dim, device=device)
+        self.inv_std = torch.ones(dim, device=device)
+        self.scratch = torch.zeros(_lib.lib().ppo_running_stats_scratch_bytes(dim) // 8, dtype=torch.float64, device=device)
+
+    def update(self, x: torch.Tensor) -> None:
+        assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] >= self.dim and x.stride(1) == 1
+        check(_lib.lib().ppo_running_stats_update(_p(x), x.stride(0), x.shape[0], self.dim, _p(self.stats), self.eps, _p(self.mean),
+                                                  _p(self.inv_std), _p(self.scratch), _stream(self.device)))
+
+    def state_dict(self):
+        return {"stats": self.stats.clone(), "mean": self.mean.clone(), "inv_std": self.inv_std.clone()}
+
+    def load_state_dict(self, sd):
+        self.stats.copy_(sd["stats"]); self.mean.copy_(sd["mean"]); self.inv_std.copy_(sd["inv_std"])
+
+    def allreduce_(self) -> None:
+        """Merge the replicas' statistics (each saw different envs) -- optional, tiny."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        d = self.dim
+        mean, var, cnt = self.stats[:d].clone(), self.stats[d:2 * d].clone(), self.stats[2 * d].clone()
+        tot = cnt.clone()
+        dist.all_reduce(tot)
+        gmean = mean * cnt
+        dist.all_reduce(gmean)
+        gmean /= tot
+        m2 = (var + (mean - gmean) ** 2) * cnt
+        dist.all_reduce(m2)
+        self.stats[:d], self.stats[d:2 * d], self.stats[2 * d] = gmean, m2 / tot, tot / dist.get_world_size()
+        self.mean.copy_(gmean.float())
+        self.inv_std.copy_((1.0 / torch.sqrt(m2 / tot + self.eps)).float())
+
+
+def policy_forward(pol: PackedPolicy, obs: torch.Tensor, *, obs_stats: RunningStats | None = None, obs_clip: float = 10.0, seed: int = 0,
+                   row0: int = 0, step: int = 0, step_base: torch.Tensor | None = None, deterministic: bool = False,
+                   actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None) -> None:
+    """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward)."""
+    n = obs.shape[0]
+    assert obs.dtype == torch.float32 and obs.stride(1) == 1
+    check(_lib.lib().ppo_policy_forward(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(obs_stats.mean) if obs_stats else None,
+                                        _p(obs_stats.inv_std) if obs_stats else None, obs_clip, seed, row0, step, _p(step_base),
+                                        int(deterministic), _p(actions), _p(env_actions), _p(values), _p(log_probs), _p(obs_norm),
+                                        _stream(pol.device)))
+
+
+def gae(rewards, values, dones, last_values, gamma: float, lam: float, advantages, returns) -> None:
+    """``RolloutBuffer.compute_returns_and_advantage`` (ppo_gae); all [T, n] contiguous."""
+    T, n = rewards.shape
+    check(_lib.lib().ppo_gae(_p(rewards), _p(values), _p(dones), _p(last_values), T, n, gamma, lam, _p(advantages), _p(returns),
+                             _stream(rewards.device)))
+
+
+@dataclass
+class PPOConfig:
+    n_envs: int = 4096
+    n_steps: int = 64
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    learning_rate: float = 3e-4  # train_hover.py:56
+    n_epochs: int = 10
+    batch_size: int = 8192
+    norm_obs: bool = True  # train_hover.py:43
+    norm_reward: bool = True
+    clip_obs: float = 10.0
+    clip_reward: float = 10.0
+    seed: int = 0
+    use_cuda_graph: bool = True
+
+
+class RolloutEngine:
+    """``PPO.collect_rollouts`` with everything on the device: per env step
+
+        VecNormalize obs statistics -> policy forward + sampling -> env step ->
+        time-limit bootstrap -> env reset of finished episodes -> reward normalisation
+
+    and GAE at the end.  The T-step loop is captured once into a CUDA graph and
+    replayed, so a rollout costs one host call."""
+
+    def __init__(self, sim: QuadXSim, policy: PackedPolicy, cfg: PPOConfig, row0: int = 0):
+        self.sim, self.pol, self.cfg = sim, policy, cfg
+        self.lib = _lib.lib()
+        n, T, d = sim.n, cfg.n_steps, sim.device
+        od, ad = sim.obs_dim, sim.act_dim
+        self.n, self.T, self.device, self.row0 = n, T, d, row0
+        f = dict(device=d, dtype=torch.float32)
+        self.cur_obs = torch.zeros(n, od, **f)
+        self.obs = torch.zeros(T, n, od, **f)  # normalised, as seen by the policy
+        self.actions = torch.zeros(T, n, ad, **f)
+        self.env_actions = torch.zeros(n, ad, **f)
+        self.log_probs = torch.zeros(T, n, **f)
+        self.values = torch.zeros(T, n, **f)
+        self.rewards = torch.zeros(T, n, **f)
+        self.raw_reward = torch.zeros(n, **f)
+        self.dones = torch.zeros(T, n, dtype=torch.uint8, device=d)
+        self.te = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.tr = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.terminal_obs = torch.zeros(n, od, **f)
+        self.last_values = torch.zeros(n, **f)
+        self.advantages = torch.zeros(T, n, **f)
+        self.returns = torch.zeros(T, n, **f)
+        self.returns_acc = torch.zeros(n, **f)
+        self.obs_stats = RunningStats(od, d)
+        self.ret_stats = RunningStats(1, d)
+        self.step_base = torch.zeros(1, dtype=torch.int64, device=d)
+        cnt, idx = C.c_void_p(), C.c_void_p()
+        check(self.lib.qx_done_queue(sim._h, C.byref(cnt), C.byref(idx)))
+        self._q_count, self._q_idx = cnt, idx
+        self._graph = None
+        self.sim.reset(self.cur_obs)
+        # one-time kernel attribute setup must not happen inside a graph capture
+        policy_forward(self.pol, self.cur_obs, deterministic=True, values=self.last_values)
+
+    # one env step of the rollout, slot t
+    def _step(self, t: int) -> None:
+        cfg, sim, L, s = self.cfg, self.sim, self.lib, _stream(self.device)
+        stats = self.obs_stats if cfg.norm_obs else None
+        if cfg.norm_obs:
+            self.obs_stats.update(self.cur_obs)
+        policy_forward(self.pol, self.cur_obs, obs_stats=stats, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
+                       step_base=self.step_base, actions=self.actions[t], env_actions=self.env_actions, values=self.values[t],
+                       log_probs=self.log_probs[t], obs_norm=self.obs[t])
+        check(L.qx_step_begin(sim._h, _p(self.env_actions), _p(self.cur_obs), 0, self.cur_obs.stride(0), _p(self.raw_reward), _p(self.te),
+                              _p(self.tr), _p(self.terminal_obs), s))
+        if cfg.norm_reward:
+            check(L.ppo_reward_normalize(_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
+                                         self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]),
+                                         _p(self.ret_stats.scratch), s))
+        else:
+            self.rewards[t].copy_(self.raw_reward)
+            torch.bitwise_or(self.te, self.tr, out=self.dones[t])
+        # SB3: rewards[idx] += gamma * V(terminal_obs) when the time limit, not the task, ended the episode
+        check(L.ppo_bootstrap_truncated(C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
+                                        _p(stats.mean) if stats else None, _p(stats.inv_std) if stats else None, cfg.clip_obs,
+                                        self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), s))
+        check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), s))
+
+    def _rollout_body(self) -> None:
+        for t in range(self.T):
+            self._step(t)
+        stats = self.obs_stats if self.cfg.norm_obs else None
+        policy_forward(self.pol, self.cur_obs, obs_stats=stats, obs_clip=self.cfg.clip_obs, deterministic=True, values=self.last_values)
+        gae(self.rewards, self.values, self.dones, self.last_values, self.cfg.gamma, self.cfg.gae_lambda, self.advantages, self.returns)
+        self.step_base += self.T
+
+    def collect(self) -> None:
+        """Fill the rollout buffers with T x n transitions and their advantages / returns."""
+        if not self.cfg.use_cuda_graph:
+            self._rollout_body()
+            return
+        if self._graph is None:
+            st = torch.cuda.Stream(device=self.device)
+            st.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(st):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=st):
+                    self._rollout_body()
+            torch.cuda.current_stream(self.device).wait_stream(st)
+            self._graph = g
+        self._graph.replay()
+
+    @property
+    def launches_per_rollout(self) -> int:
+        per_step = 2 + 1 + 2 + 1 + (4 if self.cfg.norm_reward else 2)  # stats, forward, env step/reset, bootstrap, reward path
+        return self.T * per_step + 3
+
+
+class PPOTrainer:
+    """``PPO.learn`` (train_hover.py:47-60, with PPO instead of SAC as the north star asks)."""
+
+    def __init__(self, cfg: PPOConfig, device=None, env_cfg=None, rank: int = 0, world: int = 1):
+        self.cfg, self.rank, self.world = cfg, rank, world
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        torch.manual_seed(cfg.seed)  # identical initial weights on every rank
+        self.model = ActorCritic().to(dev)
+        self.packed = PackedPolicy(self.model, dev)
+        from ._lib import default_config
+
+        ecfg = env_cfg if env_cfg is not None else default_config()
+        ecfg.update(auto_reset=1)
+        self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=rank * cfg.n_envs, device=dev)
+        self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=rank * cfg.n_envs)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5)
+        self.num_timesteps = 0
+        self._flat_grad = None
+        self.gen = torch.Generator(device=dev).manual_seed(cfg.seed + 1000 + rank)
+
+    def _allreduce_grads(self) -> None:
+        if self.world == 1:
+            return
+        params = [p for p in self.model.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in params])  # 39 049 floats = 156 KB
+        dist.all_reduce(flat)
+        flat /= self.world
+        o = 0
+        for p in params:
+            k = p.numel()
+            p.grad.copy_(flat[o:o + k].view_as(p.grad))
+            o += k
+
+    def update(self) -> dict:
+        cfg, ro = self.cfg, self.rollout
+        N = ro.T * ro.n
+        obs = ro.obs.view(N, -1)
+        act = ro.actions.view(N, -1)
+        old_logp, adv_all, ret_all, old_v = ro.log_probs.view(N), ro.advantages.view(N), ro.returns.view(N), ro.values.view(N)
+        bs = min(cfg.batch_size, N)
+        stats = {"pg": 0.0, "vf": 0.0, "kl": 0.0, "clipfrac": 0.0}
+        n_mb = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(N, device=self.device, generator=self.gen)
+            for s in range(0, N - bs + 1, bs):
+                idx = perm[s:s + bs]
+                adv = adv_all[idx]
+                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                value, logp, entropy = self.model.evaluate_actions(obs[idx], act[idx])
+                ratio = torch.exp(logp - old_logp[idx])
+                pg = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                vf = torch.nn.functional.mse_loss(ret_all[idx], value)
+                loss = pg + cfg.vf_coef * vf - cfg.ent_coef * entropy.mean()
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads()
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                with torch.no_grad():
+                    stats["pg"] += pg.detach(); stats["vf"] += vf.detach()
+                    stats["kl"] += (old_logp[idx] - logp).mean().detach()
+                    stats["clipfrac"] += ((ratio - 1).abs() > cfg.clip_range).float().mean()
+                n_mb += 1
+        self.packed.refresh()
+        return {k: float(v) / max(n_mb, 1) for k, v in stats.items()}
+
+    def learn_iteration(self) -> dict:
+        self.rollout.collect()
+        self.num_timesteps += self.rollout.T * self.rollout.n * self.world
+        out = self.update()
+        s, l, c = self.sim.episode_stats(clear=True)
+        if self.world > 1:
+            t = torch.tensor([s, float(l), float(c)], device=self.device, dtype=torch.float64)
+            dist.all_reduce(t)
+            s, l, c = float(t[0]), float(t[1]), float(t[2])
+        out.update(ep_rew_mean=s / c if c else float("nan"), ep_len_mean=l / c if c else float("nan"), episodes=int(c),
+                   timesteps=self.num_timesteps)
+        return out
+
+    def save(self, path: str) -> None:
+        """Counterpart of model.save + env.save (train_hover.py:26-27,62-63): policy, optimiser, VecNormalize statistics."""
+        torch.save({"model": self.model.state_dict(), "opt": self.opt.state_dict(), "obs_stats": self.rollout.obs_stats.state_dict(),
+                    "ret_stats": self.rollout.ret_stats.state_dict(), "num_timesteps": self.num_timesteps, "cfg": self.cfg.__dict__}, path)
+
+    def load(self, path: str) -> None:
+        sd = torch.load(path, map_location=self.device, weights_only=False)
+        self.model.load_state_dict(sd["model"]); self.opt.load_state_dict(sd["opt"])
+        self.rollout.obs_stats.load_state_dict(sd["obs_stats"]); self.rollout.ret_stats.load_state_dict(sd["ret_stats"])
+        self.num_timesteps = sd["num_timesteps"]
+        self.packed.refresh()

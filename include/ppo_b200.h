@@ -1,0 +1,84 @@
+/*
+ * ppo_b200.h -- C-ABI of the on-device PPO rollout kernels (same library,
+ * libquadx_b200.so).  These replace, for the rollout half of PPO, the
+ * stable-baselines3 2.7.0 calls the reference's training script reaches
+ * through `model.learn` (train_hover.py:47-60; SB3 is un-vendored, see
+ * SURVEY.md 8a row X4):
+ *   ActorCriticPolicy.forward            -> ppo_policy_forward
+ *   RolloutBuffer.compute_returns_and_advantage -> ppo_gae
+ *   VecNormalize (running obs / return statistics) -> ppo_obs_stats_update, ppo_reward_normalize
+ * All pointers are device pointers on the current device; work is enqueued on
+ * `stream` (cudaStream_t as void*); return 0 / negative QX_E* like quadx_b200.h.
+ */
+#ifndef PPO_B200_H
+#define PPO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPO_HIDDEN 128   /* policy_kwargs=dict(net_arch=[128, 128]), train_hover.py:57 */
+#define PPO_IN_PAD 32    /* observation columns padded to the MMA K granularity */
+#define PPO_HEAD_PAD 16  /* action-mean columns + value column, padded to the MMA N granularity */
+
+/* Weights of the separate tanh MLPs pi / vf (SB3 MlpPolicy), bf16, PyTorch Linear layout [out][in]:
+ *   w1   [2*128][32]   rows 0..127 pi layer 1, rows 128..255 vf layer 1, input columns >= obs_dim are zero
+ *   w2p  [128][128], w2v [128][128]
+ *   w3   [16][256]     rows 0..act_dim-1: action_net over the pi half (cols 0..127),
+ *                      row act_dim: value_net over the vf half (cols 128..255), other entries zero
+ *   b1 [256], b2 [256] (pi | vf), b3 [16]  fp32;  log_std [act_dim] fp32 */
+typedef struct PpoPolicy {
+  const void* w1;
+  const void* w2p;
+  const void* w2v;
+  const void* w3;
+  const float* b1;
+  const float* b2;
+  const float* b3;
+  const float* log_std;
+  int32_t obs_dim;
+  int32_t act_dim;
+} PpoPolicy;
+
+/* ActorCriticPolicy.forward for n rows: normalise obs with (mean, inv_std, clip) when obs_mean != NULL
+ * (VecNormalize.normalize_obs), run both MLPs on the tensor cores (tcgen05, bf16 x bf16 -> fp32),
+ * sample a ~ N(mean, exp(log_std)) with Philox key (seed, row0 + row) and counter step + *step_base_dev
+ * (step_base_dev may be NULL; deterministic != 0: a = mean), and write
+ *   actions [n, act_dim] (unclipped, what PPO stores), env_actions [n, act_dim] (clipped to [-1, 1],
+ *   what the env receives), values [n], log_probs [n], obs_norm_out [n, obs_dim] (the normalised
+ *   observation the policy saw, what PPO stores).  Any output may be NULL. */
+int ppo_policy_forward(const PpoPolicy* p, const float* obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                       const float* obs_inv_std, float obs_clip, uint64_t seed, uint64_t row0, uint64_t step,
+                       const uint64_t* step_base_dev, int32_t deterministic, float* actions, float* env_actions, float* values,
+                       float* log_probs, float* obs_norm_out, void* stream);
+
+/* SB3 collect_rollouts time-limit bootstrap: for the envs listed in the done queue of the step just taken
+ * (qx_done_queue) that were truncated but not terminated, reward += gamma * V(terminal_obs). */
+int ppo_bootstrap_truncated(const PpoPolicy* p, const float* terminal_obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                            const float* obs_inv_std, float obs_clip, const uint32_t* done_count_dev, const uint32_t* done_idx_dev,
+                            const uint8_t* terminated, const uint8_t* truncated, float gamma, float* reward_inout, void* stream);
+
+/* RolloutBuffer.compute_returns_and_advantage: rewards, values, dones [T, n] (dones[t] = episode ended AT step t),
+ * last_values [n]; writes advantages, returns [T, n]. */
+int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int32_t T, int64_t n,
+            float gamma, float lam, float* advantages, float* returns, void* stream);
+
+/* VecNormalize running statistics: merge the batch moments of x [n, dim] (row stride `stride`) into
+ * stats = {mean[dim], var[dim], count} (fp64, device) with the parallel-Welford update, then refresh
+ * mean_f32[dim] / inv_std_f32[dim] = 1/sqrt(var + eps). */
+int ppo_running_stats_update(const float* x, int64_t stride, int64_t n, int32_t dim, double* stats, float eps, float* mean_f32,
+                             float* inv_std_f32, void* scratch, void* stream);
+int64_t ppo_running_stats_scratch_bytes(int32_t dim);
+
+/* VecNormalize reward path: ret = ret * gamma + r; stats over ret (dim 1); r_norm = clip(r / sqrt(var + eps), +-clip);
+ * ret = 0 where done; done_out [n] (nullable) = terminated | truncated.  `returns_acc` [n] is the per-env discounted return accumulator. */
+int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                         float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream);
+
+/* test hook: D[128, n] (fp32) = A[128, k] x B[n, k]^T with one tcgen05.mma chain (bf16 inputs) */
+int ppo_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPO_B200_H */

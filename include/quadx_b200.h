@@ -130,6 +130,15 @@ int qx_reset(QxHandle* h, const uint8_t* mask_dev, void* obs_dev, int32_t obs_dt
 int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
             float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream);
 
+/* qx_step in two halves, for callers that need the finished envs between the step and their reset (the PPO
+ * rollout bootstraps truncated episodes from terminal_obs there): qx_step_begin runs the step and queues the
+ * finished envs, qx_step_end re-creates them and writes their first observation.  qx_step == begin + end.
+ * qx_done_queue gives the device addresses of the queue (count, env indices) valid between the two calls. */
+int qx_step_begin(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
+                  float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream);
+int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_t obs_stride, void* stream);
+int qx_done_queue(QxHandle* h, const uint32_t** count_dev, const uint32_t** idx_dev);
+
 /* k consecutive qx_step in one launch with the state kept in registers
  * (physics-only benchmarking): actions_dev f32 [k, n, act_dim],
  * obs_dev f32 [k, n, obs_dim], reward_dev [k, n], terminated/truncated [k, n]. */

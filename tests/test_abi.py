@@ -32,6 +32,10 @@ def test_header_symbols_exported(built):
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/quadx_b200.h but not exported"
     assert sorted(built.EXPORTED) == names
+    pnames = _declared("ppo_b200.h")
+    for n in pnames:
+        assert hasattr(L, n), f"{n} declared in include/ppo_b200.h but not exported"
+    assert sorted(built.PPO_EXPORTED) == pnames
 
 
 def test_config_layout_and_defaults(built):
