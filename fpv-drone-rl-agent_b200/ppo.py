@@ -163,6 +163,27 @@ def gae(rewards, values, dones, last_values, gamma: float, lam: float, advantage
                              _stream(rewards.device)))
 
 
+def allreduce_gradients(params, world: int) -> None:
+    """The one collective of the PPO update: average the flattened gradient (39 049 floats = 156 KB for the
+    [128,128] hover policy) over the ranks.  Each rank holds a replica of the policy and a disjoint env shard."""
+    if world == 1:
+        return
+    params = [p for p in params if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat)
+    flat /= world
+    o = 0
+    for p in params:
+        k = p.numel()
+        p.grad.copy_(flat[o:o + k].view_as(p.grad))
+        o += k
+
+
+def shard_env_ids(rank: int, envs_per_rank: int) -> int:
+    """First global env id of a rank's contiguous shard (Philox keys are global env ids)."""
+    return rank * envs_per_rank
+
+
 @dataclass
 class PPOConfig:
     n_envs: int = 4096
@@ -295,25 +316,15 @@ class PPOTrainer:
 
         ecfg = env_cfg if env_cfg is not None else default_config()
         ecfg.update(auto_reset=1)
-        self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=rank * cfg.n_envs, device=dev)
-        self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=rank * cfg.n_envs)
+        self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev)
+        self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=shard_env_ids(rank, cfg.n_envs))
         self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5)
         self.num_timesteps = 0
         self._flat_grad = None
         self.gen = torch.Generator(device=dev).manual_seed(cfg.seed + 1000 + rank)
 
     def _allreduce_grads(self) -> None:
-        if self.world == 1:
-            return
-        params = [p for p in self.model.parameters() if p.grad is not None]
-        flat = torch.cat([p.grad.reshape(-1) for p in params])  # 39 049 floats = 156 KB
-        dist.all_reduce(flat)
-        flat /= self.world
-        o = 0
-        for p in params:
-            k = p.numel()
-            p.grad.copy_(flat[o:o + k].view_as(p.grad))
-            o += k
+        allreduce_gradients(self.model.parameters(), self.world)
 
     def update(self) -> dict:
         cfg, ro = self.cfg, self.rollout

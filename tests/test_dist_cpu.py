@@ -1,0 +1,90 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path (gradient all-reduce, merge of the
+normalisation statistics, rank handling of bench.py's reference arm).  The data path itself has no collective."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fpv_drone_rl_agent_b200 import ppo
+
+    # (1) replicas start identical, see different data, and stay identical after all-reduced steps
+    torch.manual_seed(0)
+    model = ppo.ActorCritic()
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4, eps=1e-5)
+    g = torch.Generator().manual_seed(100 + rank)
+    local_grads = None
+    for it in range(3):
+        obs, act = torch.randn(256, 20, generator=g), torch.randn(256, 4, generator=g)
+        v, logp, _ = model.evaluate_actions(obs, act)
+        loss = (v**2).mean() - logp.mean()
+        opt.zero_grad()
+        loss.backward()
+        if it == 0:
+            local_grads = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+        ppo.allreduce_gradients(model.parameters(), world)
+        if it == 0:
+            avg = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+        opt.step()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    lg = [torch.zeros_like(local_grads) for _ in range(world)]
+    dist.all_gather(lg, local_grads)
+    ok_rep = all(torch.equal(gathered[0], x) for x in gathered)
+    ok_avg = torch.allclose(avg, sum(lg) / world, atol=1e-7)
+    # (2) merge of per-rank running statistics == statistics of the pooled data
+    rs = ppo.RunningStats(3, "cpu")
+    x = torch.randn(500 + 100 * rank, 3, generator=g, dtype=torch.float64) * (1 + rank) + rank
+    rs.stats[:3], rs.stats[3:6], rs.stats[6] = x.mean(0), x.var(0, unbiased=False), float(x.shape[0])
+    xs = [torch.zeros(600, 3, dtype=torch.float64) for _ in range(world)]
+    pad = torch.zeros(600, 3, dtype=torch.float64); pad[: x.shape[0]] = x
+    dist.all_gather(xs, pad)
+    pooled = torch.cat([xs[r][: 500 + 100 * r] for r in range(world)])
+    rs.allreduce_()
+    ok_stats = torch.allclose(rs.stats[:3], pooled.mean(0), atol=1e-12) and torch.allclose(rs.stats[3:6], pooled.var(0, unbiased=False), atol=1e-12)
+    ok_ids = ppo.shard_env_ids(rank, 4096) == rank * 4096
+    q.put((rank, ok_rep, ok_avg, ok_stats, ok_ids, flat.numel()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_stats_merge_world2():
+    mp.set_start_method("spawn", force=True)
+    q = mp.get_context("spawn").Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [mp.get_context("spawn").Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    for rank, ok_rep, ok_avg, ok_stats, ok_ids, nparams in res:
+        assert ok_rep and ok_avg and ok_stats and ok_ids, (rank, ok_rep, ok_avg, ok_stats, ok_ids)
+        assert nparams == 39049  # actor 19 716 + log_std 4 + critic 19 329
+
+
+def test_reference_arm_rank_handling():
+    """bench.py --impl reference under a 2-rank launch: rank 0 prints the JSON line, rank 1 exits 0 silently."""
+    env = dict(os.environ, WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    outs = []
+    for rank in (0, 1):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1",
+                            "--cpu-envs", "256"], env=dict(env, RANK=str(rank), LOCAL_RANK=str(rank)), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    line = json.loads(outs[0])
+    assert outs[1] == ""
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0 and line["n_gpus"] == 2
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
