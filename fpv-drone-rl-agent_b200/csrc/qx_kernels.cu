@@ -9,6 +9,8 @@
 // Aviary.step()) for the envs that finished.  The 44 carried words are read
 // once as 11 coalesced float4 loads, live in registers across the sub-steps,
 // and are written back once.
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -235,15 +237,28 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       a.terminated[row] = term ? 1 : 0;
       a.truncated[row] = trunc ? 1 : 0;
       if (!(c.auto_reset && (term || trunc))) break;
-      // ---- SB3 VecEnv auto-reset + Monitor episode statistics
-      atomicAdd(&a.stats->sum_ret, (double)e.ep_ret);
-      atomicAdd(&a.stats->sum_len, (unsigned long long)e.step_count);
-      atomicAdd(&a.stats->n_done, 1ull);
-      if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, QX_OBS_DIM_HOVER, false);
-      if (MODE == MODE_STEP_DEFER) {  // hand the env to the reset kernel; it writes the next obs
-        a.queue->idx[atomicAdd(&a.queue->count, 1u)] = (unsigned int)i;
-        deferred = true;
-        break;
+      // ---- SB3 VecEnv auto-reset + Monitor episode statistics.  The lanes of the warp that finished together
+      // aggregate: one atomic per counter per warp (a mass termination -- e.g. every env hitting the floor rule on
+      // its 32nd step -- would otherwise serialise ~4 atomics per env on four L2 addresses).
+      {
+        namespace cg = cooperative_groups;
+        const auto g = cg::coalesced_threads();
+        const double sr = cg::reduce(g, (double)e.ep_ret, cg::plus<double>());
+        const unsigned long long sl = cg::reduce(g, (unsigned long long)e.step_count, cg::plus<unsigned long long>());
+        unsigned int base = 0;
+        if (g.thread_rank() == 0) {
+          atomicAdd(&a.stats->sum_ret, sr);
+          atomicAdd(&a.stats->sum_len, sl);
+          atomicAdd(&a.stats->n_done, (unsigned long long)g.size());
+          if (MODE == MODE_STEP_DEFER) base = atomicAdd(&a.queue->count, (unsigned int)g.size());
+        }
+        if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, QX_OBS_DIM_HOVER, false);
+        if (MODE == MODE_STEP_DEFER) {  // hand the env to the reset kernel; it writes the next obs
+          base = g.shfl(base, 0);
+          a.queue->idx[base + g.thread_rank()] = (unsigned int)i;
+          deferred = true;
+          break;
+        }
       }
       respawn(e, c, k0, k1);
       act[0] = act[1] = act[2] = act[3] = 0.f;  // hover.py:101

@@ -9,6 +9,6 @@ CMD="python bench.py --steps 6 --warmup 3 --envs $ENVS --no-small --no-cpu-basel
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:quadx_step_kernel -s 4 -c 2 -f -o gpurun_out/k1_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:quadx_step_kernel -s 5 -c 4 -f -o gpurun_out/k1_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/plain_$TAG.log
 ls -la gpurun_out/
