@@ -102,12 +102,12 @@ __device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int
 // MODE_RESET_QUEUE : reset of the envs queued by the preceding MODE_STEP_DEFER launch
 enum { MODE_STEP_INLINE = 0, MODE_STEP_DEFER = 1, MODE_RESET_MASK = 2, MODE_RESET_QUEUE = 3 };
 
-template <int MODE>
+template <int MODE, int TASK>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, int64_t i);
 
 constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
 
-template <int MODE>
+template <int MODE, int TASK>
 __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
   if (MODE == MODE_RESET_QUEUE) {
     // Every block reads the count before any block can zero it: the zeroing
@@ -119,17 +119,18 @@ __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const
       if (atomicAdd(&a.queue->ticket, 1u) == gridDim.x - 1) { a.queue->count = 0u; a.queue->ticket = 0u; }
     }
     for (unsigned int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock)
-      run_env<MODE>(c, a, (int64_t)a.queue->idx[t]);
+      run_env<MODE, TASK>(c, a, (int64_t)a.queue->idx[t]);
   } else {
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.n) return;
     if (MODE == MODE_RESET_MASK && a.mask && !a.mask[i]) return;
-    run_env<MODE>(c, a, i);
+    run_env<MODE, TASK>(c, a, i);
   }
 }
 
-template <int MODE>
+template <int MODE, int TASK>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
+  constexpr int OBS_DIM = TASK == QX_TASK_HOVER ? QX_OBS_DIM_HOVER : QX_OBS_DIM_YAW;
   constexpr bool RESET_ONLY = MODE == MODE_RESET_MASK || MODE == MODE_RESET_QUEUE;
   Env e;
   load_env(e, a.state, a.n, i);
@@ -146,7 +147,7 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       respawn(e, c, k0, k1);
       nsub = c.n_sub_reset;
     } else {
-      if (c.task == QX_TASK_HOVER) {
+      if (TASK == QX_TASK_HOVER) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.actions) + row);
         act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
         sp[0] = act[0] * c.act_scale[0];  // hover.py:337-341
@@ -154,31 +155,47 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
         sp[2] = act[2] * c.act_scale[2];
         sp[3] = 0.5f * (act[3] + 1.f);
       } else {
-        act[0] = __ldg(a.actions + row);  // yaw.py:105-122: roll = pitch = 0, throttle = -1
+        act[0] = __ldg(a.actions + row);  // yaw.py:105-122: roll = pitch = 0, yaw * -30, throttle (-1 + 1) / 2 = 0
         sp[2] = act[0] * c.act_scale[2];
+        e.pa[0] = e.pa[1]; e.pa[1] = e.pa[2]; e.pa[2] = e.pa[3]; e.pa[3] = act[0];  // yaw.py:108 action_history.append
       }
-      nsub = (e.flags & (F_TERM | F_TRUNC)) ? 0 : c.n_sub_step;  // hover.py:347-348
+      nsub = (TASK == QX_TASK_HOVER && (e.flags & (F_TERM | F_TRUNC))) ? 0 : c.n_sub_step;  // hover.py:347-348; yaw.py:126 always steps
     }
     const bool live = RESET_ONLY || nsub > 0 || c.n_sub_step == 0;
-    float obs[QX_OBS_DIM_HOVER];
+    float obs[OBS_DIM];
     bool deferred = false;
 
     while (true) {
       // ---- Aviary.step() x ratio: control on every ctrl_every-th sub-step
       float pwm[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t stream = phase ? STREAM_RESET : STREAM_STEP;
-      uint4 bits = make_uint4(0u, 0u, 0u, 0u);
-      for (int j = 0, cc = 0; j < nsub; ++j) {
-        if (cc == 0) control_update(e, c, sp, pwm);
-        if (++cc == c.ctrl_every) cc = 0;
-        float nz[4] = {0.f, 0.f, 0.f, 0.f};
-        if (c.noise) {  // one Philox4x32-10 call feeds two sub-steps
-          if ((j & 1) == 0) bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
-          normal4((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, nz);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) nz[m] *= c.noise_ratio;
+      if (c.ctrl_every == 2 && (nsub & 1) == 0) {
+        // default scheduling (control_hz = physics_hz / 2): one rate-PID update and one Philox call per
+        // Aviary.step(), then its two physics sub-steps
+        for (int j = 0; j < nsub; j += 2) {
+          control_update(e, c, sp, pwm);
+          float nz[4] = {0.f, 0.f, 0.f, 0.f};
+          uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+          if (c.noise) {
+            bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
+            normal4_scaled(bits.x, bits.y, c.noise_k, nz);
+          }
+          physics_substep(e, c, pwm, nz, false);
+          if (c.noise) normal4_scaled(bits.z, bits.w, c.noise_k, nz);
+          physics_substep(e, c, pwm, nz, j + 2 == nsub);
         }
-        physics_substep(e, c, pwm, nz);
+      } else {
+        uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0, cc = 0; j < nsub; ++j) {
+          if (cc == 0) control_update(e, c, sp, pwm);
+          if (++cc == c.ctrl_every) cc = 0;
+          float nz[4] = {0.f, 0.f, 0.f, 0.f};
+          if (c.noise) {  // one Philox4x32-10 call feeds two sub-steps
+            if ((j & 1) == 0) bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
+            normal4_scaled((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, c.noise_k, nz);
+          }
+          physics_substep(e, c, pwm, nz, j + 1 == nsub);
+        }
       }
       // ---- compute_attitude / compute_state, hover.py:224-272
       float er, ep, ey;
@@ -194,18 +211,47 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       d1 = d1 - two_pi * floorf(d1 * (1.f / two_pi)) - pi;
       d2 = d2 - two_pi * floorf(d2 * (1.f / two_pi)) - pi;
       bool vis;
-      float cx, cy, area, ratio;
-      vision(e, c, vis, cx, cy, area, ratio);
-      if (c.task == QX_TASK_HOVER) {
+      float cx, cy, area = 0.f, ratio = 0.f;
+      if (TASK == QX_TASK_HOVER) {
+        vision(e, c, vis, cx, cy, area, ratio);
         obs[0] = d0 * c.inv_agent_dt; obs[1] = d1 * c.inv_agent_dt; obs[2] = d2 * c.inv_agent_dt;
         euler_to_quat(er, ep, ey, obs[3], obs[4], obs[5], obs[6]);  // hover.py:233
         obs[7] = cx; obs[8] = cy; obs[9] = e.pcx; obs[10] = e.pcy;
         obs[11] = area; obs[12] = e.parea; obs[13] = vis ? 1.f : 0.f; obs[14] = ratio; obs[15] = e.pratio;
         obs[16] = act[0]; obs[17] = act[1]; obs[18] = act[2]; obs[19] = act[3];
+        e.pcx = cx; e.pcy = cy; e.parea = area; e.pratio = ratio;  // hover.py:270-272
+      } else {
+        // yaw.py:57-74: [euler / pi (3) | sphere centre (2) | angular velocity (3) | last 4 yaw actions (4)].  The
+        // reference's sphere detector and calculate_angular_velocity are missing; declared stand-ins: the analytic
+        // projection of the sphere centre, and the wrapped Euler finite difference of hover.py:228-230 scaled by the
+        // 30 rad/s command range into the Box(-1, 1) of yaw.py:41-45.
+        vision_point(e, c, vis, cx, cy);
+        const float k = c.inv_agent_dt * (1.f / 30.f);
+        obs[0] = er * (1.f / pi); obs[1] = ep * (1.f / pi); obs[2] = ey * (1.f / pi);
+        obs[3] = cx; obs[4] = cy;
+        obs[5] = clampf(d0 * k, -1.f, 1.f); obs[6] = clampf(d1 * k, -1.f, 1.f); obs[7] = clampf(d2 * k, -1.f, 1.f);
+        obs[8] = e.pa[0]; obs[9] = e.pa[1]; obs[10] = e.pa[2]; obs[11] = e.pa[3];
+        e.pcx = cx; e.pcy = cy;
       }
-      e.pcx = cx; e.pcy = cy; e.parea = area; e.pratio = ratio;  // hover.py:270-272
       if (phase == 1) break;
 
+      if (TASK == QX_TASK_YAW) {
+        // ---- yaw.py:138-149.  calculate_reward is missing from the reference; declared stand-in:
+        // keep the sphere horizontally centred, 1 - |cx| when seen else -1, minus 0.05 |a_t - a_(t-1)|.
+        uint32_t fl = e.flags;
+        if (e.step_count >= c.max_steps) fl |= F_TRUNC;  // yaw.py:138-139
+        if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB | F_TERM;  // yaw.py:141-143
+        const float reward = (vis ? 1.f - fabsf(cx) : -1.f) - 0.05f * fabsf(e.pa[3] - e.pa[2]);
+        e.flags = fl;
+        e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;
+        e.step_count += 1;  // yaw.py:145
+        e.rng_ctr += 1u;
+        e.ep_ret += reward;
+        a.reward[row] = reward;
+        a.terminated[row] = (fl & F_TERM) ? 1 : 0;
+        a.truncated[row] = (fl & F_TRUNC) ? 1 : 0;
+        if (!(c.auto_reset && (fl & (F_TERM | F_TRUNC)))) break;
+      } else {
       // ---- compute_term_trunc_reward, hover.py:274-332
       float reward = -0.1f;  // hover.py:343
       uint32_t fl = e.flags;
@@ -237,6 +283,7 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       a.terminated[row] = term ? 1 : 0;
       a.truncated[row] = trunc ? 1 : 0;
       if (!(c.auto_reset && (term || trunc))) break;
+      }
       // ---- SB3 VecEnv auto-reset + Monitor episode statistics.  The lanes of the warp that finished together
       // aggregate: one atomic per counter per warp (a mass termination -- e.g. every env hitting the floor rule on
       // its 32nd step -- would otherwise serialise ~4 atomics per env on four L2 addresses).
@@ -252,7 +299,7 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
           atomicAdd(&a.stats->n_done, (unsigned long long)g.size());
           if (MODE == MODE_STEP_DEFER) base = atomicAdd(&a.queue->count, (unsigned int)g.size());
         }
-        if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, QX_OBS_DIM_HOVER, false);
+        if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, OBS_DIM, false);
         if (MODE == MODE_STEP_DEFER) {  // hand the env to the reset kernel; it writes the next obs
           base = g.shfl(base, 0);
           a.queue->idx[base + g.thread_rank()] = (unsigned int)i;
@@ -337,14 +384,20 @@ extern "C" int qx_default_config(int32_t task, QxConfig* c) {
   c->agent_dt = 0.025f; c->flight_dome_size = 3.0f; c->floor_threshold = 0.1f;
   c->target_area = 0.013f; c->target_ratio = 1.53f;
   c->action_scale[0] = 30.f; c->action_scale[1] = 30.f; c->action_scale[2] = -30.f;
-  c->spawn_yaw_noise = task == QX_TASK_YAW ? 3.14159265f : 0.f;
+  c->spawn_yaw_noise = task == QX_TASK_YAW ? 3.14159265f : 0.f;  /* yaw.py:79 U(-pi, pi) */
+  if (task == QX_TASK_YAW) {
+    /* main.py:8-23 / yaw.py: default PyFlyt camera (20 deg up), red sphere at (2, 0, 1), one Aviary.step per env step */
+    c->cam_tilt_up_deg = 20.f;
+    c->panel[0] = 2.f; c->panel[1] = 0.f; c->panel[2] = 1.f;
+    c->agent_dt = 1.0f / 120.f;
+  }
   c->render = 0; c->auto_reset = 1; c->noise = 1;
   return QX_OK;
 }
 
 static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevConfig* d) {
   memset(d, 0, sizeof(*d));
-  if (s.task != QX_TASK_HOVER) return fail(QX_EINVAL, "qx_create: only QX_TASK_HOVER is implemented in this build");
+  if (s.task != QX_TASK_HOVER && s.task != QX_TASK_YAW) return fail(QX_EINVAL, "qx_create: unknown task");
   if (!(s.physics_hz > 0) || !(s.control_hz > 0) || s.control_hz > s.physics_hz) return fail(QX_EINVAL, "qx_create: bad rates");
   const int per = (int)(s.physics_hz / s.control_hz);
   d->task = s.task;
@@ -354,9 +407,11 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   d->max_steps = s.max_steps; d->floor_grace = s.floor_grace_steps; d->render = s.render; d->auto_reset = s.auto_reset;
   d->noise = (s.noise && s.noise_ratio != 0.f) ? 1 : 0;
   d->state_stale = s.state_stale; d->gyro = s.gyro;
-  d->obs_dim = QX_OBS_DIM_HOVER; d->act_dim = QX_ACT_DIM_HOVER;
+  d->obs_dim = s.task == QX_TASK_HOVER ? QX_OBS_DIM_HOVER : QX_OBS_DIM_YAW;
+  d->act_dim = s.task == QX_TASK_HOVER ? QX_ACT_DIM_HOVER : QX_ACT_DIM_YAW;
   const double h = 1.0 / s.physics_hz, T = 1.0 / s.control_hz;
-  d->h = (float)h; d->lag_alpha = (float)(h / s.tau); d->noise_ratio = s.noise_ratio;
+  d->h = (float)h; d->lag_alpha = (float)(h / s.tau); d->one_m_alpha = (float)(1.0 - h / s.tau); d->noise_ratio = s.noise_ratio;
+  d->noise_k = (float)(-2.0 * M_LN2 * (double)s.noise_ratio * (double)s.noise_ratio);
   d->thrust_k = (float)(s.total_thrust / 4.0); d->pwm_idle = s.pwm_idle;
   const double max_rpm2 = s.total_thrust / (4.0 * s.thrust_coef);
   for (int m = 0; m < 4; ++m) {
@@ -440,18 +495,24 @@ extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0
 extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
 extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
 
-static int launch(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
+template <int TASK>
+static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((h->n + qx::kBlock - 1) / qx::kBlock);
   switch (mode) {
-    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     default: {
       const unsigned g = grid < (unsigned)qx::kResetQueueBlocks ? grid : (unsigned)qx::kResetQueueBlocks;
-      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE><<<g, qx::kBlock, 0, s>>>(h->dev, a);
+      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE, TASK><<<g, qx::kBlock, 0, s>>>(h->dev, a);
       break;
     }
   }
+}
+
+static int launch(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
+  if (h->dev.task == QX_TASK_HOVER) launch_task<QX_TASK_HOVER>(h, mode, a, s);
+  else launch_task<QX_TASK_YAW>(h, mode, a, s);
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;

@@ -22,7 +22,7 @@ namespace qx {
 struct DevConfig {
   int32_t task, n_sub_step, n_sub_reset, ctrl_every, max_steps, floor_grace, render, auto_reset, noise,
       state_stale, gyro, obs_dim, act_dim;
-  float h, lag_alpha, noise_ratio, thrust_k, pwm_idle;
+  float h, lag_alpha, one_m_alpha, noise_ratio, noise_k, thrust_k, pwm_idle;  // noise_k = -2 ln2 noise_ratio^2
   float torque_k[4], mx[4], my[4], map[16];
   float drag_c, drag_pqr, kp[3], kiT[3], kd_T[3], lim[3];
   float inv_mass, g, I[3], invI[3], vmax, floor_z;
@@ -122,15 +122,20 @@ __device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float((x >> 
 __device__ __forceinline__ float u01_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
 __device__ __forceinline__ float u01_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
 
-// 4 x N(0,1) from two 32-bit words, like oracle normal4(): each word is one
-// Box-Muller pair (low half -> radius, high half -> angle).
-__device__ __forceinline__ void normal4(uint32_t w0, uint32_t w1, float n[4]) {
-  const float ra = fsqrt(-1.38629436112f * __log2f(u01_lo16(w0)));  // sqrt(-2 ln u)
-  const float rb = fsqrt(-1.38629436112f * __log2f(u01_lo16(w1)));
-  // angle 2 pi u shifted by -pi into the accurate MUFU range: sin(t - pi) = -sin t, cos(t - pi) = -cos t
-  const float ta = fmaf(6.28318530718f, u01_hi16(w0), -3.14159265359f);
-  const float tb = fmaf(6.28318530718f, u01_hi16(w1), -3.14159265359f);
-  n[0] = -ra * __cosf(ta); n[1] = -ra * __sinf(ta); n[2] = -rb * __cosf(tb); n[3] = -rb * __sinf(tb);
+// 16-bit field in the top of the mantissa of [1,2): m = 1 + k 2^-16
+__device__ __forceinline__ float m12_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u); }
+__device__ __forceinline__ float m12_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u); }
+
+// 4 x noise_ratio * N(0,1) from two 32-bit words, like oracle normal4(): each word is one Box-Muller pair
+// (low half -> radius, high half -> angle).  u = m - (1 - 2^-17) in (0,1);  scale folded into the radius:
+// noise_ratio sqrt(-2 ln u) = sqrt(noise_k lg2 u);  angle 2 pi u - pi = 2 pi m - (2 pi (1 - 2^-17) + pi), and
+// sin(t - pi) = -sin t, cos(t - pi) = -cos t keeps the MUFU argument in [-pi, pi].
+__device__ __forceinline__ void normal4_scaled(uint32_t w0, uint32_t w1, float noise_k, float n[4]) {
+  const float ra = -fsqrt(noise_k * __log2f(m12_lo16(w0) - 0.99999237060546875f));
+  const float rb = -fsqrt(noise_k * __log2f(m12_lo16(w1) - 0.99999237060546875f));
+  const float ta = fmaf(6.28318530718f, m12_hi16(w0), -9.42473002f);
+  const float tb = fmaf(6.28318530718f, m12_hi16(w1), -9.42473002f);
+  n[0] = ra * __cosf(ta); n[1] = ra * __sinf(ta); n[2] = rb * __cosf(tb); n[3] = rb * __sinf(tb);
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
@@ -138,6 +143,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 // ---------------------------------------------------------------------------
 // PyFlyt QuadX.update_control, mode 0: rate PID -> motor mix -> saturation
 // ---------------------------------------------------------------------------
+// pwm[] returns lag_alpha * pwm (see the end of the function)
 __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const float sp[4], float pwm[4]) {
   float cmd[4];
 #pragma unroll
@@ -164,6 +170,9 @@ __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const
 #pragma unroll
     for (int m = 0; m < 4; ++m) pwm[m] = fmaf(1.0f - pwm[m], k, pwm[m]);
   }
+  // the motor lag thr += alpha (pwm - thr) is applied as thr (1 - alpha) + (alpha pwm): hoist alpha pwm out of the sub-steps
+#pragma unroll
+  for (int m = 0; m < 4; ++m) pwm[m] *= c.lag_alpha;
 }
 
 // ---------------------------------------------------------------------------
@@ -177,12 +186,12 @@ __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const
 // (Bullet's +-100 clamp acts on world components; here on body components --
 // the two differ only beyond 100 rad/s.)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float pwm[4], const float nz[4]) {
+__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float apwm[4], const float nz[4], const bool last) {
   // motors: first-order lag, multiplicative noise, thrust and torques
   float fz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    float t = fmaf(c.lag_alpha, pwm[m] - e.thr[m], e.thr[m]);
+    float t = fmaf(e.thr[m], c.one_m_alpha, apwm[m]);
     t = fmaf(nz[m], t, t);                // nz already scaled by noise_ratio
     e.thr[m] = t;
     const float rr = fabsf(t) * t;        // rpm |rpm| / max_rpm^2
@@ -213,7 +222,7 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
     e.svb[0] = r00 * e.vx + r10 * e.vy + r20 * e.vz;
     e.svb[1] = r01 * e.vx + r11 * e.vy + r21 * e.vz;
     e.svb[2] = r02 * e.vx + r12 * e.vy + r22 * e.vz;
-    e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
+    if (last) { e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.px; e.spy = e.py; e.spz = e.pz; }  // only the final pose is read
   }
   // angular half, body frame
   float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -221,14 +230,19 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
     const float lx = c.I[0] * e.wx, ly = c.I[1] * e.wy, lz = c.I[2] * e.wz;
     gx = e.wy * lz - e.wz * ly; gy = e.wz * lx - e.wx * lz; gz = e.wx * ly - e.wy * lx;
   }
-  e.wx = clampf(fmaf(c.h * c.invI[0], tx - gx, e.wx), -c.vmax, c.vmax);
-  e.wy = clampf(fmaf(c.h * c.invI[1], ty - gy, e.wy), -c.vmax, c.vmax);
-  e.wz = clampf(fmaf(c.h * c.invI[2], tz - gz, e.wz), -c.vmax, c.vmax);
+  e.wx = fmaf(c.h * c.invI[0], tx - gx, e.wx);
+  e.wy = fmaf(c.h * c.invI[1], ty - gy, e.wy);
+  e.wz = fmaf(c.h * c.invI[2], tz - gz, e.wz);
   // linear half, world frame: semi-implicit Euler
   const float hm = c.h * c.inv_mass;
-  e.vx = clampf(fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx), -c.vmax, c.vmax);
-  e.vy = clampf(fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy), -c.vmax, c.vmax);
-  e.vz = clampf(fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.h * c.g, -c.vmax, c.vmax);
+  e.vx = fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx);
+  e.vy = fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy);
+  e.vz = fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.h * c.g;
+  // btMultiBody's +-max_coord_vel clamp: one max over the six components, the clamp itself is a cold path
+  if (fmaxf(fmaxf(fmaxf(fabsf(e.vx), fabsf(e.vy)), fmaxf(fabsf(e.vz), fabsf(e.wx))), fmaxf(fabsf(e.wy), fabsf(e.wz))) > c.vmax) {
+    e.vx = clampf(e.vx, -c.vmax, c.vmax); e.vy = clampf(e.vy, -c.vmax, c.vmax); e.vz = clampf(e.vz, -c.vmax, c.vmax);
+    e.wx = clampf(e.wx, -c.vmax, c.vmax); e.wy = clampf(e.wy, -c.vmax, c.vmax); e.wz = clampf(e.wz, -c.vmax, c.vmax);
+  }
   e.px = fmaf(c.h, e.vx, e.px);
   e.py = fmaf(c.h, e.vy, e.py);
   e.pz = fmaf(c.h, e.vz, e.pz);
@@ -264,7 +278,7 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
     e.svb[0] = a00 * e.vx + a10 * e.vy + a20 * e.vz;
     e.svb[1] = a01 * e.vx + a11 * e.vy + a21 * e.vz;
     e.svb[2] = a02 * e.vx + a12 * e.vy + a22 * e.vz;
-    e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
+    if (last) { e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.px; e.spy = e.py; e.spz = e.pz; }
   }
 }
 
@@ -357,6 +371,36 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
   ratio = ok ? wpx * frcp(hpx) : 0.f;
 }
 
+// yaw task: centre of the red sphere (main.py:16-23, radius 0.1 at (2,0,1); yaw.py:63 detect_red_sphere_center is
+// missing from the reference) projected through the same FPV camera model; (0,0) when it is not in the image.
+__device__ __forceinline__ void vision_point(const Env& e, const DevConfig& c, bool& vis, float& cx, float& cy) {
+  const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
+  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
+  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
+  float sph = 0.f, cph = 1.f;
+  if (fabsf(r20) < 0.99999f) {
+    const float inv = frsqrt(r21 * r21 + r22 * r22);
+    sph = r21 * inv; cph = r22 * inv;
+  }
+  const float sd = c.cam_sd, cd = c.cam_cd;
+  const float fx = cd, fy = sd * sph, fzz = sd * cph;
+  const float ux = -sd * cph, uy = sph * cph * (cd - 1.f), uz = fmaf(sph, sph, cd * cph * cph);
+  const float rx = fy * uz - fzz * uy, ry = fzz * ux - fx * uz, rz = fx * uy - fy * ux;
+  const float dx = c.panel[0] - e.px, dy = c.panel[1] - e.py, dz = c.panel[2] - e.pz;
+  const float bx = r00 * dx + r10 * dy + r20 * dz - c.cam_off[0];
+  const float by = r01 * dx + r11 * dy + r21 * dz - c.cam_off[1];
+  const float bz = r02 * dx + r12 * dy + r22 * dz - c.cam_off[2];
+  const float depth = fx * bx + fy * by + fzz * bz;
+  const float k1 = c.inv_tan * frcp(fmaxf(depth, 1e-9f));
+  const float px = fmaf((rx * bx + ry * by + rz * bz) * k1, c.half_res, c.half_res);
+  const float py = fmaf(-(ux * bx + uy * by + uz * bz) * k1, c.half_res, c.half_res);
+  vis = depth > c.cam_near && px >= 0.f && px <= c.res && py >= 0.f && py <= c.res;
+  cx = vis ? fmaf(px, c.inv_half_res, -1.f) : 0.f;
+  cy = vis ? fmaf(py, c.inv_half_res, -1.f) : 0.f;
+}
+
 // Aviary(start_pos, start_orn) + Aviary.reset() + the env bookkeeping of
 // hover.py:98-107.  prev_action is deliberately left alone (hover.py:31,357).
 __device__ __forceinline__ void respawn(Env& e, const DevConfig& c, uint32_t k0, uint32_t k1) {
@@ -389,6 +433,7 @@ __device__ __forceinline__ void respawn(Env& e, const DevConfig& c, uint32_t k0,
   e.step_count = 0;
   e.pcx = e.pcy = e.parea = e.pratio = 0.f;
   e.ep_ret = 0.f;
+  if (c.task == 1) { e.pa[0] = e.pa[1] = e.pa[2] = e.pa[3] = 0.f; }  // yaw.py:90-92 clears the action history
 }
 
 }  // namespace qx
