@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-envs", type=int, default=8192, help="envs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the configs[1] (4096 envs) side measurements")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO rollout side measurements (metric M2)")
     return ap.parse_args()
 
 
@@ -281,6 +282,12 @@ def main_ours(args):
         }
         if world == 1 and not args.no_small:
             line["hover_4096"] = small_config(pkg, dev)
+        if world == 1 and not args.no_ppo:
+            sim.close()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_ppo
+
+            line["ppo"] = bench_ppo.measure(131072, 32)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(args.cpu_envs, 40, 2, budget_s=20.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}

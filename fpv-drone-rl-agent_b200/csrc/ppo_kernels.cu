@@ -61,28 +61,36 @@ __global__ void __launch_bounds__(128) test_gemm_kernel(const __nv_bfloat16* __r
 
 
 // ---------------------------------------------------------------------------
-// K2: ActorCriticPolicy.forward.  One CTA = 128 threads = one tile of 128 rows
-// (thread == row), persistent over tiles.  All weights stay resident in shared
-// memory in the interleaved K-major layout; per tile
-//   L1  X[128x32]  . W1^T [32x256]        -> TMEM cols [0,256)   (pi | vf)
-//   L2  H1p[128x128] . W2p^T, H1v . W2v^T -> TMEM cols [0,128), [128,256)
-//   L3  [H2p|H2v][128x256] . W3^T [256x16] -> TMEM cols [0,16)   (mean0..3, value)
-// with the bias + tanh + bf16 epilogues run by the same 128 threads straight
-// out of TMEM (tcgen05.ld 32x32b: thread t of warp w owns accumulator row
-// 32w + t) into the next layer's A operand in shared memory.
+// K2: ActorCriticPolicy.forward.  Persistent CTAs, one per SM, 512 threads = two
+// independent "slots" of 256 threads; each slot walks its own sequence of
+// 128-row tiles, so while one slot waits for its tcgen05.mma chain the other
+// runs its bias + tanh epilogue (the tensor pipe and the MUFU pipe overlap
+// without any explicit software pipeline).  All weights stay resident in
+// shared memory in the interleaved K-major layout; per tile and slot
+//   [L1p]      X[128x32]    . W1p^T          -> acc (TMEM 128 cols)
+//   [L2p]      H1p[128x128] . W2p^T          -> acc
+//   [L3p, L1v] H2p . W3p^T -> out (16 cols: action means);  X . W1v^T -> acc
+//   [L2v]      H1v . W2v^T                   -> acc
+//   [L3v]      H2v . W3v^T  accumulated into out (column act_dim: value)
+// Each [..] is one commit -> mbarrier wait; after it the slot's 8 warps read
+// the accumulator with tcgen05.ld 32x32b (warp w: TMEM lanes 32 (w % 4).., 64
+// columns (w / 4)), add the bias, tanh, pack to bf16 and store the next A
+// operand.  thread == accumulator row in the final epilogue (sampling).
 // ---------------------------------------------------------------------------
 constexpr int kHid = PPO_HIDDEN, kIn = PPO_IN_PAD, kHead = PPO_HEAD_PAD;
-constexpr uint32_t kSmW1 = 0;                                  // [4][256][16 B]
+constexpr int kSlots = 2, kSlotThreads = 256, kFwdThreads = kSlots * kSlotThreads;
+constexpr uint32_t kSmW1 = 0;                                  // [4][256][16 B]   rows 0..127 pi, 128..255 vf
 constexpr uint32_t kSmW2p = kSmW1 + 2 * kHid * kIn * 2;        // [16][128][16 B]
 constexpr uint32_t kSmW2v = kSmW2p + kHid * kHid * 2;
-constexpr uint32_t kSmW3 = kSmW2v + kHid * kHid * 2;           // [32][16][16 B]
-constexpr uint32_t kSmX = kSmW3 + kHead * 2 * kHid * 2;        // [4][128][16 B]
-constexpr uint32_t kSmH = kSmX + 128 * kIn * 2;                // [32][128][16 B]
-constexpr uint32_t kSmB1 = kSmH + 128 * 2 * kHid * 2;          // 256 f32
+constexpr uint32_t kSmW3 = kSmW2v + kHid * kHid * 2;           // [32][16][16 B]   K chunks 0..15 pi half, 16..31 vf half
+constexpr uint32_t kSmSlot = kSmW3 + kHead * 2 * kHid * 2;     // per slot: X [4][128][16 B] then H [16][128][16 B]
+constexpr uint32_t kSlotX = 0, kSlotH = 128 * kIn * 2, kSlotBytes = kSlotH + 128 * kHid * 2;
+constexpr uint32_t kSmB1 = kSmSlot + kSlots * kSlotBytes;      // 256 f32
 constexpr uint32_t kSmB2 = kSmB1 + 2 * kHid * 4;
 constexpr uint32_t kSmB3 = kSmB2 + 2 * kHid * 4;               // 16 f32
 constexpr uint32_t kSmNorm = kSmB3 + kHead * 4;                // mean[32], inv_std[32]
 constexpr uint32_t kSmTotal = kSmNorm + 2 * kIn * 4;
+constexpr uint32_t kTmemCols = 512, kSlotTmem = 256, kTmemOut = 128;  // per slot: acc cols [0,128), out cols [128,144)
 
 struct FwdArgs {
   PpoPolicy p;
@@ -125,13 +133,18 @@ __device__ __forceinline__ uint32_t tanh_pack_bf16x2(float lo, float hi) {
 #endif
 }
 
-// bias + tanh + bf16 of 256 accumulator columns of this thread's row -> sH chunks
-__device__ __forceinline__ void hidden_epilogue(uint32_t trow, const float* __restrict__ bias, uint8_t* sH, uint32_t row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < 2 * kHid; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(trow + c0, r);
-    tmem_ld_wait();
+__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(kSlotThreads) : "memory"); }
+
+// bias + tanh + bf16 of this warp's 64 accumulator columns of this thread's row -> H chunks (A operand of the next layer)
+__device__ __forceinline__ void hidden_epilogue(uint32_t tacc, const float* __restrict__ bias, uint8_t* sH, uint32_t row, int col0) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(tacc + col0, r0);
+  tmem_ld32(tacc + col0 + 32, r1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t* r = half ? r1 : r0;
+    const int c0 = col0 + 32 * half;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 v;
@@ -145,143 +158,174 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t trow, const float* __re
   }
 }
 
-__global__ void __launch_bounds__(128, 1) policy_forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const FwdArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[kSlots];
   __shared__ uint32_t tmem_slot;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x;
+  const int slot = tid / kSlotThreads;
+  const uint32_t st = tid % kSlotThreads, swarp = st >> 5, lane = tid & 31;   // thread / warp within the slot
+  const uint32_t erow = (swarp & 3) * 32 + lane;   // accumulator row this thread reads in the epilogues
+  const int ecol0 = (int)(swarp >> 2) * 64;        // and its 64 columns
+  const uint32_t xrow = st & 127, xh = st >> 7;    // X-tile staging: row, pair of 8-column chunks
   const int obs_dim = a.p.obs_dim, act_dim = a.p.act_dim;
-  // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barrier
-  stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, 128);
-  stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, 128);
-  stage_weight(smem + kSmW2v, (const __nv_bfloat16*)a.p.w2v, kHid, kHid, tid, 128);
-  stage_weight(smem + kSmW3, (const __nv_bfloat16*)a.p.w3, kHead, 2 * kHid, tid, 128);
+  // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barriers
+  stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, kFwdThreads);
+  stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, kFwdThreads);
+  stage_weight(smem + kSmW2v, (const __nv_bfloat16*)a.p.w2v, kHid, kHid, tid, kFwdThreads);
+  stage_weight(smem + kSmW3, (const __nv_bfloat16*)a.p.w3, kHead, 2 * kHid, tid, kFwdThreads);
   float* sB1 = reinterpret_cast<float*>(smem + kSmB1);
   float* sB2 = reinterpret_cast<float*>(smem + kSmB2);
   float* sB3 = reinterpret_cast<float*>(smem + kSmB3);
   float* sMean = reinterpret_cast<float*>(smem + kSmNorm);
   float* sInv = sMean + kIn;
-  for (int j = tid; j < 2 * kHid; j += 128) { sB1[j] = a.p.b1[j]; sB2[j] = a.p.b2[j]; }
+  if (tid < 2 * kHid) { sB1[tid] = a.p.b1[tid]; sB2[tid] = a.p.b2[tid]; }
   if (tid < kHead) sB3[tid] = a.p.b3[tid];
   if (tid < kIn) {
     sMean[tid] = (a.obs_mean && (int)tid < obs_dim) ? a.obs_mean[tid] : 0.f;
     sInv[tid] = (a.obs_inv_std && (int)tid < obs_dim) ? a.obs_inv_std[tid] : 1.f;
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (tid < 32) tmem_alloc(&tmem_slot, kTmemCols);
+  if (tid == 0) {
+    for (int sidx = 0; sidx < kSlots; ++sidx) mbar_init(&bars[sidx], 1);
+    mbar_fence_init();
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tbase = tmem_slot;
-  const uint32_t trow = tbase + ((warp * 32u) << 16);
-  const uint32_t sX = smem_u32(smem + kSmX), sH = smem_u32(smem + kSmH);
+  uint64_t* bar = &bars[slot];
+  const uint32_t tacc = tmem_slot + slot * kSlotTmem;             // MMA destination (lane field 0)
+  const uint32_t tacc_row = tacc + (((swarp & 3) * 32u) << 16);   // this warp's lane quarter
+  uint8_t* slotp = smem + kSmSlot + slot * kSlotBytes;
+  const uint32_t sX = smem_u32(slotp + kSlotX), sH = smem_u32(slotp + kSlotH);
   const uint32_t sW1 = smem_u32(smem + kSmW1), sW2p = smem_u32(smem + kSmW2p), sW2v = smem_u32(smem + kSmW2v), sW3 = smem_u32(smem + kSmW3);
   constexpr uint32_t LBO_ACT = 128 * 16, LBO_W1 = 2 * kHid * 16, LBO_W2 = kHid * 16, LBO_W3 = kHead * 16;
+  const uint32_t idesc_h = make_idesc_bf16(128, kHid), idesc_o = make_idesc_bf16(128, kHead);
   uint32_t phase = 0;
   const int64_t n_rows = a.gather_idx ? (int64_t)*a.gather_count : a.n;
   const int64_t n_tiles = (n_rows + 127) / 128;
   const float clipv = a.obs_clip > 0.f ? a.obs_clip : 3.0e38f;
   const uint64_t step = a.step + (a.step_base ? *a.step_base : 0ull);
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const bool valid = tile * 128 + tid < n_rows;
-    const int64_t row = !valid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + tid] : tile * 128 + tid);
-    // ---- X tile: normalise (VecNormalize.normalize_obs), bf16, interleaved K-major
+  for (int64_t tile = (int64_t)blockIdx.x * kSlots + slot; tile < n_tiles; tile += (int64_t)gridDim.x * kSlots) {
+    // ---- X tile: normalise (VecNormalize.normalize_obs), bf16, interleaved K-major; 2 threads per row, 2 chunks each
     {
-      float x[kIn];
+      const bool xvalid = tile * 128 + xrow < n_rows;
+      const int64_t xr = !xvalid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + xrow] : tile * 128 + xrow);
 #pragma unroll
-      for (int j = 0; j < kIn; ++j) x[j] = 0.f;
-      if (valid) {
-        const float* src = a.obs + row * a.obs_stride;
-        if (obs_dim == 20 && (a.obs_stride & 3) == 0) {
+      for (int qq = 0; qq < 2; ++qq) {
+        const int q = 2 * (int)xh + qq, c0 = 8 * q;
+        float x[8];
 #pragma unroll
-          for (int j = 0; j < 20; j += 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + j));
-            x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        if (xvalid && c0 < obs_dim) {
+          const float* src = a.obs + xr * a.obs_stride + c0;
+          if ((a.obs_stride & 3) == 0 && c0 + 8 <= obs_dim) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (c0 + j < obs_dim) x[j] = __ldg(src + j);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < kIn; ++j)
-            if (j < obs_dim) x[j] = __ldg(src + j);
         }
-      }
-#pragma unroll
-      for (int q = 0; q < kIn / 8; ++q) {
         uint32_t w[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const int j = 8 * q + 2 * h;
-          const float v0 = fminf(fmaxf((x[j] - sMean[j]) * sInv[j], -clipv), clipv);
-          const float v1 = fminf(fmaxf((x[j + 1] - sMean[j + 1]) * sInv[j + 1], -clipv), clipv);
+          const int j = 2 * h;
+          const float v0 = fminf(fmaxf((x[j] - sMean[c0 + j]) * sInv[c0 + j], -clipv), clipv);
+          const float v1 = fminf(fmaxf((x[j + 1] - sMean[c0 + j + 1]) * sInv[c0 + j + 1], -clipv), clipv);
           x[j] = v0; x[j + 1] = v1;
           __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
           w[h] = *reinterpret_cast<uint32_t*>(&pk);
         }
-        *reinterpret_cast<uint4*>(smem + kSmX + chunk_off(tid, q, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      if (a.obs_norm_out && valid) {
-        float* dst = a.obs_norm_out + row * obs_dim;
-        if (obs_dim == 20) {
+        *reinterpret_cast<uint4*>(slotp + kSlotX + chunk_off(xrow, q, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (a.obs_norm_out && xvalid) {
+          float* dst = a.obs_norm_out + xr * obs_dim + c0;
 #pragma unroll
-          for (int j = 0; j < 20; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kIn; ++j)
-            if (j < obs_dim) dst[j] = x[j];
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < obs_dim) dst[j] = x[j];
         }
       }
     }
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
-    // ---- L1
-    if (tid == 0) {
+    slot_sync(slot);
+    // ---- [L1p]
+    if (st == 0) {
       fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, 2 * kHid);
 #pragma unroll
       for (int ks = 0; ks < kIn / 16; ++ks)
-        mma_bf16(tbase, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + ks * 2 * LBO_W1, LBO_W1, 128), idesc, ks > 0);
-      mma_commit(&bar);
+        mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
+      mma_commit(bar);
     }
-    mbar_wait(&bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    hidden_epilogue(trow, sB1, smem + kSmH, tid);
+    hidden_epilogue(tacc_row, sB1, slotp + kSlotH, erow, ecol0);
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
-    // ---- L2 (two independent 128x128x128 chains)
-    if (tid == 0) {
+    slot_sync(slot);
+    // ---- [L2p]
+    if (st == 0) {
       fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, kHid);
 #pragma unroll
       for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tbase, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2p + ks * 2 * LBO_W2, LBO_W2, 128), idesc, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tbase + kHid, make_desc(sH + (16 + ks * 2) * LBO_ACT, LBO_ACT, 128), make_desc(sW2v + ks * 2 * LBO_W2, LBO_W2, 128), idesc, ks > 0);
-      mma_commit(&bar);
+        mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2p + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
+      mma_commit(bar);
     }
-    mbar_wait(&bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    hidden_epilogue(trow, sB2, smem + kSmH, tid);
+    hidden_epilogue(tacc_row, sB2, slotp + kSlotH, erow, ecol0);
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
-    // ---- L3 (action_net + value_net as one 128x16x256 GEMM)
-    if (tid == 0) {
+    slot_sync(slot);
+    // ---- [L3p, L1v]: action head from H2p into the out columns; critic layer 1 from X into the accumulator
+    if (st == 0) {
       fence_after_sync();
-      const uint32_t idesc = make_idesc_bf16(128, kHead);
 #pragma unroll
-      for (int ks = 0; ks < 2 * kHid / 16; ++ks)
-        mma_bf16(tbase, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + ks * 2 * LBO_W3, LBO_W3, 128), idesc, ks > 0);
-      mma_commit(&bar);
+      for (int ks = 0; ks < kHid / 16; ++ks)
+        mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + ks * 2 * LBO_W3, LBO_W3, 128), idesc_o, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < kIn / 16; ++ks)
+        mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + kHid * 16 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
+      mma_commit(bar);
     }
-    mbar_wait(&bar, phase); phase ^= 1;
+    mbar_wait(bar, phase); phase ^= 1;
     fence_after_sync();
-    {
+    hidden_epilogue(tacc_row, sB1 + kHid, slotp + kSlotH, erow, ecol0);
+    fence_async_smem();
+    fence_before_sync();
+    slot_sync(slot);
+    // ---- [L2v]
+    if (st == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < kHid / 16; ++ks)
+        mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2v + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
+      mma_commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    hidden_epilogue(tacc_row, sB2 + kHid, slotp + kSlotH, erow, ecol0);
+    fence_async_smem();
+    fence_before_sync();
+    slot_sync(slot);
+    // ---- [L3v]: value head from H2v, accumulated onto the action-head result
+    if (st == 0) {
+      fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < kHid / 16; ++ks)
+        mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + (16 + ks * 2) * LBO_W3, LBO_W3, 128), idesc_o, true);
+      mma_commit(bar);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    if (swarp < 4) {  // one thread per row finishes the sample
+      const bool valid = tile * 128 + erow < n_rows;
+      const int64_t row = !valid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + erow] : tile * 128 + erow);
       uint32_t r[16];
-      tmem_ld16(trow, r);
+      tmem_ld16(tacc_row + kTmemOut, r);
       tmem_ld_wait();
       if (valid) {
         float mean[4] = {0.f, 0.f, 0.f, 0.f}, act[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
@@ -327,9 +371,10 @@ __global__ void __launch_bounds__(128, 1) policy_forward_kernel(const FwdArgs a)
       }
     }
     fence_before_sync();
-    __syncthreads();  // TMEM cols [0,16) and sX are reused by the next tile
+    slot_sync(slot);  // the slot's TMEM columns and X buffer are reused by its next tile
   }
-  if (warp == 0) tmem_dealloc(tbase, 256);
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_slot, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------
@@ -459,9 +504,9 @@ static int launch_forward(ppo::FwdArgs& a, int64_t max_rows, void* stream) {
     if (cudaFuncSetAttribute(ppo::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppo::kSmTotal) != cudaSuccess)
       return pfail(QX_ECUDA, "ppo_policy_forward: cannot reserve shared memory");
   }
-  const int64_t tiles = (max_rows + 127) / 128;
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  ppo::policy_forward_kernel<<<grid, 128, ppo::kSmTotal, (cudaStream_t)stream>>>(a);
+  const int64_t tiles = (max_rows + 127) / 128, ctas = (tiles + ppo::kSlots - 1) / ppo::kSlots;
+  const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+  ppo::policy_forward_kernel<<<grid, ppo::kFwdThreads, ppo::kSmTotal, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_policy_forward: launch failed");
 }
 
