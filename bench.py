@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-envs", type=int, default=8192, help="envs of the bounded CPU sample")
+    ap.add_argument("--cpu-envs", type=int, default=262144, help="envs of the bounded CPU sample (one CPU step = this many envs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the configs[1] (4096 envs) side measurements")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO rollout side measurements (metric M2)")
@@ -277,7 +277,7 @@ def main_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "qx::quadx_step_kernel<false>", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
+                         "kernel": "qx::quadx_step_kernel<MODE_STEP_DEFER, HOVER> (+ the reset-queue launch, both inside the step time)", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
         }
         if world == 1 and not args.no_small:
@@ -289,7 +289,7 @@ def main_ours(args):
 
             line["ppo"] = bench_ppo.measure(131072, 32)
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_run(args.cpu_envs, 40, 2, budget_s=20.0)
+            r = cpu_run(args.cpu_envs, 150, 2, budget_s=12.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
     sim.close()
     if world > 1:

@@ -66,6 +66,44 @@ class ActorCritic(nn.Module):
         return value, logp, entropy
 
 
+# stable-baselines3 ActorCriticPolicy parameter names (net_arch=[128,128], separate pi / vf MLPs) -> ActorCritic modules
+SB3_KEYS = {
+    "mlp_extractor.policy_net.0": "pi1", "mlp_extractor.policy_net.2": "pi2", "action_net": "mu",
+    "mlp_extractor.value_net.0": "vf1", "mlp_extractor.value_net.2": "vf2", "value_net": "v",
+}
+
+
+def export_sb3_state_dict(model: "ActorCritic") -> dict:
+    """Policy weights under stable-baselines3's parameter names, so that `policy.load_state_dict(...)` of an SB3
+    `ActorCriticPolicy(net_arch=[128, 128])` (what train_hover.py:47-58 builds with PPO) accepts them -- the
+    counterpart of `model.save` in train_hover.py:26,62 for users who play the policy back with SB3
+    (test_hover.py:8-21)."""
+    sd = {"log_std": model.log_std.detach().cpu().clone()}
+    for sb3, mine in SB3_KEYS.items():
+        lin = getattr(model, mine)
+        sd[f"{sb3}.weight"] = lin.weight.detach().cpu().clone()
+        sd[f"{sb3}.bias"] = lin.bias.detach().cpu().clone()
+    return sd
+
+
+def import_sb3_state_dict(model: "ActorCritic", sd: dict) -> None:
+    with torch.no_grad():
+        model.log_std.copy_(sd["log_std"])
+        for sb3, mine in SB3_KEYS.items():
+            getattr(model, mine).weight.copy_(sd[f"{sb3}.weight"])
+            getattr(model, mine).bias.copy_(sd[f"{sb3}.bias"])
+
+
+def export_vecnormalize(obs_stats: "RunningStats", ret_stats: "RunningStats", cfg: "PPOConfig") -> dict:
+    """The fields of SB3's VecNormalize pickle (`env.save`, train_hover.py:27,63): obs_rms / ret_rms
+    {mean, var, count}, clip_obs, clip_reward, gamma, epsilon, norm_obs, norm_reward."""
+    def rms(st):
+        s, d = st.stats.detach().cpu().numpy(), st.dim
+        return {"mean": s[:d].copy(), "var": s[d:2 * d].copy(), "count": float(s[2 * d])}
+    return {"obs_rms": rms(obs_stats), "ret_rms": rms(ret_stats), "clip_obs": cfg.clip_obs, "clip_reward": cfg.clip_reward,
+            "gamma": cfg.gamma, "epsilon": obs_stats.eps, "norm_obs": cfg.norm_obs, "norm_reward": cfg.norm_reward}
+
+
 class PackedPolicy:
     """bf16 copy of an ``ActorCritic`` in the layout of ``struct PpoPolicy``."""
 
@@ -375,7 +413,9 @@ class PPOTrainer:
     def save(self, path: str) -> None:
         """Counterpart of model.save + env.save (train_hover.py:26-27,62-63): policy, optimiser, VecNormalize statistics."""
         torch.save({"model": self.model.state_dict(), "opt": self.opt.state_dict(), "obs_stats": self.rollout.obs_stats.state_dict(),
-                    "ret_stats": self.rollout.ret_stats.state_dict(), "num_timesteps": self.num_timesteps, "cfg": self.cfg.__dict__}, path)
+                    "ret_stats": self.rollout.ret_stats.state_dict(), "num_timesteps": self.num_timesteps, "cfg": self.cfg.__dict__,
+                    "sb3_policy_state_dict": export_sb3_state_dict(self.model),
+                    "sb3_vecnormalize": export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg)}, path)
 
     def load(self, path: str) -> None:
         sd = torch.load(path, map_location=self.device, weights_only=False)

@@ -88,3 +88,26 @@ def test_reference_arm_rank_handling():
     assert outs[1] == ""
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0 and line["n_gpus"] == 2
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_sb3_compatible_export_roundtrip():
+    """train_hover.py:26-27,62-63 save an SB3 zip + VecNormalize pkl; the export uses SB3's parameter names."""
+    sys.path.insert(0, ROOT)
+    from fpv_drone_rl_agent_b200 import ppo
+
+    torch.manual_seed(3)
+    m = ppo.ActorCritic()
+    sd = ppo.export_sb3_state_dict(m)
+    assert set(sd) == {"log_std", "mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias", "mlp_extractor.policy_net.2.weight",
+                       "mlp_extractor.policy_net.2.bias", "mlp_extractor.value_net.0.weight", "mlp_extractor.value_net.0.bias",
+                       "mlp_extractor.value_net.2.weight", "mlp_extractor.value_net.2.bias", "action_net.weight", "action_net.bias",
+                       "value_net.weight", "value_net.bias"}
+    assert sd["mlp_extractor.policy_net.0.weight"].shape == (128, 20) and sd["action_net.weight"].shape == (4, 128) and sd["value_net.weight"].shape == (1, 128)
+    assert sum(v.numel() for v in sd.values()) == 39049
+    m2 = ppo.ActorCritic()
+    ppo.import_sb3_state_dict(m2, sd)
+    x = torch.randn(5, 20)
+    assert torch.equal(m(x)[0], m2(x)[0]) and torch.equal(m(x)[1], m2(x)[1])
+    rs, rr = ppo.RunningStats(20, "cpu"), ppo.RunningStats(1, "cpu")
+    vn = ppo.export_vecnormalize(rs, rr, ppo.PPOConfig())
+    assert vn["obs_rms"]["mean"].shape == (20,) and vn["obs_rms"]["count"] == 1e-4 and vn["clip_obs"] == 10.0 and vn["gamma"] == 0.99

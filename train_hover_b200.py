@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--ent-coef", type=float, default=0.0)
+    ap.add_argument("--gamma", type=float, default=0.99)
+    ap.add_argument("--print-every", type=int, default=1)
     ap.add_argument("--save-path", default="./ppo_hover_checkpoints/")
     ap.add_argument("--min-steps-between-checkpoints", type=int, default=20000)  # train_hover.py:9
     ap.add_argument("--tensorboard", default="")
@@ -56,7 +59,8 @@ def main():
         dist.barrier()
     from fpv_drone_rl_agent_b200 import ppo
 
-    cfg = ppo.PPOConfig(n_envs=args.envs, n_steps=args.steps, n_epochs=args.epochs, batch_size=args.batch, learning_rate=args.lr, seed=args.seed)
+    cfg = ppo.PPOConfig(n_envs=args.envs, n_steps=args.steps, n_epochs=args.epochs, batch_size=args.batch, learning_rate=args.lr, seed=args.seed,
+                        ent_coef=args.ent_coef, gamma=args.gamma)
     trainer = ppo.PPOTrainer(cfg, device=f"cuda:{local}", rank=rank, world=world)
     writer = None
     if args.tensorboard and rank == 0:
@@ -72,8 +76,9 @@ def main():
         out["wall_s"] = time.time() - t0
         out["fps"] = out["timesteps"] / out["wall_s"]
         if rank == 0:
-            print(f"iter {it:4d} steps {out['timesteps']:>12,d} fps {out['fps']:>12,.0f} ep_len {out['ep_len_mean']:7.1f} ep_rew {out['ep_rew_mean']:9.2f} "
-                  f"pg {out['pg']:+.4f} vf {out['vf']:.4f} kl {out['kl']:+.4f}", flush=True)
+            if it % args.print_every == 0:
+                print(f"iter {it:4d} steps {out['timesteps']:>12,d} fps {out['fps']:>12,.0f} ep_len {out['ep_len_mean']:7.1f} ep_rew {out['ep_rew_mean']:9.2f} "
+                      f"pg {out['pg']:+.4f} vf {out['vf']:.4f} kl {out['kl']:+.4f}", flush=True)
             log.append(out)
             if writer:
                 for tag, key in (("rollout/ep_len_mean", "ep_len_mean"), ("rollout/ep_rew_mean", "ep_rew_mean"), ("time/fps", "fps"),
