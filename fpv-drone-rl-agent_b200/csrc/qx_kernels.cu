@@ -61,6 +61,7 @@ struct StepArgs {
   Stats* stats;
   ResetQueue* queue;        // deferred-reset mode (MODE_STEP_DEFER / MODE_RESET_QUEUE)
   int64_t n;
+  int64_t env_begin, env_count;  // step modes: the env sub-range this launch covers (host-side chunked pipeline)
   int64_t obs_stride;
   int32_t k;
   int32_t obs_bf16;
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const
     for (unsigned int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock)
       run_env<MODE, TASK>(c, a, (int64_t)a.queue->idx[t]);
   } else {
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i >= a.n) return;
+    const int64_t i = a.env_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.env_begin + a.env_count) return;
     if (MODE == MODE_RESET_MASK && a.mask && !a.mask[i]) return;
     run_env<MODE, TASK>(c, a, i);
   }
@@ -332,7 +333,8 @@ struct QxHandle {
   qx::Stats* stats;
   qx::ResetQueue* queue;
   // staging for the *_host calls
-  cudaStream_t stream;
+  cudaStream_t stream, h2d_stream, d2h_stream;
+  cudaEvent_t ev_h2d[16], ev_k[16], ev_d2h;
   float* h_act; float* d_act;
   float* h_obs; float* d_obs;
   float* h_rew; float* d_rew;
@@ -465,6 +467,13 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * 11 * n_envs);
   if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 16 && e == cudaSuccess; ++k) {
+    e = cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_k[k], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue); delete h;
@@ -485,6 +494,10 @@ extern "C" int qx_destroy(QxHandle* h) {
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_flags); cudaFree(h->d_tobs);
   }
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  for (int k = 0; k < 16; ++k) { if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]); if (h->ev_k[k]) cudaEventDestroy(h->ev_k[k]); }
+  if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
   cudaSetDevice(prev);
   delete h;
   return QX_OK;
@@ -497,7 +510,7 @@ extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
 
 template <int TASK>
 static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
-  const unsigned grid = (unsigned)((h->n + qx::kBlock - 1) / qx::kBlock);
+  const unsigned grid = (unsigned)((a.env_count + qx::kBlock - 1) / qx::kBlock);
   switch (mode) {
     case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
@@ -510,7 +523,8 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
   }
 }
 
-static int launch(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
+static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
+  if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
   if (h->dev.task == QX_TASK_HOVER) launch_task<QX_TASK_HOVER>(h, mode, a, s);
   else launch_task<QX_TASK_YAW>(h, mode, a, s);
   ++g_launches;
@@ -627,8 +641,10 @@ static bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-// Pinned caller buffers are used in place (one DMA each way); pageable ones go
-// through the handle's pinned staging area.
+// Pinned caller buffers are used in place; pageable ones go through the handle's pinned staging area.  Large
+// batches are cut into chunks and pipelined over three streams -- actions H2D (chunk k+1) | step + reset kernels
+// (chunk k) | results D2H (chunk k-1) -- so the PCIe transfers, which dominate this call, overlap the kernels and
+// each other (H2D and D2H use different copy engines).
 extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
                             uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
   if (!h || !actions_host) return fail(QX_EINVAL, "qx_step_host: bad arguments");
@@ -639,18 +655,41 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
   const int od = h->dev.obs_dim, ad = h->dev.act_dim;
   const float* src = actions_host;
   if (!is_pinned(actions_host)) { memcpy(h->h_act, actions_host, sizeof(float) * n * ad); src = h->h_act; }
-  QX_CUDA(cudaMemcpyAsync(h->d_act, src, sizeof(float) * n * ad, cudaMemcpyHostToDevice, h->stream));
-  rc = qx_step(h, h->d_act, h->d_obs, QX_OBS_F32, od, h->d_rew, h->d_flags, h->d_flags + n,
-               terminal_obs_host ? h->d_tobs : nullptr, h->stream);
-  if (rc) return rc;
   const bool p_obs = is_pinned(obs_host), p_rew = is_pinned(reward_host), p_te = is_pinned(terminated_host),
              p_tr = is_pinned(truncated_host);
-  if (obs_host) QX_CUDA(cudaMemcpyAsync(p_obs ? obs_host : h->h_obs, h->d_obs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->stream));
-  if (reward_host) QX_CUDA(cudaMemcpyAsync(p_rew ? reward_host : h->h_rew, h->d_rew, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-  QX_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * n, cudaMemcpyDeviceToHost, h->stream));
-  if (p_te) QX_CUDA(cudaMemcpyAsync(terminated_host, h->d_flags, n, cudaMemcpyDeviceToHost, h->stream));
-  if (p_tr) QX_CUDA(cudaMemcpyAsync(truncated_host, h->d_flags + n, n, cudaMemcpyDeviceToHost, h->stream));
-  if (terminal_obs_host) QX_CUDA(cudaMemcpyAsync(h->h_tobs, h->d_tobs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->stream));
+  float* dst_obs = obs_host ? (p_obs ? obs_host : h->h_obs) : nullptr;
+  float* dst_rew = reward_host ? (p_rew ? reward_host : h->h_rew) : nullptr;
+  const int chunks = n >= (1 << 17) ? 8 : 1;
+  const int64_t per = ((n + chunks - 1) / chunks + qx::kBlock - 1) / qx::kBlock * qx::kBlock;
+  for (int k = 0; k < chunks; ++k) {
+    const int64_t b = k * per, cnt = (b + per <= n ? per : n - b);
+    if (cnt <= 0) break;
+    QX_CUDA(cudaMemcpyAsync(h->d_act + b * ad, src + b * ad, sizeof(float) * cnt * ad, cudaMemcpyHostToDevice, h->h2d_stream));
+    QX_CUDA(cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
+    QX_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[k], 0));
+    qx::StepArgs a{};
+    a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.reward = h->d_rew;
+    a.terminated = h->d_flags; a.truncated = h->d_flags + n; a.terminal_obs = terminal_obs_host ? h->d_tobs : nullptr;
+    a.stats = h->stats; a.queue = h->queue; a.n = n; a.k = 1; a.env_begin = b; a.env_count = cnt;
+    if (h->cfg.auto_reset) {
+      rc = launch(h, qx::MODE_STEP_DEFER, a, h->stream);
+      if (rc) return rc;
+      rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);
+    } else {
+      rc = launch(h, qx::MODE_STEP_INLINE, a, h->stream);
+    }
+    if (rc) return rc;
+    QX_CUDA(cudaEventRecord(h->ev_k[k], h->stream));
+    QX_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->ev_k[k], 0));
+    if (dst_obs) QX_CUDA(cudaMemcpyAsync(dst_obs + b * od, h->d_obs + b * od, sizeof(float) * cnt * od, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (dst_rew) QX_CUDA(cudaMemcpyAsync(dst_rew + b, h->d_rew + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    QX_CUDA(cudaMemcpyAsync(h->h_flags + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    QX_CUDA(cudaMemcpyAsync(h->h_flags + n + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (p_te) QX_CUDA(cudaMemcpyAsync(terminated_host + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (p_tr) QX_CUDA(cudaMemcpyAsync(truncated_host + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+  }
+  if (terminal_obs_host) QX_CUDA(cudaMemcpyAsync(h->h_tobs, h->d_tobs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->d2h_stream));
+  QX_CUDA(cudaStreamSynchronize(h->d2h_stream));
   QX_CUDA(cudaStreamSynchronize(h->stream));
   if (obs_host && !p_obs) memcpy(obs_host, h->h_obs, sizeof(float) * n * od);
   if (reward_host && !p_rew) memcpy(reward_host, h->h_rew, sizeof(float) * n);

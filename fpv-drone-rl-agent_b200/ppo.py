@@ -241,6 +241,8 @@ class PPOConfig:
     clip_reward: float = 10.0
     seed: int = 0
     use_cuda_graph: bool = True
+    target_kl: float = 0.0  # SB3 PPO target_kl: stop the epoch loop once the approximate KL exceeds 1.5 x this (0 = off)
+    log_std_init: float = 0.0  # SB3 policy_kwargs log_std_init
 
 
 class RolloutEngine:
@@ -348,7 +350,7 @@ class PPOTrainer:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = dev
         torch.manual_seed(cfg.seed)  # identical initial weights on every rank
-        self.model = ActorCritic().to(dev)
+        self.model = ActorCritic(log_std_init=cfg.log_std_init).to(dev)
         self.packed = PackedPolicy(self.model, dev)
         from ._lib import default_config
 
@@ -373,7 +375,10 @@ class PPOTrainer:
         bs = min(cfg.batch_size, N)
         stats = {"pg": 0.0, "vf": 0.0, "kl": 0.0, "clipfrac": 0.0}
         n_mb = 0
+        stop = False
         for _ in range(cfg.n_epochs):
+            if stop:
+                break
             perm = torch.randperm(N, device=self.device, generator=self.gen)
             for s in range(0, N - bs + 1, bs):
                 idx = perm[s:s + bs]
@@ -384,6 +389,16 @@ class PPOTrainer:
                 pg = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
                 vf = torch.nn.functional.mse_loss(ret_all[idx], value)
                 loss = pg + cfg.vf_coef * vf - cfg.ent_coef * entropy.mean()
+                if cfg.target_kl > 0.0:  # SB3: early stop on the k3 estimator, checked once per epoch to avoid a sync per minibatch
+                    if s == 0:
+                        with torch.no_grad():
+                            lr_ = logp - old_logp[idx]
+                            akl = ((torch.exp(lr_) - 1) - lr_).mean()
+                            if self.world > 1:
+                                dist.all_reduce(akl); akl /= self.world
+                        if float(akl) > 1.5 * cfg.target_kl:
+                            stop = True
+                            break
                 self.opt.zero_grad(set_to_none=True)
                 loss.backward()
                 self._allreduce_grads()

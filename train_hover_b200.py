@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--ent-coef", type=float, default=0.0)
     ap.add_argument("--gamma", type=float, default=0.99)
     ap.add_argument("--print-every", type=int, default=1)
+    ap.add_argument("--target-kl", type=float, default=0.0)
+    ap.add_argument("--log-std-init", type=float, default=0.0)
     ap.add_argument("--save-path", default="./ppo_hover_checkpoints/")
     ap.add_argument("--min-steps-between-checkpoints", type=int, default=20000)  # train_hover.py:9
     ap.add_argument("--tensorboard", default="")
@@ -60,7 +62,7 @@ def main():
     from fpv_drone_rl_agent_b200 import ppo
 
     cfg = ppo.PPOConfig(n_envs=args.envs, n_steps=args.steps, n_epochs=args.epochs, batch_size=args.batch, learning_rate=args.lr, seed=args.seed,
-                        ent_coef=args.ent_coef, gamma=args.gamma)
+                        ent_coef=args.ent_coef, gamma=args.gamma, target_kl=args.target_kl, log_std_init=args.log_std_init)
     trainer = ppo.PPOTrainer(cfg, device=f"cuda:{local}", rank=rank, world=world)
     writer = None
     if args.tensorboard and rank == 0:
