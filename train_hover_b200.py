@@ -37,8 +37,8 @@ def main():
     ap.add_argument("--ent-coef", type=float, default=0.0)
     ap.add_argument("--gamma", type=float, default=0.99)
     ap.add_argument("--print-every", type=int, default=1)
-    ap.add_argument("--target-kl", type=float, default=0.0)
-    ap.add_argument("--log-std-init", type=float, default=0.0)
+    ap.add_argument("--target-kl", type=float, default=0.02)
+    ap.add_argument("--log-std-init", type=float, default=-1.0)
     ap.add_argument("--save-path", default="./ppo_hover_checkpoints/")
     ap.add_argument("--min-steps-between-checkpoints", type=int, default=20000)  # train_hover.py:9
     ap.add_argument("--tensorboard", default="")
