@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   const int ecol0 = (int)(swarp >> 2) * 64;        // and its 64 columns
   const uint32_t xrow = st & 127, xh = st >> 7;    // X-tile staging: row, pair of 8-column chunks
   const int obs_dim = a.p.obs_dim, act_dim = a.p.act_dim;
+  // gather mode (time-limit bootstrap): most steps have no truncated env at all -- leave before staging 88 KB of weights
+  if (a.gather_idx && (int64_t)blockIdx.x * kSlots * 128 >= (int64_t)*a.gather_count) return;
   // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barriers
   stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, kFwdThreads);
   stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, kFwdThreads);

@@ -11,8 +11,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 envs = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
-rep = os.path.join(ROOT, "gpurun_out", f"k1_{tag}.ncu-rep")
-launches = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+prefix = sys.argv[3] if len(sys.argv) > 3 else "k1"
+rep = os.path.join(ROOT, "gpurun_out", f"{prefix}_{tag}.ncu-rep")
+launches = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv") if prefix == "k1" else "/nonexistent"
 SEL = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -30,7 +31,12 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 seen = set()
 traffic = None
-for r in rows[2:]:
+def _dur(r):
+    try:
+        return float(r[hdr.index("gpu__time_duration.sum")])
+    except ValueError:
+        return 0.0
+for r in sorted(rows[2:], key=lambda r: -_dur(r)):  # the longest instance of every kernel
     name = r[hdr.index("Kernel Name")]
     if name in seen:
         continue
@@ -42,13 +48,13 @@ for r in rows[2:]:
         if k in hdr:
             vals[k] = r[hdr.index(k)]
             out.append(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |")
-    if "dram__bytes_read.sum" in vals and traffic is None and ("<1>" in name or "policy_forward" in name or "<0>" in name):
+    if "dram__bytes_read.sum" in vals and traffic is None and ("quadx_step_kernel<1" in name or "policy_forward" in name):
         def tobytes(v, u):
             return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         rd = tobytes(vals["dram__bytes_read.sum"], units[hdr.index("dram__bytes_read.sum")])
         wr = tobytes(vals["dram__bytes_write.sum"], units[hdr.index("dram__bytes_write.sum")])
         traffic = {"kernel": name, "envs": envs, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
-                   "per_env_step": (rd + wr) / envs, "source": f"ncu --set full, profiles/{tag}.md"}
+                   "per_env_step": (rd + wr) / envs, "source": f"ncu --set full, profiles/{prefix}_{tag}.md"}
 if os.path.exists(launches):
     out.append("\n## launch list (gpu__time_duration, cold-cache, serialised)\n")
     tot = {}
@@ -60,7 +66,7 @@ if os.path.exists(launches):
     for k, v in sorted(tot.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| `{k}` | {len(v)} | {sum(v) / 1e3:.1f} | {100 * sum(v) / s:.1f} % |")
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-open(os.path.join(ROOT, "profiles", f"{tag}.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", f"{prefix}_{tag}.md"), "w").write("\n".join(out) + "\n")
 if traffic and "quadx" in traffic["kernel"]:
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "k1_traffic.json"), "w"), indent=1)
 print("\n".join(out[:60]))
