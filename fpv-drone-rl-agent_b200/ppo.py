@@ -345,18 +345,19 @@ class RolloutEngine:
 class PPOTrainer:
     """``PPO.learn`` (train_hover.py:47-60, with PPO instead of SAC as the north star asks)."""
 
-    def __init__(self, cfg: PPOConfig, device=None, env_cfg=None, rank: int = 0, world: int = 1):
+    def __init__(self, cfg: PPOConfig, device=None, env_cfg=None, rank: int = 0, world: int = 1, task: int = 0):
+        """task: QX_TASK_HOVER (0, hover.py) or QX_TASK_YAW (1, yaw.py: 12-D obs, 1-D action)."""
         self.cfg, self.rank, self.world = cfg, rank, world
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = dev
         torch.manual_seed(cfg.seed)  # identical initial weights on every rank
-        self.model = ActorCritic(log_std_init=cfg.log_std_init).to(dev)
+        self.model = (ActorCritic(log_std_init=cfg.log_std_init) if task == 0 else ActorCritic(12, 1, log_std_init=cfg.log_std_init)).to(dev)
         self.packed = PackedPolicy(self.model, dev)
         from ._lib import default_config
 
-        ecfg = env_cfg if env_cfg is not None else default_config()
+        ecfg = env_cfg if env_cfg is not None else default_config(task)
         ecfg.update(auto_reset=1)
-        self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev)
+        self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev, task=task)
         self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=shard_env_ids(rank, cfg.n_envs))
         self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5)
         self.num_timesteps = 0

@@ -243,3 +243,21 @@ def test_rollout_graph_equals_eager_and_training_improves(env):
     for it in range(3):
         out = t.learn_iteration()
     assert all(math.isfinite(out[k]) for k in ("pg", "vf", "kl")) and out["timesteps"] == 3 * 2048 * 16
+
+
+def test_yaw_rollout_on_device(env):
+    """BASELINE configs[2]: the yaw task with the full on-device PPO rollout (12-D obs, 1-D action)."""
+    pkg, _lib, ppo = env
+    cfg = ppo.PPOConfig(n_envs=4096, n_steps=16, seed=1, n_epochs=1, batch_size=16384, log_std_init=-1.0)
+    t = ppo.PPOTrainer(cfg, device="cuda", task=pkg.QX_TASK_YAW)
+    ro = t.rollout
+    assert ro.obs.shape == (16, 4096, 12) and ro.actions.shape == (16, 4096, 1)
+    out = t.learn_iteration()
+    assert math.isfinite(out["pg"]) and math.isfinite(out["vf"])
+    assert torch.isfinite(ro.advantages).all() and ro.obs.abs().max().item() <= 10.0 + 1e-6
+    # the stored log-probs are those of the stored actions under the stored (normalised) observations
+    with torch.no_grad():
+        ro.collect()
+        torch.cuda.synchronize()
+        v, lp, _ = t.model.evaluate_actions(ro.obs.view(-1, 12), ro.actions.view(-1, 1))
+    assert (lp - ro.log_probs.view(-1)).abs().max().item() < 0.2 and (v - ro.values.view(-1)).abs().max().item() < 5e-2
