@@ -407,6 +407,62 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rew,
   }
 }
 
+// K3b: the same recurrence as a warp scan over time, for batches too small to fill the GPU with one thread per env.
+// A block owns 32 envs; per 32-step time tile (walked from the end) warp w loads row t0 + w coalesced across its 32
+// envs, the tile is transposed through shared memory so that warp w holds env w with lane = time, and the affine maps
+// x -> delta_t + c_t x (c_t = gamma lam (1 - d_t)) are composed by a 5-round Kogge-Stone suffix scan with
+// __shfl_down_sync; the carry into the tile is the advantage at the start of the previously processed tile.
+constexpr int kScanTile = 32;
+__global__ void __launch_bounds__(1024) gae_warpscan_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+                                                           const float* __restrict__ last_val, int T, int64_t n, float gamma, float lam,
+                                                           float* __restrict__ adv, float* __restrict__ ret) {
+  __shared__ float sV[kScanTile + 1][kScanTile + 1], sD[kScanTile][kScanTile + 1], sC[kScanTile][kScanTile + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * kScanTile;
+  const int64_t env_row = e0 + lane;   // load / store phase: lane = env, warp = time
+  const bool env_ok = env_row < n;
+  float carry = 0.f;                   // scan phase: warp = env; advantage at the first step of the tile processed before
+  const int n_tiles = (T + kScanTile - 1) / kScanTile;
+  for (int tile = n_tiles - 1; tile >= 0; --tile) {
+    const int t0 = tile * kScanTile, t = t0 + w;
+    const bool ok = env_ok && t < T;
+    float r = 0.f, v = 0.f, nnt = 1.f;
+    if (ok) {
+      r = rew[(int64_t)t * n + env_row]; v = val[(int64_t)t * n + env_row];
+      nnt = done[(int64_t)t * n + env_row] ? 0.f : 1.f;
+    }
+    sV[w][lane] = v;
+    if (w == 0) {  // row t0 + 32: value after the tile (the rollout's last_values for the final tile)
+      const int tn = t0 + kScanTile;
+      sV[kScanTile][lane] = !env_ok ? 0.f : (tn < T ? val[(int64_t)tn * n + env_row] : last_val[env_row]);
+    }
+    __syncthreads();
+    // value of the next step: next row of the tile, or last_values right after the final step of the rollout
+    const float vn = (t + 1 < T) ? sV[w + 1][lane] : (env_ok ? last_val[env_row] : 0.f);
+    sD[w][lane] = ok ? fmaf(gamma * vn, nnt, r) - v : 0.f;   // delta_t; steps past T are the identity map
+    sC[w][lane] = ok ? gamma * lam * nnt : 1.f;
+    __syncthreads();
+    // transposed: warp w = env e0 + w, lane = time t0 + lane
+    float d = sD[lane][w], c = sC[lane][w];
+#pragma unroll
+    for (int off = 1; off < kScanTile; off <<= 1) {
+      const float d2 = __shfl_down_sync(0xffffffffu, d, off), c2 = __shfl_down_sync(0xffffffffu, c, off);
+      if (lane + off < kScanTile) { d = fmaf(c, d2, d); c *= c2; }
+    }
+    const float a = fmaf(c, carry, d);
+    carry = __shfl_sync(0xffffffffu, a, 0);
+    __syncthreads();
+    sD[lane][w] = a;
+    __syncthreads();
+    if (ok) {
+      const float av = sD[w][lane];
+      adv[(int64_t)t * n + env_row] = av;
+      ret[(int64_t)t * n + env_row] = av + v;
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K4: VecNormalize running statistics.  Stage 1: per-block fp64 sums of x and
 // x^2 per column; stage 2 (one block): batch moments -> parallel-Welford merge
@@ -545,7 +601,12 @@ extern "C" int ppo_bootstrap_truncated(const PpoPolicy* p, const float* terminal
 extern "C" int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int32_t T, int64_t n,
                        float gamma, float lam, float* advantages, float* returns, void* stream) {
   if (!rewards || !values || !dones || !last_values || !advantages || !returns || T <= 0 || n <= 0) return pfail(QX_EINVAL, "ppo_gae: bad arguments");
-  ppo::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns);
+  // one thread per env saturates the memory system once there are enough envs; below that, scan over time in warps
+  if (n >= (1 << 17) || T < 16)
+    ppo::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns);
+  else
+    ppo::gae_warpscan_kernel<<<(unsigned)((n + ppo::kScanTile - 1) / ppo::kScanTile), 1024, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T,
+                                                                                                                       n, gamma, lam, advantages, returns);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_gae: launch failed");
 }
 

@@ -119,9 +119,10 @@ def test_policy_forward_matches_torch(env, n):
         assert torch.equal(a5, acts[100:])
 
 
-def test_gae_matches_sb3_recurrence(env):
+@pytest.mark.parametrize("T,n", [(37, 1000), (8, 4096), (128, 4096), (2048, 33), (33, 31), (64, 200_000), (5, 300_000)])
+def test_gae_matches_sb3_recurrence(env, T, n):
+    """Both GAE kernels (warp scan over time for small batches, one thread per env for large ones) against the SB3 loop."""
     pkg, _lib, ppo = env
-    T, n = 37, 1000
     g = torch.Generator(device="cuda").manual_seed(0)
     rew = torch.randn(T, n, device="cuda", generator=g)
     val = torch.randn(T, n, device="cuda", generator=g)
