@@ -282,6 +282,8 @@ def main_ours(args):
         }
         if world == 1 and not args.no_small:
             line["hover_4096"] = small_config(pkg, dev)
+        if world == 1 and not args.no_small:
+            line["yaw_same_batch"] = yaw_side(pkg, dev, E)
         if world == 1 and not args.no_ppo:
             sim.close()
             sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -297,6 +299,39 @@ def main_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+def yaw_side(pkg, dev, envs: int) -> dict:
+    """The yaw task (yaw.py: one Aviary.step = 2 physics sub-steps per env step) at the same batch size: with 6x less
+    arithmetic per step the same kernel is HBM-bound, which shows what the memory path alone sustains.
+    Algorithmic bytes per env-step: 128 + 128 state, 4 action, 48 obs, 4 reward, 2 flags = 314 B."""
+    import statistics as st
+
+    import torch
+
+    env = pkg.QuadXYawVecEnv(envs, seed=1234, device=dev)
+    env.reset()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    acts = (torch.rand(8, envs, 1, generator=g) * 2 - 1).to(dev)
+    obs, rew, te, tr = env.obs, env.rewards, env.terminated, env.truncated
+    for k in range(5):
+        env.sim.step(acts[k % 8], obs, rew, te, tr)
+    K = 32
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record()
+    for k in range(K):
+        env.sim.step(acts[k % 8], obs, rew, te, tr)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    ms = st.mean(ev[k].elapsed_time(ev[k + 1]) for k in range(K))
+    env.close()
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks))["hbm_gbs"] if os.path.exists(peaks) else 6650.0
+    gbs = envs * 314 / (ms * 1e-3) / 1e9
+    moved = envs * (176 * 2 + 4 + 48 + 4 + 2) / (ms * 1e-3) / 1e9
+    return {"envs": envs, "env_steps_per_s": envs / (ms * 1e-3), "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "alg_bytes_per_env_step": 314,
+                         "moved_gbs": moved, "moved_frac": moved / peak}}
 
 
 def small_config(pkg, dev) -> dict:

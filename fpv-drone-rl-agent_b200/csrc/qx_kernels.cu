@@ -30,6 +30,9 @@ namespace qx {
 #ifndef QX_MIN_BLOCKS
 #define QX_MIN_BLOCKS 4
 #endif
+#ifndef QX_PAIR_UNROLL
+#define QX_PAIR_UNROLL 1
+#endif
 constexpr int kBlock = QX_BLOCK;
 
 struct Stats {
@@ -173,6 +176,8 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       if (c.ctrl_every == 2 && (nsub & 1) == 0) {
         // default scheduling (control_hz = physics_hz / 2): one rate-PID update and one Philox call per
         // Aviary.step(), then its two physics sub-steps
+        constexpr int kPairUnroll = QX_PAIR_UNROLL;
+#pragma unroll kPairUnroll
         for (int j = 0; j < nsub; j += 2) {
           control_update(e, c, sp, pwm);
           float nz[4] = {0.f, 0.f, 0.f, 0.f};
