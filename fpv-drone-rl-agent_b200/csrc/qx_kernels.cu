@@ -434,6 +434,10 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
     d->start_pos[a] = s.start_pos[a]; d->start_rpy[a] = s.start_rpy[a];
   }
   d->inv_mass = (float)(1.0 / s.mass); d->g = s.gravity; d->vmax = s.max_coord_vel; d->floor_z = s.floor_z;
+  for (int a = 0; a < 3; ++a) d->hI[a] = (float)(h / s.inertia[a]);
+  d->hm = (float)(h / s.mass); d->hg = (float)(h * s.gravity); d->hh = (float)(0.5 * h); d->hh2 = (float)(0.25 * h * h);
+  d->kq1 = (float)(-0.5 * h / 6.0); d->kq2 = (float)(0.5 * h / 120.0);
+  d->ndrag_c = -(float)(0.5 * s.air_density * s.drag_coef_xyz * s.drag_area_xyz); d->ndrag_pqr = -s.drag_coef_pqr;
   const double tilt = s.cam_tilt_up_deg * M_PI / 180.0;
   d->cam_sd = (float)sin(tilt); d->cam_cd = (float)cos(tilt);
   d->inv_tan = (float)(1.0 / tan(0.5 * s.cam_fov_deg * M_PI / 180.0));

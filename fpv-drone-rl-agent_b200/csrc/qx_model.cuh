@@ -26,6 +26,7 @@ struct DevConfig {
   float torque_k[4], mx[4], my[4], map[16];
   float drag_c, drag_pqr, kp[3], kiT[3], kd_T[3], lim[3];
   float inv_mass, g, I[3], invI[3], vmax, floor_z;
+  float hI[3], hm, hg, hh, hh2, ndrag_c, ndrag_pqr, kq1, kq2;  // h/I, h/m, h g, h/2, (h/2)^2, -drag, series coefficients * h/2
   float cam_sd, cam_cd, inv_tan, res, half_res, inv_half_res, inv_res2, cam_near, cam_off[3], margin, panel[12];
   float inv_agent_dt, dome2, floor_thr, target_area, target_ratio, act_scale[3];
   float start_pos[3], start_rpy[3], spawn_thr, spawn_pos_noise, spawn_yaw_noise;
@@ -202,13 +203,13 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
   }
   fz *= c.thrust_k; tx *= c.thrust_k; ty *= -c.thrust_k;
   // drag from the (stale) snapshot, body frame
-  const float fbx = -c.drag_c * fabsf(e.svb[0]) * e.svb[0];
-  const float fby = -c.drag_c * fabsf(e.svb[1]) * e.svb[1];
-  const float fbz = fmaf(-c.drag_c * fabsf(e.svb[2]), e.svb[2], fz);
+  const float fbx = c.ndrag_c * fabsf(e.svb[0]) * e.svb[0];
+  const float fby = c.ndrag_c * fabsf(e.svb[1]) * e.svb[1];
+  const float fbz = fmaf(c.ndrag_c * fabsf(e.svb[2]), e.svb[2], fz);
   if (!(e.flags & F_CONTACT)) {
-    tx = fmaf(-c.drag_pqr * fabsf(e.swb[0]), e.swb[0], tx);
-    ty = fmaf(-c.drag_pqr * fabsf(e.swb[1]), e.swb[1], ty);
-    tz = fmaf(-c.drag_pqr * fabsf(e.swb[2]), e.swb[2], tz);
+    tx = fmaf(c.ndrag_pqr * fabsf(e.swb[0]), e.swb[0], tx);
+    ty = fmaf(c.ndrag_pqr * fabsf(e.swb[1]), e.swb[1], ty);
+    tz = fmaf(c.ndrag_pqr * fabsf(e.swb[2]), e.swb[2], tz);
   }
   // rotation matrix of the current attitude
   const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
@@ -230,14 +231,14 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
     const float lx = c.I[0] * e.wx, ly = c.I[1] * e.wy, lz = c.I[2] * e.wz;
     gx = e.wy * lz - e.wz * ly; gy = e.wz * lx - e.wx * lz; gz = e.wx * ly - e.wy * lx;
   }
-  e.wx = fmaf(c.h * c.invI[0], tx - gx, e.wx);
-  e.wy = fmaf(c.h * c.invI[1], ty - gy, e.wy);
-  e.wz = fmaf(c.h * c.invI[2], tz - gz, e.wz);
+  e.wx = fmaf(c.hI[0], tx - gx, e.wx);
+  e.wy = fmaf(c.hI[1], ty - gy, e.wy);
+  e.wz = fmaf(c.hI[2], tz - gz, e.wz);
   // linear half, world frame: semi-implicit Euler
-  const float hm = c.h * c.inv_mass;
+  const float hm = c.hm;
   e.vx = fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx);
   e.vy = fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy);
-  e.vz = fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.h * c.g;
+  e.vz = fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.hg;
   // btMultiBody's +-max_coord_vel clamp: one max over the six components, the clamp itself is a cold path
   if (fmaxf(fmaxf(fmaxf(fabsf(e.vx), fabsf(e.vy)), fmaxf(fabsf(e.vz), fabsf(e.wx))), fmaxf(fabsf(e.wy), fabsf(e.wz))) > c.vmax) {
     e.vx = clampf(e.vx, -c.vmax, c.vmax); e.vy = clampf(e.vy, -c.vmax, c.vmax); e.vz = clampf(e.vz, -c.vmax, c.vmax);
@@ -247,10 +248,10 @@ __device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, cons
   e.py = fmaf(c.h, e.vy, e.py);
   e.pz = fmaf(c.h, e.vz, e.pz);
   // q <- q exp(h w_b / 2): series in s = (|w| h / 2)^2 (no sqrt / sin / cos), then renormalise
-  const float hh = 0.5f * c.h;
-  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * (hh * hh);
-  const float kq = hh * (1.f + s * (-1.f / 6.f + s * (1.f / 120.f + s * (-1.f / 5040.f))));
-  const float dw = 1.f + s * (-0.5f + s * (1.f / 24.f + s * (-1.f / 720.f + s * (1.f / 40320.f))));
+  // sin(x)/x * h/2 and cos(x) in s = x^2, x = |w| h / 2 <= 0.37 at the +-100 rad/s clamp: truncation < 4e-9
+  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * c.hh2;
+  const float kq = fmaf(s, fmaf(s, c.kq2, c.kq1), c.hh);
+  const float dw = fmaf(s, fmaf(s, fmaf(s, -1.f / 720.f, 1.f / 24.f), -0.5f), 1.f);
   const float dx = e.wx * kq, dy = e.wy * kq, dz = e.wz * kq;
   const float nx = w * dx + x * dw + y * dz - z * dy;
   const float ny = w * dy - x * dz + y * dw + z * dx;
