@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         "qx_get_state": (C.c_int, [vp, vp]),
         "qx_set_state": (C.c_int, [vp, vp]),
         "qx_episode_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64), i32]),
+        "qx_nonfinite_count": (C.c_int, [vp, C.POINTER(i64)]),
         "qx_num_envs": (i64, [vp]),
         "qx_obs_dim": (i32, [vp]),
         "qx_act_dim": (i32, [vp]),
@@ -118,7 +119,7 @@ def lib() -> C.CDLL:
 
 EXPORTED = [
     "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
-    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr",
+    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -39,6 +40,7 @@ struct Stats {
   double sum_ret;
   unsigned long long sum_len;
   unsigned long long n_done;
+  unsigned long long n_nonfinite;  // envs whose state stopped being finite and were terminated (failure detection)
 };
 
 // Envs that finished in a step and must be re-created before the next one.
@@ -267,6 +269,20 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
         if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB;
         if (e.spz < c.floor_thr) fl |= F_LOWZ;
       }
+      bool bad = false;
+      // failure containment (no counterpart in the reference): a state that is no longer finite ends the episode like
+      // an out-of-bounds flight, is counted, and the env is re-created by the auto-reset -- it cannot poison the batch
+      if (live && !(fabsf(e.px) + fabsf(e.py) + fabsf(e.pz) + fabsf(e.vx) + fabsf(e.vy) + fabsf(e.vz) + fabsf(e.wx) + fabsf(e.wy) + fabsf(e.wz) +
+                    fabsf(e.qw) < 3.0e38f)) {
+        fl |= F_OOB;
+        bad = true;
+        atomicAdd(&a.stats->n_nonfinite, 1ull);
+        e.px = e.py = 0.f; e.pz = c.floor_z; e.vx = e.vy = e.vz = 0.f; e.wx = e.wy = e.wz = 0.f; e.qx = e.qy = e.qz = 0.f; e.qw = 1.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) e.thr[m] = 0.f;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) { e.pi[ax] = e.pe[ax] = e.swb[ax] = e.svb[ax] = 0.f; }
+      }
       if (fl & F_OOB) { reward = -100.f; fl |= F_TERM; }  // hover.py:278-281
       if (e.step_count > c.floor_grace && !c.render && (fl & F_LOWZ)) {  // hover.py:283-290
         reward = -100.f; fl |= F_TERM | F_ONFLOOR;
@@ -278,6 +294,11 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       const float a0 = act[0] - e.pa[0], a1 = act[1] - e.pa[1], a2 = act[2] - e.pa[2], a3 = act[3] - e.pa[3];
       reward -= 0.2f * fsqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
       reward += 1.0f;                                               // hover.py:332
+      if (bad) {  // nothing derived from the broken state may leave the kernel
+        reward = -100.f;
+#pragma unroll
+        for (int j = 0; j < OBS_DIM; ++j) obs[j] = 0.f;
+      }
       e.flags = fl;
       e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;  // hover.py:354
       e.step_count += 1;                               // hover.py:356
@@ -512,6 +533,21 @@ extern "C" int qx_destroy(QxHandle* h) {
   return QX_OK;
 }
 
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+extern "C" int qx_nonfinite_count(QxHandle* h, int64_t* count) {
+  if (!h || !count) return fail(QX_EINVAL, "qx_nonfinite_count: bad arguments");
+  DeviceGuard g(h->device);
+  qx::Stats s;
+  QX_CUDA(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
+  *count = (int64_t)s.n_nonfinite;
+  return QX_OK;
+}
+
 extern "C" int64_t qx_num_envs(const QxHandle* h) { return h ? h->n : 0; }
 extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0; }
 extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
@@ -611,11 +647,6 @@ static int ensure_staging(QxHandle* h) {
   return QX_OK;
 }
 
-struct DeviceGuard {
-  int prev = 0;
-  explicit DeviceGuard(int d) { cudaGetDevice(&prev); cudaSetDevice(d); }
-  ~DeviceGuard() { cudaSetDevice(prev); }
-};
 
 extern "C" int qx_reset_host(QxHandle* h, const uint8_t* mask_host, float* obs_host) {
   if (!h) return fail(QX_EINVAL, "qx_reset_host: null handle");
@@ -751,7 +782,7 @@ extern "C" int qx_episode_stats(QxHandle* h, double* sum_return, int64_t* sum_le
   DeviceGuard g(h->device);
   qx::Stats s;
   QX_CUDA(cudaMemcpy(&s, h->stats, sizeof(s), cudaMemcpyDeviceToHost));
-  if (clear) QX_CUDA(cudaMemset(h->stats, 0, sizeof(s)));
+  if (clear) QX_CUDA(cudaMemset(h->stats, 0, offsetof(qx::Stats, n_nonfinite)));  // the failure counter is since creation
   if (sum_return) *sum_return = s.sum_ret;
   if (sum_length) *sum_length = (int64_t)s.sum_len;
   if (n_episodes) *n_episodes = (int64_t)s.n_done;

@@ -188,6 +188,13 @@ class QuadXSim:
             raw[k] = v.astype(_INT_FIELDS[name]).view(np.float32) if name in _INT_FIELDS else v.astype(np.float32)
         check(self.lib.qx_set_state(self._h, raw.ctypes.data_as(C.c_void_p)))
 
+    def nonfinite_count(self) -> int:
+        """Envs terminated because their state stopped being finite (failure containment)."""
+        torch.cuda.synchronize(self.device)
+        n = C.c_int64()
+        check(self.lib.qx_nonfinite_count(self._h, C.byref(n)))
+        return n.value
+
     def episode_stats(self, clear: bool = True) -> tuple[float, int, int]:
         torch.cuda.synchronize(self.device)
         s, l, n = C.c_double(), C.c_int64(), C.c_int64()

@@ -160,6 +160,10 @@ int qx_set_state(QxHandle* h, const void* planes_host);
  * sums over the episodes finished since the last call with clear != 0. */
 int qx_episode_stats(QxHandle* h, double* sum_return, int64_t* sum_length, int64_t* n_episodes, int32_t clear);
 
+/* Failure detection (no reference counterpart): envs whose state stopped being finite since creation; each was
+ * terminated like an out-of-bounds flight and re-created by the auto-reset. */
+int qx_nonfinite_count(QxHandle* h, int64_t* count);
+
 int64_t qx_num_envs(const QxHandle* h);
 int32_t qx_obs_dim(const QxHandle* h);
 int32_t qx_act_dim(const QxHandle* h);

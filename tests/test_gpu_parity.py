@@ -330,3 +330,35 @@ def test_bf16_obs_into_strided_policy_buffer(pkg):
         sim_a.step(a, buf, rew, te, tr); sim_b.step(a, ref, rew, te, tr)
     torch.cuda.synchronize()
     assert torch.equal(buf[:, :20].float(), ref.to(torch.bfloat16).float()) and torch.all(buf[:, 20:] == 0)
+
+
+def test_nonfinite_state_is_contained(pkg):
+    """Failure containment: an env whose state turns NaN / inf is terminated (like an out-of-bounds flight), counted and
+    re-created by the auto-reset; its neighbours in the batch are untouched."""
+    n = 256
+    a = torch.zeros(n, 4, device="cuda")
+    a[:, 3] = 2 * HOVER_THR - 1
+    envs = [pkg.QuadXHoverVecEnv(n, seed=8, infos=False, noise=0) for _ in range(2)]
+    for e in envs:
+        e.reset()
+        e.step(a)
+    st = envs[0].sim.get_state()
+    bad = np.zeros(n, bool)
+    bad[[3, 64, 200]] = True
+    st["vx"][3] = np.nan
+    st["qw"][64] = np.inf
+    st["wbz"][200] = np.nan  # (an infinite rate would simply be caught by the +-100 velocity clamp)
+    envs[0].sim.set_state(st)
+    o0, r0, d0, _ = envs[0].step(a)
+    o1, r1, d1, _ = envs[1].step(a)
+    torch.cuda.synchronize()
+    assert envs[0].sim.nonfinite_count() == 3 and envs[1].sim.nonfinite_count() == 0
+    assert np.array_equal(d0.cpu().numpy(), bad) and not d1.any()
+    assert torch.isfinite(o0).all() and torch.isfinite(r0).all()
+    assert torch.equal(o0[~torch.as_tensor(bad)], o1[~torch.as_tensor(bad)]) and torch.equal(r0[~torch.as_tensor(bad)], r1[~torch.as_tensor(bad)])
+    assert (r0[torch.as_tensor(bad)] < -90).all()
+    for k in range(3):
+        o0, r0, d0, _ = envs[0].step(a)
+    assert torch.isfinite(o0).all() and envs[0].sim.nonfinite_count() == 3
+    for e in envs:
+        e.close()
