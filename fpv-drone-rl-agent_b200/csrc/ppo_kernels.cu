@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(128) test_gemm_kernel(const __nv_bfloat16* __r
 // operand.  thread == accumulator row in the final epilogue (sampling).
 // ---------------------------------------------------------------------------
 constexpr int kHid = PPO_HIDDEN, kIn = PPO_IN_PAD, kHead = PPO_HEAD_PAD;
-constexpr int kSlots = 2, kSlotThreads = 256, kFwdThreads = kSlots * kSlotThreads;
+#ifndef PPO_SLOTS
+#define PPO_SLOTS 3
+#endif
+constexpr int kSlots = PPO_SLOTS, kSlotThreads = 256, kFwdThreads = kSlots * kSlotThreads;
 constexpr uint32_t kSmW1 = 0;                                  // [4][256][16 B]   rows 0..127 pi, 128..255 vf
 constexpr uint32_t kSmW2p = kSmW1 + 2 * kHid * kIn * 2;        // [16][128][16 B]
 constexpr uint32_t kSmW2v = kSmW2p + kHid * kHid * 2;
@@ -90,7 +93,8 @@ constexpr uint32_t kSmB2 = kSmB1 + 2 * kHid * 4;
 constexpr uint32_t kSmB3 = kSmB2 + 2 * kHid * 4;               // 16 f32
 constexpr uint32_t kSmNorm = kSmB3 + kHead * 4;                // mean[32], inv_std[32]
 constexpr uint32_t kSmTotal = kSmNorm + 2 * kIn * 4;
-constexpr uint32_t kTmemCols = 512, kSlotTmem = 256, kTmemOut = 128;  // per slot: acc cols [0,128), out cols [128,144)
+constexpr uint32_t kTmemCols = 512, kSlotTmem = 160, kTmemOut = 128;  // per slot: acc cols [0,128), out cols [128,144)
+static_assert(kSlots * kSlotTmem <= kTmemCols && kSmTotal <= 227 * 1024, "slots must fit TMEM and shared memory");
 
 struct FwdArgs {
   PpoPolicy p;
@@ -133,18 +137,20 @@ __device__ __forceinline__ uint32_t tanh_pack_bf16x2(float lo, float hi) {
 #endif
 }
 
+// optional phase-timing buffer (debug / tuning only, see tools/k2_phases.py): [tile iteration][16] clock64 stamps of CTA 0, slot 0
+__device__ long long* g_phase_clk = nullptr;
+#define PHASE_STAMP(k) do { if (dbg && st == 0 && it < 8) dbg[it * 16 + (k)] = clock64(); } while (0)
+
 __device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "r"(kSlotThreads) : "memory"); }
 
 // bias + tanh + bf16 of this warp's 64 accumulator columns of this thread's row -> H chunks (A operand of the next layer)
 __device__ __forceinline__ void hidden_epilogue(uint32_t tacc, const float* __restrict__ bias, uint8_t* sH, uint32_t row, int col0) {
-  uint32_t r0[32], r1[32];
-  tmem_ld32(tacc + col0, r0);
-  tmem_ld32(tacc + col0 + 32, r1);
-  tmem_ld_wait();
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    const uint32_t* r = half ? r1 : r0;
     const int c0 = col0 + 32 * half;
+    uint32_t r[32];
+    tmem_ld32(tacc + c0, r);
+    tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 v;
@@ -155,6 +161,32 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tacc, const float* __re
       v.w = tanh_pack_bf16x2(__uint_as_float(r[8 * q + 6]) + b1.z, __uint_as_float(r[8 * q + 7]) + b1.w);
       *reinterpret_cast<uint4*>(sH + chunk_off(row, (uint32_t)(c0 >> 3) + q, 128)) = v;
     }
+  }
+}
+
+// raw observation columns [16 xh, 16 xh + 16) of row `xrow` of `tile` -> x[16] (zeros beyond obs_dim / n_rows)
+__device__ __forceinline__ void load_obs_chunks(const FwdArgs& a, int64_t tile, int64_t n_rows, uint32_t xrow, uint32_t xh, int obs_dim, float (&x)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = 0.f;
+  if (tile * 128 + xrow >= n_rows) return;
+  const int64_t xr = a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + xrow] : tile * 128 + xrow;
+  const float* src = a.obs + xr * a.obs_stride + 16 * xh;
+  const int c0 = 16 * (int)xh;
+  if ((a.obs_stride & 3) == 0) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (c0 + 4 * v + 4 <= obs_dim) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + 4 * v));
+        x[4 * v] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + 4 * v + j < obs_dim) x[4 * v + j] = __ldg(src + 4 * v + j);
+      }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < obs_dim) x[j] = __ldg(src + j);
   }
 }
 
@@ -210,170 +242,199 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   const float clipv = a.obs_clip > 0.f ? a.obs_clip : 3.0e38f;
   const uint64_t step = a.step + (a.step_base ? *a.step_base : 0ull);
 
-  for (int64_t tile = (int64_t)blockIdx.x * kSlots + slot; tile < n_tiles; tile += (int64_t)gridDim.x * kSlots) {
-    // ---- X tile: normalise (VecNormalize.normalize_obs), bf16, interleaved K-major; 2 threads per row, 2 chunks each
-    {
-      const bool xvalid = tile * 128 + xrow < n_rows;
-      const int64_t xr = !xvalid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + xrow] : tile * 128 + xrow);
+  long long* dbg = (blockIdx.x == 0 && slot == 0) ? g_phase_clk : nullptr;
+  int it = -1;
+  const int64_t tile_stride = (int64_t)gridDim.x * kSlots, tile0 = (int64_t)blockIdx.x * kSlots + slot;
+
+  // normalise (VecNormalize.normalize_obs) the raw row chunks in xbuf, write them as bf16 into the slot's X operand
+  // (interleaved K-major; 2 threads per row, 2 chunks of 8 columns each) and, if asked, as fp32 into obs_norm_out
+  auto stage_x = [&](int64_t tile, const float (&xraw)[16]) {
+    const bool xvalid = tile * 128 + xrow < n_rows;
+    const int64_t xr = !xvalid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + xrow] : tile * 128 + xrow);
 #pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {
-        const int q = 2 * (int)xh + qq, c0 = 8 * q;
-        float x[8];
+    for (int qq = 0; qq < 2; ++qq) {
+      const int q = 2 * (int)xh + qq, c0 = 8 * q;
+      float x[8];
+      uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.f;
-        if (xvalid && c0 < obs_dim) {
-          const float* src = a.obs + xr * a.obs_stride + c0;
-          if ((a.obs_stride & 3) == 0 && c0 + 8 <= obs_dim) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (c0 + j < obs_dim) x[j] = __ldg(src + j);
-          }
-        }
-        uint32_t w[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int j = 2 * h;
-          const float v0 = fminf(fmaxf((x[j] - sMean[c0 + j]) * sInv[c0 + j], -clipv), clipv);
-          const float v1 = fminf(fmaxf((x[j + 1] - sMean[c0 + j + 1]) * sInv[c0 + j + 1], -clipv), clipv);
-          x[j] = v0; x[j + 1] = v1;
-          __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
-          w[h] = *reinterpret_cast<uint32_t*>(&pk);
-        }
-        *reinterpret_cast<uint4*>(slotp + kSlotX + chunk_off(xrow, q, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
-        if (a.obs_norm_out && xvalid) {
-          float* dst = a.obs_norm_out + xr * obs_dim + c0;
+      for (int h = 0; h < 4; ++h) {
+        const float v0 = fminf(fmaxf((xraw[8 * qq + 2 * h] - sMean[c0 + 2 * h]) * sInv[c0 + 2 * h], -clipv), clipv);
+        const float v1 = fminf(fmaxf((xraw[8 * qq + 2 * h + 1] - sMean[c0 + 2 * h + 1]) * sInv[c0 + 2 * h + 1], -clipv), clipv);
+        x[2 * h] = v0; x[2 * h + 1] = v1;
+        __nv_bfloat162 pk = __floats2bfloat162_rn(v0, v1);
+        w[h] = *reinterpret_cast<uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(slotp + kSlotX + chunk_off(xrow, q, 128)) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (a.obs_norm_out && xvalid) {
+        float* dst = a.obs_norm_out + xr * obs_dim + c0;
+        if ((obs_dim & 3) == 0 && c0 + 8 <= obs_dim) {
+          *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (c0 + j < obs_dim) dst[j] = x[j];
         }
       }
     }
-    fence_async_smem();
-    fence_before_sync();
-    slot_sync(slot);
-    // ---- [L1p]
-    if (st == 0) {
-      fence_after_sync();
+  };
+  // last epilogue of a tile: action mean + value out of TMEM, Gaussian sample, log-prob, clipping, global stores
+  auto finish_tile = [&](int64_t tile) {
+    if (swarp >= 4) return;  // one thread per row
+    const bool valid = tile * 128 + erow < n_rows;
+    const int64_t row = !valid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + erow] : tile * 128 + erow);
+    uint32_t r[16];
+    tmem_ld16(tacc_row + kTmemOut, r);
+    tmem_ld_wait();
+    if (!valid) return;
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, act[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ks = 0; ks < kIn / 16; ++ks)
-        mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
-      mma_commit(bar);
+    for (int j = 0; j < 4; ++j)
+      if (j < act_dim) mean[j] = __uint_as_float(r[j]) + sB3[j];
+    float value = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (j == act_dim) value = __uint_as_float(r[j]) + sB3[j];
+    float logp = 0.f;
+    if (!a.deterministic) {
+      const uint64_t gid = a.row0 + (uint64_t)row;
+      const uint4 b = qx::philox4x32_10(make_uint4(0u, 3u, (uint32_t)step, (uint32_t)(step >> 32)), a.seed_lo ^ (uint32_t)gid,
+                                        a.seed_hi ^ (uint32_t)(gid >> 32));
+      const float ra = sqrtf(-2.f * __logf(qx::u01(b.x))), rb = sqrtf(-2.f * __logf(qx::u01(b.z)));
+      float s0, c0, s1, c1;
+      __sincosf(6.28318530718f * qx::u01(b.y) - 3.14159265359f, &s0, &c0);
+      __sincosf(6.28318530718f * qx::u01(b.w) - 3.14159265359f, &s1, &c1);
+      nz[0] = -ra * c0; nz[1] = -ra * s0; nz[2] = -rb * c1; nz[3] = -rb * s1;
     }
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    hidden_epilogue(tacc_row, sB1, slotp + kSlotH, erow, ecol0);
-    fence_async_smem();
-    fence_before_sync();
-    slot_sync(slot);
-    // ---- [L2p]
-    if (st == 0) {
-      fence_after_sync();
 #pragma unroll
-      for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2p + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
-      mma_commit(bar);
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    hidden_epilogue(tacc_row, sB2, slotp + kSlotH, erow, ecol0);
-    fence_async_smem();
-    fence_before_sync();
-    slot_sync(slot);
-    // ---- [L3p, L1v]: action head from H2p into the out columns; critic layer 1 from X into the accumulator
-    if (st == 0) {
-      fence_after_sync();
-#pragma unroll
-      for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + ks * 2 * LBO_W3, LBO_W3, 128), idesc_o, ks > 0);
-#pragma unroll
-      for (int ks = 0; ks < kIn / 16; ++ks)
-        mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + kHid * 16 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
-      mma_commit(bar);
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    hidden_epilogue(tacc_row, sB1 + kHid, slotp + kSlotH, erow, ecol0);
-    fence_async_smem();
-    fence_before_sync();
-    slot_sync(slot);
-    // ---- [L2v]
-    if (st == 0) {
-      fence_after_sync();
-#pragma unroll
-      for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2v + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
-      mma_commit(bar);
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    hidden_epilogue(tacc_row, sB2 + kHid, slotp + kSlotH, erow, ecol0);
-    fence_async_smem();
-    fence_before_sync();
-    slot_sync(slot);
-    // ---- [L3v]: value head from H2v, accumulated onto the action-head result
-    if (st == 0) {
-      fence_after_sync();
-#pragma unroll
-      for (int ks = 0; ks < kHid / 16; ++ks)
-        mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + (16 + ks * 2) * LBO_W3, LBO_W3, 128), idesc_o, true);
-      mma_commit(bar);
-    }
-    mbar_wait(bar, phase); phase ^= 1;
-    fence_after_sync();
-    if (swarp < 4) {  // one thread per row finishes the sample
-      const bool valid = tile * 128 + erow < n_rows;
-      const int64_t row = !valid ? 0 : (a.gather_idx ? (int64_t)a.gather_idx[tile * 128 + erow] : tile * 128 + erow);
-      uint32_t r[16];
-      tmem_ld16(tacc_row + kTmemOut, r);
-      tmem_ld_wait();
-      if (valid) {
-        float mean[4] = {0.f, 0.f, 0.f, 0.f}, act[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < act_dim) mean[j] = __uint_as_float(r[j]) + sB3[j];
-        float value = 0.f;
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
-          if (j == act_dim) value = __uint_as_float(r[j]) + sB3[j];
-        float logp = 0.f;
-        if (!a.deterministic) {
-          const uint64_t gid = a.row0 + (uint64_t)row;
-          const uint4 b = qx::philox4x32_10(make_uint4(0u, 3u, (uint32_t)step, (uint32_t)(step >> 32)),
-                                            a.seed_lo ^ (uint32_t)gid, a.seed_hi ^ (uint32_t)(gid >> 32));
-          const float ra = sqrtf(-2.f * __logf(qx::u01(b.x))), rb = sqrtf(-2.f * __logf(qx::u01(b.z)));
-          float s0, c0, s1, c1;
-          __sincosf(6.28318530718f * qx::u01(b.y) - 3.14159265359f, &s0, &c0);
-          __sincosf(6.28318530718f * qx::u01(b.w) - 3.14159265359f, &s1, &c1);
-          nz[0] = -ra * c0; nz[1] = -ra * s0; nz[2] = -rb * c1; nz[3] = -rb * s1;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < act_dim) {
-            const float ls = __ldg(a.p.log_std + j);
-            act[j] = fmaf(__expf(ls), nz[j], mean[j]);
-            logp += -0.5f * nz[j] * nz[j] - ls - 0.91893853320467f;
-          }
-        if (act_dim == 4) {
-          if (a.actions) *reinterpret_cast<float4*>(a.actions + row * 4) = make_float4(act[0], act[1], act[2], act[3]);
-          if (a.env_actions)
-            *reinterpret_cast<float4*>(a.env_actions + row * 4) =
-                make_float4(qx::clampf(act[0], -1.f, 1.f), qx::clampf(act[1], -1.f, 1.f), qx::clampf(act[2], -1.f, 1.f), qx::clampf(act[3], -1.f, 1.f));
-        } else {
-          for (int j = 0; j < act_dim; ++j) {
-            if (a.actions) a.actions[row * act_dim + j] = act[j];
-            if (a.env_actions) a.env_actions[row * act_dim + j] = qx::clampf(act[j], -1.f, 1.f);
-          }
-        }
-        if (a.values) a.values[row] = value;
-        if (a.log_probs) a.log_probs[row] = logp;
-        if (a.boot_reward && a.boot_tr[row] && !a.boot_te[row]) a.boot_reward[row] = fmaf(a.boot_gamma, value, a.boot_reward[row]);
+    for (int j = 0; j < 4; ++j)
+      if (j < act_dim) {
+        const float ls = __ldg(a.p.log_std + j);
+        act[j] = fmaf(__expf(ls), nz[j], mean[j]);
+        logp += -0.5f * nz[j] * nz[j] - ls - 0.91893853320467f;
+      }
+    if (act_dim == 4) {
+      if (a.actions) *reinterpret_cast<float4*>(a.actions + row * 4) = make_float4(act[0], act[1], act[2], act[3]);
+      if (a.env_actions)
+        *reinterpret_cast<float4*>(a.env_actions + row * 4) =
+            make_float4(qx::clampf(act[0], -1.f, 1.f), qx::clampf(act[1], -1.f, 1.f), qx::clampf(act[2], -1.f, 1.f), qx::clampf(act[3], -1.f, 1.f));
+    } else {
+      for (int j = 0; j < act_dim; ++j) {
+        if (a.actions) a.actions[row * act_dim + j] = act[j];
+        if (a.env_actions) a.env_actions[row * act_dim + j] = qx::clampf(act[j], -1.f, 1.f);
       }
     }
+    if (a.values) a.values[row] = value;
+    if (a.log_probs) a.log_probs[row] = logp;
+    if (a.boot_reward && a.boot_tr[row] && !a.boot_te[row]) a.boot_reward[row] = fmaf(a.boot_gamma, value, a.boot_reward[row]);
+  };
+  auto issue_l1p = [&]() {
+#pragma unroll
+    for (int ks = 0; ks < kIn / 16; ++ks)
+      mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
+  };
+
+  // Software pipeline over this slot's tiles.  Commit groups per tile i:
+  //   G_a = {L3v(i-1), L1p(i)}   G_b = {L2p(i)}   G_c = {L3p(i), L1v(i)}   G_d = {L2v(i)}
+  // The X operand of tile i+1 is staged (from registers prefetched one tile earlier) right after G_c(i) released X,
+  // so neither its global-memory latency nor the global stores (obs_norm_out, actions, ...) sit between a
+  // fence.proxy.async and the barrier that precedes an MMA issue.
+  if (tile0 < n_tiles) {
+    float xbuf[16];
+    load_obs_chunks(a, tile0, n_rows, xrow, xh, obs_dim, xbuf);
+    stage_x(tile0, xbuf);
+    load_obs_chunks(a, tile0 + tile_stride, n_rows, xrow, xh, obs_dim, xbuf);
+    fence_async_smem();
     fence_before_sync();
-    slot_sync(slot);  // the slot's TMEM columns and X buffer are reused by its next tile
+    slot_sync(slot);
+    if (st == 0) { fence_after_sync(); issue_l1p(); mma_commit(bar); }
+    int64_t prev = -1;
+    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+      ++it;
+      PHASE_STAMP(0);
+      // ---- G_a: action/value of the previous tile are complete, and this tile's actor layer 1
+      mbar_wait(bar, phase); phase ^= 1;
+      fence_after_sync();
+      PHASE_STAMP(1);
+      if (prev >= 0) finish_tile(prev);
+      hidden_epilogue(tacc_row, sB1, slotp + kSlotH, erow, ecol0);
+      fence_async_smem();
+      fence_before_sync();
+      slot_sync(slot);
+      PHASE_STAMP(2);
+      // ---- G_b = [L2p]
+      if (st == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < kHid / 16; ++ks)
+          mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2p + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, phase); phase ^= 1;
+      fence_after_sync();
+      PHASE_STAMP(3);
+      hidden_epilogue(tacc_row, sB2, slotp + kSlotH, erow, ecol0);
+      fence_async_smem();
+      fence_before_sync();
+      slot_sync(slot);
+      PHASE_STAMP(4);
+      // ---- G_c = [L3p, L1v]: action head from H2p into the out columns; critic layer 1 from X into the accumulator
+      if (st == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < kHid / 16; ++ks)
+          mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + ks * 2 * LBO_W3, LBO_W3, 128), idesc_o, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < kIn / 16; ++ks)
+          mma_bf16(tacc, make_desc(sX + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW1 + kHid * 16 + ks * 2 * LBO_W1, LBO_W1, 128), idesc_h, ks > 0);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, phase); phase ^= 1;
+      fence_after_sync();
+      PHASE_STAMP(5);
+      // X is free: stage the next tile (its raw rows are in xbuf) and request the one after
+      const int64_t next = tile + tile_stride;
+      if (next < n_tiles) {
+        stage_x(next, xbuf);
+        load_obs_chunks(a, next + tile_stride, n_rows, xrow, xh, obs_dim, xbuf);
+      }
+      hidden_epilogue(tacc_row, sB1 + kHid, slotp + kSlotH, erow, ecol0);
+      fence_async_smem();
+      fence_before_sync();
+      slot_sync(slot);
+      PHASE_STAMP(6);
+      // ---- G_d = [L2v]
+      if (st == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < kHid / 16; ++ks)
+          mma_bf16(tacc, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW2v + ks * 2 * LBO_W2, LBO_W2, 128), idesc_h, ks > 0);
+        mma_commit(bar);
+      }
+      mbar_wait(bar, phase); phase ^= 1;
+      fence_after_sync();
+      PHASE_STAMP(7);
+      hidden_epilogue(tacc_row, sB2 + kHid, slotp + kSlotH, erow, ecol0);
+      fence_async_smem();
+      fence_before_sync();
+      slot_sync(slot);
+      PHASE_STAMP(8);
+      // ---- G_a of the next tile = [L3v (value head accumulated onto the action-head result), L1p(next)]
+      if (st == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < kHid / 16; ++ks)
+          mma_bf16(tacc + kTmemOut, make_desc(sH + ks * 2 * LBO_ACT, LBO_ACT, 128), make_desc(sW3 + (16 + ks * 2) * LBO_W3, LBO_W3, 128), idesc_o, true);
+        if (next < n_tiles) issue_l1p();
+        mma_commit(bar);
+      }
+      prev = tile;
+      PHASE_STAMP(9);
+    }
+    mbar_wait(bar, phase); phase ^= 1;
+    fence_after_sync();
+    finish_tile(prev);
+    fence_before_sync();
   }
   __syncthreads();
   if (tid < 32) tmem_dealloc(tmem_slot, kTmemCols);
@@ -632,4 +693,9 @@ extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminat
   if (rc) return rc;
   ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_reward_normalize: launch failed");
+}
+
+// debug / tuning hook (not part of the public header): device buffer of 8 x 16 int64 clock stamps, or NULL to switch off
+extern "C" int ppo_debug_phase_clock(long long* dev_buf) {
+  return cudaMemcpyToSymbol(ppo::g_phase_clk, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? QX_OK : QX_ECUDA;
 }
