@@ -314,7 +314,8 @@ class RolloutEngine:
 
     def _rollout_body(self) -> None:
         for t in range(self.T):
-            self._step(t)
+            with torch.cuda.nvtx.range(f"rollout_step_{t}"):  # shows up per step in nsys / ncu timelines
+                self._step(t)
         stats = self.obs_stats if self.cfg.norm_obs else None
         policy_forward(self.pol, self.cur_obs, obs_stats=stats, obs_clip=self.cfg.clip_obs, deterministic=True, values=self.last_values)
         gae(self.rewards, self.values, self.dones, self.last_values, self.cfg.gamma, self.cfg.gae_lambda, self.advantages, self.returns)
@@ -414,9 +415,11 @@ class PPOTrainer:
         return {k: float(v) / max(n_mb, 1) for k, v in stats.items()}
 
     def learn_iteration(self) -> dict:
-        self.rollout.collect()
+        with torch.cuda.nvtx.range("ppo_collect_rollouts"):
+            self.rollout.collect()
         self.num_timesteps += self.rollout.T * self.rollout.n * self.world
-        out = self.update()
+        with torch.cuda.nvtx.range("ppo_update"):
+            out = self.update()
         s, l, c = self.sim.episode_stats(clear=True)
         if self.world > 1:
             t = torch.tensor([s, float(l), float(c)], device=self.device, dtype=torch.float64)

@@ -362,3 +362,32 @@ def test_nonfinite_state_is_contained(pkg):
     assert torch.isfinite(o0).all() and envs[0].sim.nonfinite_count() == 3
     for e in envs:
         e.close()
+
+
+def test_gym_api_conformance(pkg):
+    """What SB3's check_env (yaw.py:217) asserts about a gymnasium env, for both single-env facades: spaces, dtypes,
+    reset -> (obs, info), step -> (obs, float, bool, bool, dict), observations inside the observation space."""
+    for make, od, ad in ((lambda: pkg.QuadXHoverEnv(seed=1), 20, 4), (lambda: pkg.DroneEnv(seed=1), 12, 1)):
+        env = make()
+        assert env.action_space.shape == (ad,) and env.observation_space.shape == (od,)
+        assert np.all(env.action_space.low == -1) and np.all(env.action_space.high == 1)
+        obs, info = env.reset(seed=0)
+        assert isinstance(info, dict) and obs.shape == (od,) and np.all(np.isfinite(obs))
+        rng = np.random.default_rng(0)
+        for _ in range(5):
+            a = env.action_space.sample(rng)
+            assert env.action_space.contains(a)
+            out = env.step(a)
+            assert len(out) == 5
+            obs, r, te, tr, info = out
+            assert obs.shape == (od,) and isinstance(r, float) and isinstance(te, bool) and isinstance(tr, bool) and isinstance(info, dict)
+            assert np.all(obs >= env.observation_space.low - 1e-6) and np.all(obs <= env.observation_space.high + 1e-6)
+        if od == 20:
+            assert obs.dtype == np.float64 and set(info) == {"out_of_bounds", "collision", "env_complete", "on_floor"}  # hover.py:53-57,70
+        env.close()
+    # the env refuses wrong-shaped device buffers loudly instead of corrupting memory
+    sim = pkg.QuadXSim(64)
+    with pytest.raises(ValueError):
+        sim.step(torch.zeros(63, 4, device="cuda"), None, torch.zeros(64, device="cuda"), torch.zeros(64, dtype=torch.uint8, device="cuda"),
+                 torch.zeros(64, dtype=torch.uint8, device="cuda"))
+    sim.close()
