@@ -132,3 +132,47 @@ def test_episode_accounting_at_scale(pkg):
     assert done_at == [31] and c == n and l == 32 * n
     assert -101.5 * n < s - (-30.0 * n) < -50.0 * n  # 31 shaped steps + one -100
     env.close()
+
+
+def test_chunked_host_pipeline_equals_device_path(pkg):
+    """qx_step_host cuts batches >= 2^17 into 8 chunks pipelined over three streams (H2D | kernels | D2H); the results
+    must be those of the plain device-buffer call, including across a mass termination (reset queue per chunk), with
+    pinned and with pageable host buffers, for a batch size that is not a multiple of anything."""
+    n = (1 << 17) + 37
+    cfg = pkg.default_config()
+    sim_h = pkg.QuadXSim(n, cfg, seed=3)
+    sim_d = pkg.QuadXSim(n, pkg.default_config(), seed=3)
+    d = sim_d.device
+    obs = torch.zeros(n, 20, device=d); rew = torch.zeros(n, device=d)
+    te = torch.zeros(n, dtype=torch.uint8, device=d); tr = torch.zeros_like(te)
+    sim_d.reset(obs)
+    torch.cuda.synchronize()
+    assert np.array_equal(sim_h.reset_host(), obs.cpu().numpy())
+    import ctypes as C
+
+    from fpv_drone_rl_agent_b200 import _lib
+
+    L = _lib.lib()
+    a_pin = torch.zeros(n, 4).pin_memory(); o_pin = torch.zeros(n, 20).pin_memory(); r_pin = torch.zeros(n).pin_memory()
+    te_pin = torch.zeros(n, dtype=torch.uint8).pin_memory(); tr_pin = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    g = torch.Generator().manual_seed(0)
+    for k in range(34):  # zero thrust: every env terminates on its 32nd step
+        a = torch.rand(n, 4, generator=g) * 0.2 - 0.1
+        a[:, 3] = -1.0
+        sim_d.step(a.to(d), obs, rew, te, tr)
+        torch.cuda.synchronize()
+        if k % 2 == 0:  # pinned buffers, used in place
+            a_pin.copy_(a)
+            _lib.check(L.qx_step_host(sim_h._h, C.c_void_p(a_pin.data_ptr()), C.c_void_p(o_pin.data_ptr()), C.c_void_p(r_pin.data_ptr()),
+                                      C.c_void_p(te_pin.data_ptr()), C.c_void_p(tr_pin.data_ptr()), None))
+            o2, r2, te2, tr2 = o_pin.numpy(), r_pin.numpy(), te_pin.numpy().astype(bool), tr_pin.numpy().astype(bool)
+        else:  # pageable numpy buffers through the staging area
+            o2, r2, te2, tr2, _ = sim_h.step_host(a.numpy())
+        assert np.array_equal(obs.cpu().numpy(), o2) and np.array_equal(rew.cpu().numpy(), r2), k
+        assert np.array_equal(te.cpu().numpy().astype(bool), te2) and np.array_equal(tr.cpu().numpy().astype(bool), tr2), k
+        if k == 31:
+            assert te2.all()
+    sa, sb = sim_h.get_state(), sim_d.get_state()
+    for key in sa:
+        assert np.array_equal(sa[key], sb[key]), key
+    assert sim_h.episode_stats()[1:] == sim_d.episode_stats()[1:] == (32 * n, n)
