@@ -294,6 +294,20 @@ def main_ours(args):
             r = cpu_run(args.cpu_envs, 150, 2, budget_s=12.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
     sim.close()
+    if world > 1 and not args.no_ppo:
+        # metric M2 at N GPUs: every rank collects its own rollouts (env shard + policy replica, no collective in the
+        # rollout); aggregate samples/s = total samples / slowest rank
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_ppo
+
+        m = bench_ppo.measure(131072, 32, rank=rank, world=world, rollout_only=True)
+        t = torch.tensor([m["rollout"]["ms_per_rollout"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            m["rollout"]["ms_per_rollout"] = float(t.item())
+            m["rollout"]["samples_per_s"] = world * 131072 * 32 / (float(t.item()) * 1e-3)
+            m["rollout"]["what"] += "; aggregate over all ranks, slowest rank's time"
+            line["ppo"] = m
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

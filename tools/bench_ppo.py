@@ -20,7 +20,7 @@ FLOP_PER_SAMPLE = 77056  # [128,128] pi and vf nets on 20-D obs
 GAE_BYTES = 17  # r, V, done in; adv, ret out
 
 
-def measure(envs: int = 131072, steps: int = 32, reps: int = 5) -> dict:
+def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, world: int = 1, rollout_only: bool = False) -> dict:
     import torch
 
     from fpv_drone_rl_agent_b200 import ppo
@@ -33,7 +33,7 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5) -> dict:
     tflops_peak = peaks.get("bf16_tflops", 1590.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     cfg = ppo.PPOConfig(n_envs=envs, n_steps=steps, seed=0, use_cuda_graph=True)
-    tr = ppo.PPOTrainer(cfg, device=dev)
+    tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world)
     ro = tr.rollout
 
     def timed(fn, reps=reps):
@@ -51,6 +51,9 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5) -> dict:
     out = {"envs": envs, "n_steps": steps,
            "rollout": {"samples_per_s": envs * steps / (ms * 1e-3), "ms_per_rollout": ms, "launches_per_rollout": ro.launches_per_rollout,
                        "what": "env step + reset + obs/reward normalisation + policy forward + sampling + time-limit bootstrap, x n_steps, + GAE; one CUDA graph replay"}}
+    if rollout_only:
+        tr.sim.close()
+        return out
     # stand-alone policy forward over a batch larger than L2 is pointless (weights are tiny; activations stay on chip):
     # use the rollout's own batch, all outputs on
     n = envs
