@@ -243,6 +243,8 @@ class PPOConfig:
     use_cuda_graph: bool = True
     target_kl: float = 0.0  # SB3 PPO target_kl: stop the epoch loop once the approximate KL exceeds 1.5 x this (0 = off)
     log_std_init: float = 0.0  # SB3 policy_kwargs log_std_init
+    graph_update: bool = True  # replay one captured minibatch step instead of ~25 eager launches (single GPU)
+    tf32_update: bool = True  # library GEMMs of the update in TF32 (the rollout forward is bf16 on the tensor cores anyway)
 
 
 class RolloutEngine:
@@ -351,6 +353,8 @@ class PPOTrainer:
         self.cfg, self.rank, self.world = cfg, rank, world
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = dev
+        if cfg.tf32_update:
+            torch.backends.cuda.matmul.allow_tf32 = True
         torch.manual_seed(cfg.seed)  # identical initial weights on every rank
         self.model = (ActorCritic(log_std_init=cfg.log_std_init) if task == 0 else ActorCritic(12, 1, log_std_init=cfg.log_std_init)).to(dev)
         self.packed = PackedPolicy(self.model, dev)
@@ -360,7 +364,7 @@ class PPOTrainer:
         ecfg.update(auto_reset=1)
         self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev, task=task)
         self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=shard_env_ids(rank, cfg.n_envs))
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5)
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5, capturable=bool(cfg.graph_update and world == 1))
         self.num_timesteps = 0
         self._flat_grad = None
         self.gen = torch.Generator(device=dev).manual_seed(cfg.seed + 1000 + rank)
@@ -368,51 +372,92 @@ class PPOTrainer:
     def _allreduce_grads(self) -> None:
         allreduce_gradients(self.model.parameters(), self.world)
 
-    def update(self) -> dict:
+    # one PPO minibatch: loss of SB3's PPO.train (clipped surrogate + vf_coef * MSE - ent_coef * entropy, advantages
+    # normalised per minibatch) and the diagnostics it logs; `acc` accumulates [pg, vf, kl, clipfrac, approx_kl_k3]
+    def _minibatch_loss(self, idx: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
         cfg, ro = self.cfg, self.rollout
         N = ro.T * ro.n
-        obs = ro.obs.view(N, -1)
-        act = ro.actions.view(N, -1)
-        old_logp, adv_all, ret_all, old_v = ro.log_probs.view(N), ro.advantages.view(N), ro.returns.view(N), ro.values.view(N)
+        obs, act = ro.obs.view(N, -1), ro.actions.view(N, -1)
+        old_logp, adv_all, ret_all = ro.log_probs.view(N), ro.advantages.view(N), ro.returns.view(N)
+        adv = adv_all[idx]
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        value, logp, entropy = self.model.evaluate_actions(obs[idx], act[idx])
+        lr_ = logp - old_logp[idx]
+        ratio = torch.exp(lr_)
+        pg = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+        vf = torch.nn.functional.mse_loss(ret_all[idx], value)
+        loss = pg + cfg.vf_coef * vf - cfg.ent_coef * entropy.mean()
+        with torch.no_grad():
+            acc += torch.stack([pg.detach(), vf.detach(), -lr_.mean(), ((ratio - 1).abs() > cfg.clip_range).float().mean(),
+                                ((ratio - 1) - lr_).mean()])
+        return loss
+
+    def _step_eager(self, idx: torch.Tensor, acc: torch.Tensor) -> None:
+        loss = self._minibatch_loss(idx, acc)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self._allreduce_grads()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.cfg.max_grad_norm)
+        self.opt.step()
+
+    def _build_update_graph(self, bs: int) -> None:
+        """Capture one minibatch step (gather, forward, loss, backward, grad clip, Adam) into a CUDA graph: the network has
+        39 k parameters, so an eager step is ~25 tiny launches of pure launch latency.  Single-GPU only (the all-reduce
+        stays eager)."""
+        import copy
+
+        self._g_idx = torch.zeros(bs, dtype=torch.int64, device=self.device)
+        self._g_acc = torch.zeros(5, device=self.device)
+        model_sd, opt_sd = copy.deepcopy(self.model.state_dict()), copy.deepcopy(self.opt.state_dict())
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm-up on a side stream, as CUDA-graph capture of an optimiser requires
+                self._step_eager(self._g_idx, self._g_acc)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.opt.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_eager(self._g_idx, self._g_acc)
+        self.model.load_state_dict(model_sd)  # the warm-up steps must not count as training
+        self.opt.load_state_dict(opt_sd)
+        self._update_graph = g
+
+    def update(self) -> dict:
+        """SB3 PPO.train: n_epochs passes over the rollout in shuffled minibatches; target_kl stops the remaining epochs
+        once the mean approximate KL of an epoch exceeds 1.5 x target (SB3 checks per minibatch; per epoch here, so that
+        the check costs one host sync per epoch)."""
+        cfg, ro = self.cfg, self.rollout
+        N = ro.T * ro.n
         bs = min(cfg.batch_size, N)
-        stats = {"pg": 0.0, "vf": 0.0, "kl": 0.0, "clipfrac": 0.0}
+        use_graph = cfg.graph_update and self.world == 1
+        if use_graph and getattr(self, "_update_graph", None) is None:
+            self._build_update_graph(bs)
+        acc = self._g_acc if use_graph else torch.zeros(5, device=self.device)
+        acc.zero_()
         n_mb = 0
-        stop = False
         for _ in range(cfg.n_epochs):
-            if stop:
-                break
             perm = torch.randperm(N, device=self.device, generator=self.gen)
+            kl_before = acc[4].clone()
+            n_epoch = 0
             for s in range(0, N - bs + 1, bs):
-                idx = perm[s:s + bs]
-                adv = adv_all[idx]
-                adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-                value, logp, entropy = self.model.evaluate_actions(obs[idx], act[idx])
-                ratio = torch.exp(logp - old_logp[idx])
-                pg = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                vf = torch.nn.functional.mse_loss(ret_all[idx], value)
-                loss = pg + cfg.vf_coef * vf - cfg.ent_coef * entropy.mean()
-                if cfg.target_kl > 0.0:  # SB3: early stop on the k3 estimator, checked once per epoch to avoid a sync per minibatch
-                    if s == 0:
-                        with torch.no_grad():
-                            lr_ = logp - old_logp[idx]
-                            akl = ((torch.exp(lr_) - 1) - lr_).mean()
-                            if self.world > 1:
-                                dist.all_reduce(akl); akl /= self.world
-                        if float(akl) > 1.5 * cfg.target_kl:
-                            stop = True
-                            break
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
-                self._allreduce_grads()
-                torch.nn.utils.clip_grad_norm_(self.model.parameters(), cfg.max_grad_norm)
-                self.opt.step()
-                with torch.no_grad():
-                    stats["pg"] += pg.detach(); stats["vf"] += vf.detach()
-                    stats["kl"] += (old_logp[idx] - logp).mean().detach()
-                    stats["clipfrac"] += ((ratio - 1).abs() > cfg.clip_range).float().mean()
-                n_mb += 1
+                if use_graph:
+                    self._g_idx.copy_(perm[s:s + bs])
+                    self._update_graph.replay()
+                else:
+                    self._step_eager(perm[s:s + bs], acc)
+                n_epoch += 1
+            n_mb += n_epoch
+            if cfg.target_kl > 0.0:
+                akl = (acc[4] - kl_before) / max(n_epoch, 1)
+                if self.world > 1:
+                    dist.all_reduce(akl)
+                    akl /= self.world
+                if float(akl) > 1.5 * cfg.target_kl:
+                    break
         self.packed.refresh()
-        return {k: float(v) / max(n_mb, 1) for k, v in stats.items()}
+        out = (acc / max(n_mb, 1)).tolist()
+        return {"pg": out[0], "vf": out[1], "kl": out[2], "clipfrac": out[3]}
 
     def learn_iteration(self) -> dict:
         with torch.cuda.nvtx.range("ppo_collect_rollouts"):
