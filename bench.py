@@ -138,6 +138,43 @@ def cpu_run(n_envs: int, steps: int, warmup: int, budget_s: float = 25.0) -> dic
             "ms_per_step": 1e3 * dt / done}
 
 
+def cpu_extras() -> dict:
+    """The other CPU yardsticks of BASELINE.md section 3 (each ~2 s): numpy oracle with one env in a Python loop (the closest
+    analogue of one PyFlyt env process, minus rendering), numpy oracle vectorised over 4096 envs, the C port on one thread."""
+    import numpy as np
+
+    from oracle.hover_oracle import HoverConfig, HoverVecOracle
+
+    out = {}
+    for name, n, budget in (("numpy_1env_python_loop", 1, 2.0), ("numpy_vectorised_4096_envs_1core", 4096, 3.0)):
+        sim = HoverVecOracle(n, cfg=HoverConfig(start_pos=(0, 0, 1.0), spawn_throttle=HOVER_THR), seed=1234, noise=True)
+        sim.reset()
+        a = np.zeros((n, 4)); a[:, 3] = 2 * HOVER_THR - 1
+        sim.step(a)
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget:
+            sim.step(a); k += 1
+        out[name] = n * k / (time.perf_counter() - t0)
+    try:
+        from oracle import c_oracle
+
+        os.environ["ORC_THREADS"] = "1"
+        sim = c_oracle.COracle(16384, seed=1234, start_pos=(0, 0, 1.0), spawn_throttle=HOVER_THR)
+        sim.reset()
+        a = np.zeros((16384, 4)); a[:, 3] = 2 * HOVER_THR - 1
+        sim.step(a)
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            sim.step(a); k += 1
+        out["c_port_1_thread"] = 16384 * k / (time.perf_counter() - t0)
+    except Exception as exc:  # noqa: BLE001
+        out["c_port_1_thread"] = f"unavailable: {exc}"
+    finally:
+        os.environ.pop("ORC_THREADS", None)
+    out["reference_logged_tensorboard_fps"] = "832-1003 env-steps/s on 16 SubprocVecEnv processes (author's PC; SAC + PyBullet + 6 CPU renders per step) -- quoted, different machine"
+    return out
+
+
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -293,6 +330,7 @@ def main_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(args.cpu_envs, 150, 2, budget_s=12.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
+            line["cpu_baseline"]["others_env_steps_per_s"] = cpu_extras()
     sim.close()
     if world > 1 and not args.no_ppo:
         # metric M2 at N GPUs: every rank collects its own rollouts (env shard + policy replica, no collective in the
