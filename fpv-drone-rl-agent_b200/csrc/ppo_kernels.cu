@@ -9,6 +9,7 @@
 
 #include "../../include/ppo_b200.h"
 #include "../../include/quadx_b200.h"
+#include "qx_internal.h"
 #include "qx_model.cuh"
 #include "tc05.cuh"
 
@@ -600,10 +601,7 @@ __global__ void __launch_bounds__(256) reward_norm_kernel(const float* __restric
 
 }  // namespace ppo
 
-static int pfail(int code, const char* msg) {
-  fprintf(stderr, "libquadx_b200/ppo: %s\n", msg);
-  return code;
-}
+static int pfail(int code, const char* msg) { return qx_fail(code, "%s", msg); }
 
 extern "C" int ppo_test_gemm(const void* a, const void* b, float* d, int32_t n, int32_t k, void* stream) {
   if (!a || !b || !d || n < 16 || n > 256 || n % 16 || k < 16 || k % 16) return pfail(QX_EINVAL, "ppo_test_gemm: bad arguments");

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -21,6 +22,7 @@
 #include <new>
 
 #include "../../include/quadx_b200.h"
+#include "qx_internal.h"
 #include "qx_model.cuh"
 
 namespace qx {
@@ -175,7 +177,12 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       // ---- Aviary.step() x ratio: control on every ctrl_every-th sub-step
       float pwm[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t stream = phase ? STREAM_RESET : STREAM_STEP;
-      if (c.ctrl_every == 2 && (nsub & 1) == 0) {
+#ifndef QX_NO_PAIR_LOOP
+      constexpr bool kPairLoop = true;
+#else
+      constexpr bool kPairLoop = false;
+#endif
+      if (kPairLoop && c.ctrl_every == 2 && (nsub & 1) == 0) {
         // default scheduling (control_hz = physics_hz / 2): one rate-PID update and one Philox call per
         // Aviary.step(), then its two physics sub-steps
         constexpr int kPairUnroll = QX_PAIR_UNROLL;
@@ -370,12 +377,14 @@ struct QxHandle {
 };
 
 static thread_local char g_err[512] = "";
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};
 
-static int fail(int code, const char* fmt, const char* detail = "") {
+// shared with ppo_kernels.cu (qx_internal.h): record the calling thread's last error, return the code
+int qx_fail(int code, const char* fmt, const char* detail) {
   snprintf(g_err, sizeof(g_err), fmt, detail);
   return code;
 }
+static int fail(int code, const char* fmt, const char* detail = "") { return qx_fail(code, fmt, detail); }
 #define QX_CUDA(call)                                                             \
   do {                                                                            \
     cudaError_t _e = (call);                                                      \
@@ -384,7 +393,7 @@ static int fail(int code, const char* fmt, const char* detail = "") {
 
 extern "C" const char* qx_last_error(void) { return g_err; }
 extern "C" int32_t qx_version(void) { return QX_VERSION; }
-extern "C" int64_t qx_launch_count(void) { return g_launches; }
+extern "C" int64_t qx_launch_count(void) { return g_launches.load(); }
 extern "C" int64_t qx_sizeof_config(void) { return (int64_t)sizeof(QxConfig); }
 
 extern "C" int qx_default_config(int32_t task, QxConfig* c) {
