@@ -532,24 +532,24 @@ __global__ void __launch_bounds__(1024) gae_warpscan_kernel(const float* __restr
 // ---------------------------------------------------------------------------
 constexpr int kStatBlocks = 296, kStatThreads = 256, kStatMaxDim = 32;
 
+// lane = column (dim <= 32), each warp strides over rows: a row is one coalesced load, no cross-lane reduction is needed;
+// the 8 warps of a block are combined through shared memory
 __global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float* __restrict__ x, int64_t stride, int64_t n, int dim, double* __restrict__ part) {
   __shared__ double sh[kStatThreads / 32][2 * kStatMaxDim];
-  double s[kStatMaxDim], q[kStatMaxDim];
-  for (int j = 0; j < kStatMaxDim; ++j) { s[j] = 0.0; q[j] = 0.0; }
-  for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStatThreads) {
-    const float* row = x + i * stride;
-#pragma unroll
-    for (int j = 0; j < kStatMaxDim; ++j)
-      if (j < dim) { const double v = (double)row[j]; s[j] += v; q[j] += v * v; }
-  }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < kStatMaxDim; ++j)
-    if (j < dim) {
-      double a = s[j], b = q[j];
-      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-      if (lane == 0) { sh[w][j] = a; sh[w][kStatMaxDim + j] = b; }
+  const int64_t warp_id = (int64_t)blockIdx.x * (kStatThreads / 32) + w, n_warps = (int64_t)gridDim.x * (kStatThreads / 32);
+  double s = 0.0, q = 0.0;
+  if (lane < dim) {
+    int64_t i = warp_id;
+    for (; i + 3 * n_warps < n; i += 4 * n_warps) {  // four independent loads in flight
+      const float v0 = x[i * stride + lane], v1 = x[(i + n_warps) * stride + lane], v2 = x[(i + 2 * n_warps) * stride + lane],
+                  v3 = x[(i + 3 * n_warps) * stride + lane];
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+      q += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
     }
+    for (; i < n; i += n_warps) { const double v = (double)x[i * stride + lane]; s += v; q += v * v; }
+  }
+  sh[w][lane] = s; sh[w][kStatMaxDim + lane] = q;
   __syncthreads();
   if (threadIdx.x < 2 * kStatMaxDim) {
     double a = 0.0;
@@ -558,14 +558,17 @@ __global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float
   }
 }
 
-__global__ void __launch_bounds__(64) stats_merge_kernel(const double* __restrict__ part, int nblocks, int64_t n, int dim, double* __restrict__ stats, float eps,
-                                                         float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
-  const int j = threadIdx.x;
+// one warp per column: lanes stride over the per-block partial sums, shuffle-reduce, lane 0 does the Welford merge
+__global__ void __launch_bounds__(kStatMaxDim * 32) stats_merge_kernel(const double* __restrict__ part, int nblocks, int64_t n, int dim, double* __restrict__ stats,
+                                                                      float eps, float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool on = j < dim;
+  double s = 0.0, q = 0.0;
+  if (on)
+    for (int b = lane; b < nblocks; b += 32) { s += part[(size_t)b * 2 * kStatMaxDim + j]; q += part[(size_t)b * 2 * kStatMaxDim + kStatMaxDim + j]; }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
   double new_mean = 0.0, new_var = 1.0, tot = 0.0;
   if (on) {
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblocks; ++b) { s += part[(size_t)b * 2 * kStatMaxDim + j]; q += part[(size_t)b * 2 * kStatMaxDim + kStatMaxDim + j]; }
     const double bc = (double)n, bm = s / bc, bv = fmax(q / bc - bm * bm, 0.0);
     const double mean = stats[j], var = stats[dim + j], count = stats[2 * dim];
     const double delta = bm - mean;
@@ -573,8 +576,8 @@ __global__ void __launch_bounds__(64) stats_merge_kernel(const double* __restric
     new_mean = mean + delta * bc / tot;
     new_var = (var * count + bv * bc + delta * delta * count * bc / tot) / tot;
   }
-  __syncthreads();  // every thread has read the old count before thread 0 replaces it
-  if (!on) return;
+  __syncthreads();  // every warp has read the old count before warp 0 replaces it
+  if (!on || lane != 0) return;
   stats[j] = new_mean;
   stats[dim + j] = new_var;
   if (j == 0) stats[2 * dim] = tot;
@@ -582,9 +585,25 @@ __global__ void __launch_bounds__(64) stats_merge_kernel(const double* __restric
   if (inv_std_f32) inv_std_f32[j] = (float)(1.0 / sqrt(new_var + (double)eps));
 }
 
-__global__ void __launch_bounds__(256) returns_acc_kernel(const float* __restrict__ r, float* __restrict__ acc, int64_t n, float gamma) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) acc[i] = fmaf(acc[i], gamma, r[i]);
+// reward path, first half fused: ret = ret * gamma + r (VecNormalize.step_wait) and the per-block sums of ret, ret^2
+__global__ void __launch_bounds__(kStatThreads) returns_partial_kernel(const float* __restrict__ r, float* __restrict__ acc, int64_t n, float gamma,
+                                                                      double* __restrict__ part) {
+  __shared__ double sh[kStatThreads / 32][2];
+  double s = 0.0, q = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStatThreads) {
+    const float v = fmaf(acc[i], gamma, r[i]);
+    acc[i] = v;
+    s += (double)v; q += (double)v * (double)v;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sh[w][0] = s; sh[w][1] = q; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int k = 0; k < kStatThreads / 32; ++k) a += sh[k][threadIdx.x];
+    part[(size_t)blockIdx.x * 2 * kStatMaxDim + (threadIdx.x ? kStatMaxDim : 0)] = a;
+  }
 }
 
 __global__ void __launch_bounds__(256) reward_norm_kernel(const float* __restrict__ r, const uint8_t* __restrict__ te, const uint8_t* __restrict__ tr, float* __restrict__ acc,
@@ -674,10 +693,10 @@ extern "C" int64_t ppo_running_stats_scratch_bytes(int32_t dim) { (void)dim; ret
 extern "C" int ppo_running_stats_update(const float* x, int64_t stride, int64_t n, int32_t dim, double* stats, float eps, float* mean_f32,
                                         float* inv_std_f32, void* scratch, void* stream) {
   if (!x || !stats || !scratch || n <= 0 || dim < 1 || dim > ppo::kStatMaxDim || stride < dim) return pfail(QX_EINVAL, "ppo_running_stats_update: bad arguments");
-  int64_t want = (n + ppo::kStatThreads - 1) / ppo::kStatThreads;
-  const int blocks = (int)(want < ppo::kStatBlocks ? want : ppo::kStatBlocks);
+  int64_t want = (n + ppo::kStatThreads / 32 * 4 - 1) / (ppo::kStatThreads / 32 * 4);  // >= 4 rows per warp
+  const int blocks = (int)(want < ppo::kStatBlocks ? (want < 1 ? 1 : want) : ppo::kStatBlocks);
   ppo::stats_partial_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(x, stride, n, dim, (double*)scratch);
-  ppo::stats_merge_kernel<<<1, 64, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, dim, stats, eps, mean_f32, inv_std_f32);
+  ppo::stats_merge_kernel<<<1, ppo::kStatMaxDim * 32, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, dim, stats, eps, mean_f32, inv_std_f32);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_running_stats_update: launch failed");
 }
 
@@ -686,9 +705,10 @@ extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminat
   if (!reward || !terminated || !truncated || !returns_acc || !ret_stats || !reward_out || !scratch || n <= 0)
     return pfail(QX_EINVAL, "ppo_reward_normalize: bad arguments");
   const unsigned grid = (unsigned)((n + 255) / 256);
-  ppo::returns_acc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma);
-  int rc = ppo_running_stats_update(returns_acc, 1, n, 1, ret_stats, eps, nullptr, nullptr, scratch, stream);
-  if (rc) return rc;
+  int64_t want = (n + ppo::kStatThreads - 1) / ppo::kStatThreads;
+  const int blocks = (int)(want < ppo::kStatBlocks ? want : ppo::kStatBlocks);
+  ppo::returns_partial_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma, (double*)scratch);
+  ppo::stats_merge_kernel<<<1, ppo::kStatMaxDim * 32, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, 1, ret_stats, eps, nullptr, nullptr);
   ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_reward_normalize: launch failed");
 }
