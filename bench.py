@@ -327,6 +327,8 @@ def main_ours(args):
             import bench_ppo
 
             line["ppo"] = bench_ppo.measure(131072, 32)
+            # BASELINE configs[2]: yaw task, 65 536 envs, full on-device rollout (policy forward + sampling + GAE), T = 128
+            line["ppo"]["yaw_65536"] = bench_ppo.measure(65536, 128, reps=3, task=1)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(args.cpu_envs, 150, 2, budget_s=12.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}

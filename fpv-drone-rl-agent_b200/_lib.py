@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libquadx_b200.so")
 QX_TASK_HOVER, QX_TASK_YAW = 0, 1
 QX_OBS_F32, QX_OBS_BF16 = 0, 1
 QX_STATE_WORDS = 44
+QX_STATE_WORDS_CASCADE = 68
 
 f32, i32 = C.c_float, C.c_int32
 
@@ -35,6 +36,8 @@ class QxConfig(C.Structure):
         ("agent_dt", f32), ("flight_dome_size", f32), ("floor_threshold", f32), ("target_area", f32), ("target_ratio", f32),
         ("action_scale", f32 * 3), ("start_pos", f32 * 3), ("start_rpy", f32 * 3), ("spawn_throttle", f32),
         ("spawn_pos_noise", f32), ("spawn_yaw_noise", f32), ("render", i32), ("auto_reset", i32), ("noise", i32),
+        ("flight_mode", i32), ("thrust_scale", f32), ("thrust_bias", f32), ("att_pid", f32 * 12), ("vel_pid", f32 * 8),
+        ("pos_pid", f32 * 8), ("zpos_pid", f32 * 4), ("zvel_pid", f32 * 4),
     ]
 
     def update(self, **kw) -> "QxConfig":
@@ -95,6 +98,7 @@ def lib() -> C.CDLL:
         "qx_obs_dim": (i32, [vp]),
         "qx_act_dim": (i32, [vp]),
         "qx_state_ptr": (vp, [vp]),
+        "qx_state_words": (i32, [vp]),
         "qx_launch_count": (i64, []),
         "qx_sizeof_config": (i64, []),
         "qx_last_error": (C.c_char_p, []),
@@ -119,7 +123,7 @@ def lib() -> C.CDLL:
 
 EXPORTED = [
     "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
-    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr",
+    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",

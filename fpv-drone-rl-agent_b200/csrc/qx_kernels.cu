@@ -110,12 +110,14 @@ __device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int
 // MODE_RESET_QUEUE : reset of the envs queued by the preceding MODE_STEP_DEFER launch
 enum { MODE_STEP_INLINE = 0, MODE_STEP_DEFER = 1, MODE_RESET_MASK = 2, MODE_RESET_QUEUE = 3 };
 
-template <int MODE, int TASK>
+// CASC: the instantiation for PyFlyt flight modes != 0 (outer PID loops; 6 more state planes).  hover.py itself only
+// ever reaches mode 0 (set_mode(0), hover.py:92), which is the CASC = false path.
+template <int MODE, int TASK, bool CASC>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, int64_t i);
 
 constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
 
-template <int MODE, int TASK>
+template <int MODE, int TASK, bool CASC = false>
 __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
   if (MODE == MODE_RESET_QUEUE) {
     // Every block reads the count before any block can zero it: the zeroing
@@ -127,21 +129,34 @@ __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const
       if (atomicAdd(&a.queue->ticket, 1u) == gridDim.x - 1) { a.queue->count = 0u; a.queue->ticket = 0u; }
     }
     for (unsigned int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock)
-      run_env<MODE, TASK>(c, a, (int64_t)a.queue->idx[t]);
+      run_env<MODE, TASK, CASC>(c, a, (int64_t)a.queue->idx[t]);
   } else {
     const int64_t i = a.env_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.env_begin + a.env_count) return;
     if (MODE == MODE_RESET_MASK && a.mask && !a.mask[i]) return;
-    run_env<MODE, TASK>(c, a, i);
+    run_env<MODE, TASK, CASC>(c, a, i);
   }
 }
 
-template <int MODE, int TASK>
+// cascade only: what Aviary.reset() + QuadX.set_mode(mode) leave behind -- cleared outer-loop memory, the Euler row
+// of the fresh snapshot, and set_mode's preset setpoint (hold the current height in modes 2-4, the pose in mode 7)
+__device__ __forceinline__ void respawn_cascade(Env& e, const DevConfig& c, float seul[3], float sp[4]) {
+#pragma unroll
+  for (int k = 0; k < 18; ++k) e.cp[k] = 0.f;
+  quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, seul[0], seul[1], seul[2]);
+  sp[0] = sp[1] = sp[2] = sp[3] = 0.f;
+  if (c.flight_mode == 2 || c.flight_mode == 3 || c.flight_mode == 4) sp[3] = e.spz;
+  if (c.flight_mode == 7) { sp[0] = e.spx; sp[1] = e.spy; sp[2] = seul[2]; sp[3] = e.spz; }
+}
+
+template <int MODE, int TASK, bool CASC>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
   constexpr int OBS_DIM = TASK == QX_TASK_HOVER ? QX_OBS_DIM_HOVER : QX_OBS_DIM_YAW;
   constexpr bool RESET_ONLY = MODE == MODE_RESET_MASK || MODE == MODE_RESET_QUEUE;
   Env e;
   load_env(e, a.state, a.n, i);
+  if (CASC) load_cascade(e, a.state, a.n, i);
+  float seul[3];  // cascade: Euler row of the Aviary.state snapshot
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
   const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i) >> 32));
 
@@ -149,10 +164,12 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
     const int64_t row = (int64_t)kk * a.n + i;
     float act[4] = {0.f, 0.f, 0.f, 0.f};
     float sp[4] = {0.f, 0.f, 0.f, 0.f};
+    seul[0] = e.peul[0]; seul[1] = e.peul[1]; seul[2] = e.peul[2];  // == previous_ang_pos (hover.py:112,354) between steps
     int phase = RESET_ONLY ? 1 : 0;  // 0: the agent step, 1: reset (idle steps + first obs)
     int nsub;
     if (RESET_ONLY) {
       respawn(e, c, k0, k1);
+      if (CASC) respawn_cascade(e, c, seul, sp);
       nsub = c.n_sub_reset;
     } else {
       if (TASK == QX_TASK_HOVER) {
@@ -161,7 +178,12 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
         sp[0] = act[0] * c.act_scale[0];  // hover.py:337-341
         sp[1] = act[1] * c.act_scale[1];
         sp[2] = act[2] * c.act_scale[2];
-        sp[3] = 0.5f * (act[3] + 1.f);
+        sp[3] = fmaf(act[3], c.thrust_scale, c.thrust_bias);
+        if (!CASC) sp[3] = __saturatef(sp[3]);  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
+        if (CASC && c.flight_mode == -1) {      // four motor pwm commands: all of them through the throttle mapping
+#pragma unroll
+          for (int m = 0; m < 3; ++m) sp[m] = fmaf(act[m], c.thrust_scale, c.thrust_bias);
+        }
       } else {
         act[0] = __ldg(a.actions + row);  // yaw.py:105-122: roll = pitch = 0, yaw * -30, throttle (-1 + 1) / 2 = 0
         sp[2] = act[0] * c.act_scale[2];
@@ -188,7 +210,8 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
         constexpr int kPairUnroll = QX_PAIR_UNROLL;
 #pragma unroll kPairUnroll
         for (int j = 0; j < nsub; j += 2) {
-          control_update(e, c, sp, pwm);
+          if (CASC) control_update_cascade(e, c, sp, seul, pwm);
+          else control_update(e, c, sp, pwm);
           float nz[4] = {0.f, 0.f, 0.f, 0.f};
           uint4 bits = make_uint4(0u, 0u, 0u, 0u);
           if (c.noise) {
@@ -197,19 +220,27 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
           }
           physics_substep(e, c, pwm, nz, false);
           if (c.noise) normal4_scaled(bits.z, bits.w, c.noise_k, nz);
-          physics_substep(e, c, pwm, nz, j + 2 == nsub);
+          physics_substep(e, c, pwm, nz, CASC || j + 2 == nsub);  // the outer loops read the snapshot pose at every control update
+          if (CASC && c.need_euler) quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, seul[0], seul[1], seul[2]);
         }
       } else {
         uint4 bits = make_uint4(0u, 0u, 0u, 0u);
         for (int j = 0, cc = 0; j < nsub; ++j) {
-          if (cc == 0) control_update(e, c, sp, pwm);
+          if (cc == 0) {
+            if (CASC) {
+              if (j > 0 && c.need_euler) quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, seul[0], seul[1], seul[2]);
+              control_update_cascade(e, c, sp, seul, pwm);
+            } else {
+              control_update(e, c, sp, pwm);
+            }
+          }
           if (++cc == c.ctrl_every) cc = 0;
           float nz[4] = {0.f, 0.f, 0.f, 0.f};
           if (c.noise) {  // one Philox4x32-10 call feeds two sub-steps
             if ((j & 1) == 0) bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
             normal4_scaled((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, c.noise_k, nz);
           }
-          physics_substep(e, c, pwm, nz, j + 1 == nsub);
+          physics_substep(e, c, pwm, nz, CASC || j + 1 == nsub);
         }
       }
       // ---- compute_attitude / compute_state, hover.py:224-272
@@ -289,6 +320,11 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
         for (int m = 0; m < 4; ++m) e.thr[m] = 0.f;
 #pragma unroll
         for (int ax = 0; ax < 3; ++ax) { e.pi[ax] = e.pe[ax] = e.swb[ax] = e.svb[ax] = 0.f; }
+        if (CASC) {
+#pragma unroll
+          for (int k = 0; k < 18; ++k) e.cp[k] = 0.f;
+          e.spx = e.spy = 0.f; e.spz = c.floor_z;
+        }
       }
       if (fl & F_OOB) { reward = -100.f; fl |= F_TERM; }  // hover.py:278-281
       if (e.step_count > c.floor_grace && !c.render && (fl & F_LOWZ)) {  // hover.py:283-290
@@ -344,12 +380,14 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
       respawn(e, c, k0, k1);
       act[0] = act[1] = act[2] = act[3] = 0.f;  // hover.py:101
       sp[0] = sp[1] = sp[2] = sp[3] = 0.f;      // set_mode(0): zero setpoint
+      if (CASC) respawn_cascade(e, c, seul, sp);
       phase = 1;
       nsub = c.n_sub_reset;
     }
     if (a.obs && !deferred) write_obs(obs, a.obs, RESET_ONLY ? i : row, a.obs_stride, a.obs_bf16 != 0);
   }
   store_env(e, a.state, a.n, i);
+  if (CASC) store_cascade(e, a.state, a.n, i);
 }
 
 }  // namespace qx
@@ -362,6 +400,7 @@ struct QxHandle {
   qx::DevConfig dev;
   int64_t n;
   int device;
+  int planes;  // float4 state planes: 11, or 17 when flight_mode != 0
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
@@ -429,6 +468,13 @@ extern "C" int qx_default_config(int32_t task, QxConfig* c) {
     c->agent_dt = 1.0f / 120.f;
   }
   c->render = 0; c->auto_reset = 1; c->noise = 1;
+  c->flight_mode = 0; c->thrust_scale = 0.5f; c->thrust_bias = 0.5f;  /* hover.py:92, :341 */
+  const float att[12] = {1, 1, 1, 0, 0, 0, 0, 0, 0, 2, 2, 2};                                  /* cf2x.yaml:21-26 */
+  const float vel[8] = {0.4f, 0.4f, 0.15f, 0.15f, 0.25f, 0.25f, 0.3f, 0.3f};                   /* cf2x.yaml:28-33 */
+  const float pos[8] = {0.5f, 0.5f, 0, 0, 0, 0, 1, 1};                                         /* cf2x.yaml:35-40 */
+  const float zp[4] = {0.8f, 0, 0, 1.5f}, zv[4] = {1.5f, 0.3f, 0.05f, 1.0f};                   /* cf2x.yaml:42-54 */
+  memcpy(c->att_pid, att, sizeof(att)); memcpy(c->vel_pid, vel, sizeof(vel)); memcpy(c->pos_pid, pos, sizeof(pos));
+  memcpy(c->zpos_pid, zp, sizeof(zp)); memcpy(c->zvel_pid, zv, sizeof(zv));
   return QX_OK;
 }
 
@@ -436,6 +482,8 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   memset(d, 0, sizeof(*d));
   if (s.task != QX_TASK_HOVER && s.task != QX_TASK_YAW) return fail(QX_EINVAL, "qx_create: unknown task");
   if (!(s.physics_hz > 0) || !(s.control_hz > 0) || s.control_hz > s.physics_hz) return fail(QX_EINVAL, "qx_create: bad rates");
+  if (s.flight_mode < -1 || s.flight_mode > 7) return fail(QX_EINVAL, "qx_create: flight_mode outside PyFlyt's -1..7");
+  if (s.flight_mode != 0 && s.task != QX_TASK_HOVER) return fail(QX_EINVAL, "qx_create: flight modes other than 0 apply to the hover task");
   const int per = (int)(s.physics_hz / s.control_hz);
   d->task = s.task;
   d->ctrl_every = per;
@@ -479,6 +527,14 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   d->spawn_thr = s.spawn_throttle; d->spawn_pos_noise = s.spawn_pos_noise; d->spawn_yaw_noise = s.spawn_yaw_noise;
   d->seed_lo = (uint32_t)seed; d->seed_hi = (uint32_t)(seed >> 32);
   d->env_lo = (uint32_t)env_id0; d->env_hi = (uint32_t)(env_id0 >> 32);
+  d->flight_mode = s.flight_mode; d->need_euler = (s.flight_mode == 1 || s.flight_mode == 3 || s.flight_mode >= 4) ? 1 : 0;
+  d->thrust_scale = s.thrust_scale; d->thrust_bias = s.thrust_bias;
+  auto gains = [T](const float* src, int w, float* dst) {  // kp | ki T | kd / T | lim
+    for (int k = 0; k < w; ++k) {
+      dst[k] = src[k]; dst[w + k] = (float)(src[w + k] * T); dst[2 * w + k] = (float)(src[2 * w + k] / T); dst[3 * w + k] = src[3 * w + k];
+    }
+  };
+  gains(s.att_pid, 3, d->att); gains(s.vel_pid, 2, d->vel); gains(s.pos_pid, 2, d->lpos); gains(s.zpos_pid, 1, d->zpos); gains(s.zvel_pid, 1, d->zvel);
   return QX_OK;
 }
 
@@ -499,11 +555,12 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(device);
-  cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * 11 * n_envs);
+  h->planes = cfg->flight_mode != 0 ? qx::kCascadePlanes : qx::kBasePlanes;
+  cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaMalloc(&h->queue, sizeof(qx::ResetQueue) + sizeof(unsigned int) * n_envs);
   if (e == cudaSuccess) e = cudaMemset(h->queue, 0, sizeof(qx::ResetQueue));
-  if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * 11 * n_envs);
+  if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
@@ -561,17 +618,18 @@ extern "C" int64_t qx_num_envs(const QxHandle* h) { return h ? h->n : 0; }
 extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0; }
 extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
 extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
+extern "C" int32_t qx_state_words(const QxHandle* h) { return h ? 4 * h->planes : 0; }
 
-template <int TASK>
+template <int TASK, bool CASC>
 static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.env_count + qx::kBlock - 1) / qx::kBlock);
   switch (mode) {
-    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     default: {
       const unsigned g = grid < (unsigned)qx::kResetQueueBlocks ? grid : (unsigned)qx::kResetQueueBlocks;
-      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE, TASK><<<g, qx::kBlock, 0, s>>>(h->dev, a);
+      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE, TASK, CASC><<<g, qx::kBlock, 0, s>>>(h->dev, a);
       break;
     }
   }
@@ -579,8 +637,9 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
 
 static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
-  if (h->dev.task == QX_TASK_HOVER) launch_task<QX_TASK_HOVER>(h, mode, a, s);
-  else launch_task<QX_TASK_YAW>(h, mode, a, s);
+  if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false>(h, mode, a, s);
+  else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true>(h, mode, a, s);
+  else launch_task<QX_TASK_HOVER, false>(h, mode, a, s);
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;
@@ -754,14 +813,15 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
 extern "C" int qx_get_state(QxHandle* h, void* planes_host) {
   if (!h || !planes_host) return fail(QX_EINVAL, "qx_get_state: bad arguments");
   DeviceGuard g(h->device);
-  // device layout: 11 planes of n float4; host layout: 44 planes of n words
+  // device layout: h->planes planes of n float4; host layout: 4 * h->planes planes of n words
   const int64_t n = h->n;
-  float4* tmp = (float4*)malloc(sizeof(float4) * 11 * n);
+  const int P = h->planes;
+  float4* tmp = (float4*)malloc(sizeof(float4) * P * n);
   if (!tmp) return fail(QX_ENOMEM, "qx_get_state: out of host memory");
-  cudaError_t e = cudaMemcpy(tmp, h->state, sizeof(float4) * 11 * n, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(tmp, h->state, sizeof(float4) * P * n, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { free(tmp); return fail(QX_ECUDA, "qx_get_state: %s", cudaGetErrorString(e)); }
   float* out = (float*)planes_host;
-  for (int p = 0; p < 11; ++p)
+  for (int p = 0; p < P; ++p)
     for (int64_t i = 0; i < n; ++i) {
       const float4 v = tmp[p * n + i];
       out[(4 * p + 0) * n + i] = v.x; out[(4 * p + 1) * n + i] = v.y; out[(4 * p + 2) * n + i] = v.z; out[(4 * p + 3) * n + i] = v.w;
@@ -774,13 +834,14 @@ extern "C" int qx_set_state(QxHandle* h, const void* planes_host) {
   if (!h || !planes_host) return fail(QX_EINVAL, "qx_set_state: bad arguments");
   DeviceGuard g(h->device);
   const int64_t n = h->n;
-  float4* tmp = (float4*)malloc(sizeof(float4) * 11 * n);
+  const int P = h->planes;
+  float4* tmp = (float4*)malloc(sizeof(float4) * P * n);
   if (!tmp) return fail(QX_ENOMEM, "qx_set_state: out of host memory");
   const float* in = (const float*)planes_host;
-  for (int p = 0; p < 11; ++p)
+  for (int p = 0; p < P; ++p)
     for (int64_t i = 0; i < n; ++i)
       tmp[p * n + i] = make_float4(in[(4 * p + 0) * n + i], in[(4 * p + 1) * n + i], in[(4 * p + 2) * n + i], in[(4 * p + 3) * n + i]);
-  cudaError_t e = cudaMemcpy(h->state, tmp, sizeof(float4) * 11 * n, cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMemcpy(h->state, tmp, sizeof(float4) * P * n, cudaMemcpyHostToDevice);
   free(tmp);
   if (e != cudaSuccess) return fail(QX_ECUDA, "qx_set_state: %s", cudaGetErrorString(e));
   return QX_OK;

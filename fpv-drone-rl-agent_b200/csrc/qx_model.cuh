@@ -4,9 +4,9 @@
 // follows, step by step,
 //   * /root/reference/simulation/hover.py:224-358 (obs, reward, termination, step)
 //   * hover.py:72-113 (reset), yaw.py:57-149 (yaw task)
-//   * the PyFlyt 0.21.0 mode-0 QuadX model and pybullet's multibody integrator
+//   * the PyFlyt 0.21.0 QuadX model (mode 0, plus the outer loops of modes -1..7) and pybullet's multibody integrator
 //     as restated in SURVEY.md section 9 (third-party, parity unpinned),
-//     parameterised by cf2x.yaml:1-19 and cf2x.urdf:10-68.
+//     parameterised by cf2x.yaml:1-54 and cf2x.urdf:10-68.
 // It is written from that description for this hardware, not translated from
 // the CPU oracle: single precision, MUFU intrinsics, no libm slow paths inside
 // the sub-step loop, Philox counters instead of a stateful generator.
@@ -31,6 +31,10 @@ struct DevConfig {
   float inv_agent_dt, dome2, floor_thr, target_area, target_ratio, act_scale[3];
   float start_pos[3], start_rpy[3], spawn_thr, spawn_pos_noise, spawn_yaw_noise;
   uint32_t seed_lo, seed_hi, env_lo, env_hi;  // env id of local env 0
+  // PyFlyt flight modes (cascade instantiation only): outer-loop gains as kp[w] ki*T[w] kd/T[w] lim[w]
+  int32_t flight_mode, need_euler;
+  float thrust_scale, thrust_bias;
+  float att[12], vel[8], lpos[8], zpos[4], zvel[4];
 };
 
 enum : uint32_t {
@@ -61,6 +65,9 @@ struct Env {
   uint32_t flags;
   // transient (not stored): pose part of the Aviary.state snapshot
   float sqx, sqy, sqz, sqw, spx, spy, spz;
+  // cascade instantiation only (planes 11..16; spx/spy/spz are carried there too): (integral, previous error) of
+  // ang_pos 0/3, lin_vel 6/8, lin_pos 10/12, z_vel 14/15, z_pos 16/17
+  float cp[18];
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
@@ -95,6 +102,27 @@ __device__ __forceinline__ void store_env(const Env& e, float4* __restrict__ st,
   st[8 * n + i] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
   st[9 * n + i] = make_float4(e.pcx, e.pcy, e.parea, e.pratio);
   st[10 * n + i] = make_float4(__int_as_float(e.step_count), __uint_as_float(e.rng_ctr), e.ep_ret, __uint_as_float(e.flags));
+}
+
+// Flight modes != 0: six more planes -- the outer loops' PID memory and the position row of the Aviary.state
+// snapshot, which those loops read at the first control update of the next step.
+constexpr int kBasePlanes = 11, kCascadePlanes = 17;
+__device__ __forceinline__ void load_cascade(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  float4 v[6];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) v[p] = ldg4(st + (int64_t)(kBasePlanes + p) * n + i);
+  const float* w = reinterpret_cast<const float*>(v);
+#pragma unroll
+  for (int k = 0; k < 18; ++k) e.cp[k] = w[k];
+  e.spx = w[18]; e.spy = w[19]; e.spz = w[20];
+}
+__device__ __forceinline__ void store_cascade(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
+  st[(int64_t)(kBasePlanes + 0) * n + i] = make_float4(e.cp[0], e.cp[1], e.cp[2], e.cp[3]);
+  st[(int64_t)(kBasePlanes + 1) * n + i] = make_float4(e.cp[4], e.cp[5], e.cp[6], e.cp[7]);
+  st[(int64_t)(kBasePlanes + 2) * n + i] = make_float4(e.cp[8], e.cp[9], e.cp[10], e.cp[11]);
+  st[(int64_t)(kBasePlanes + 3) * n + i] = make_float4(e.cp[12], e.cp[13], e.cp[14], e.cp[15]);
+  st[(int64_t)(kBasePlanes + 4) * n + i] = make_float4(e.cp[16], e.cp[17], e.spx, e.spy);
+  st[(int64_t)(kBasePlanes + 5) * n + i] = make_float4(e.spz, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -174,6 +202,58 @@ __device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const
   // the motor lag thr += alpha (pwm - thr) is applied as thr (1 - alpha) + (alpha pwm): hoist alpha pwm out of the sub-steps
 #pragma unroll
   for (int m = 0; m < 4; ++m) pwm[m] *= c.lag_alpha;
+}
+
+// ---------------------------------------------------------------------------
+// PyFlyt PID.step for one channel; g = kp[w] ki*T[w] kd/T[w] lim[w], channel k
+// ---------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ float pid_channel(const float* g, int k, float& mi, float& me, float state, float sp) {
+  const float err = sp - state, lim = g[3 * W + k];
+  mi = clampf(fmaf(g[W + k], err, mi), -lim, lim);
+  const float d = g[2 * W + k] * (err - me);
+  me = err;
+  return clampf(fmaf(g[k], err, mi) + d, -lim, lim);
+}
+
+// QuadX.update_control for flight modes != 0: the outer loops turn the setpoint into (rate commands, thrust) and the
+// mode-0 controller above finishes the job.  seul = Euler row of the Aviary.state snapshot.  Mode -1 bypasses
+// everything (setpoint = motor pwm, no mixing, no saturation).
+__device__ __forceinline__ void control_update_cascade(Env& e, const DevConfig& c, const float sp[4], const float seul[3], float pwm[4]) {
+  const int mode = c.flight_mode;
+  if (mode == -1) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pwm[m] = sp[m] * c.lag_alpha;
+    return;
+  }
+  float a[4] = {sp[0], sp[1], sp[2], sp[3]};
+  if (mode == 1 || mode == 3) {  // angles -> rates
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a[k] = pid_channel<3>(c.att, k, e.cp[k], e.cp[3 + k], seul[k], a[k]);
+  } else if (mode >= 4) {
+    if (mode == 7) {  // ground-frame position -> ground-frame velocity
+      a[0] = pid_channel<2>(c.lpos, 0, e.cp[10], e.cp[12], e.spx, a[0]);
+      a[1] = pid_channel<2>(c.lpos, 1, e.cp[11], e.cp[13], e.spy, a[1]);
+    }
+    if (mode >= 6) {  // ground frame -> yaw-rotated local frame
+      float sy, cy;
+      sincosf(seul[2], &sy, &cy);
+      const float gx = a[0], gy = a[1];
+      a[0] = cy * gx + sy * gy;
+      a[1] = cy * gy - sy * gx;
+    }
+    // local velocity -> tilt angles: +x needs +pitch, +y needs -roll
+    const float ang0 = pid_channel<2>(c.vel, 0, e.cp[6], e.cp[8], e.svb[0], a[0]);
+    const float ang1 = pid_channel<2>(c.vel, 1, e.cp[7], e.cp[9], e.svb[1], a[1]);
+    a[0] = -ang1; a[1] = ang0;
+    a[0] = pid_channel<3>(c.att, 0, e.cp[0], e.cp[3], seul[0], a[0]);
+    a[1] = pid_channel<3>(c.att, 1, e.cp[1], e.cp[4], seul[1], a[1]);
+    if (mode == 7) a[2] = pid_channel<3>(c.att, 2, e.cp[2], e.cp[5], seul[2], a[2]);  // yaw is an angle only in mode 7
+  }
+  if (mode == 2 || mode == 3 || mode == 4 || mode == 7) a[3] = pid_channel<1>(c.zpos, 0, e.cp[16], e.cp[17], e.spz, a[3]);
+  if (mode != 0) a[3] = pid_channel<1>(c.zvel, 0, e.cp[14], e.cp[15], e.svb[2], a[3]);
+  a[3] = __saturatef(a[3]);
+  control_update(e, c, a, pwm);
 }
 
 // ---------------------------------------------------------------------------

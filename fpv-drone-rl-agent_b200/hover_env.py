@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QX_OBS_BF16, QX_OBS_F32, QX_STATE_WORDS, QX_TASK_HOVER, QxConfig, check, default_config
+from ._lib import QX_OBS_BF16, QX_OBS_F32, QX_STATE_WORDS, QX_STATE_WORDS_CASCADE, QX_TASK_HOVER, QxConfig, check, default_config
 
 # names of the 44 carried state words, in plane order (see csrc/qx_model.cuh Env)
 STATE_FIELDS = (
@@ -30,6 +30,12 @@ STATE_FIELDS = (
     "prev_cx prev_cy prev_area prev_ratio step_count rng_ctr ep_return flags"
 ).split()
 assert len(STATE_FIELDS) == QX_STATE_WORDS
+# flight_mode != 0: the outer loops' (integral, previous error) memory and the position row of the state snapshot
+CASCADE_FIELDS = (
+    "att_i0 att_i1 att_i2 att_e0 att_e1 att_e2 vel_i0 vel_i1 vel_e0 vel_e1 pos_i0 pos_i1 pos_e0 pos_e1 zv_i zv_e zp_i zp_e "
+    "s_px s_py s_pz pad0 pad1 pad2"
+).split()
+assert len(STATE_FIELDS) + len(CASCADE_FIELDS) == QX_STATE_WORDS_CASCADE
 _INT_FIELDS = {"step_count": np.int32, "rng_ctr": np.uint32, "flags": np.uint32}
 
 
@@ -171,19 +177,28 @@ class QuadXSim:
                                     None if tobs is None else tobs.ctypes.data_as(C.c_void_p)))
         return obs, rew, te.astype(bool), tr.astype(bool), tobs
 
+    @property
+    def state_fields(self) -> list[str]:
+        """Names of the carried words, in plane order (qx_state_words of them)."""
+        fields = STATE_FIELDS + CASCADE_FIELDS if self.cfg.flight_mode != 0 else STATE_FIELDS
+        assert len(fields) == self.lib.qx_state_words(self._h)
+        return fields
+
     def get_state(self) -> dict[str, np.ndarray]:
         torch.cuda.synchronize(self.device)
-        raw = np.empty((QX_STATE_WORDS, self.n), np.float32)
+        fields = self.state_fields
+        raw = np.empty((len(fields), self.n), np.float32)
         check(self.lib.qx_get_state(self._h, raw.ctypes.data_as(C.c_void_p)))
         out = {}
-        for k, name in enumerate(STATE_FIELDS):
+        for k, name in enumerate(fields):
             out[name] = raw[k].view(_INT_FIELDS[name]).copy() if name in _INT_FIELDS else raw[k].copy()
         return out
 
     def set_state(self, state: dict[str, np.ndarray]) -> None:
         torch.cuda.synchronize(self.device)
-        raw = np.empty((QX_STATE_WORDS, self.n), np.float32)
-        for k, name in enumerate(STATE_FIELDS):
+        fields = self.state_fields
+        raw = np.zeros((len(fields), self.n), np.float32)
+        for k, name in enumerate(fields):
             v = np.asarray(state[name])
             raw[k] = v.astype(_INT_FIELDS[name]).view(np.float32) if name in _INT_FIELDS else v.astype(np.float32)
         check(self.lib.qx_set_state(self._h, raw.ctypes.data_as(C.c_void_p)))
@@ -299,15 +314,21 @@ class QuadXHoverEnv:
 
     ``flight_mode`` and ``agent_hz`` are accepted like the reference's
     constructor (hover.py:11-16); the reference ignores ``flight_mode``
-    (``set_mode(0)`` is literal, hover.py:92) and so does this class.
+    (``set_mode(0)`` is literal, hover.py:92) and so does this class, unless
+    ``honour_flight_mode=True`` is passed: then the drone flies in that PyFlyt
+    mode (-1..7, the outer PID loops of cf2x.yaml:21-54; set ``action_scale`` /
+    ``thrust_scale`` / ``thrust_bias`` to map the Box(-1, 1) action onto it).
     """
 
     metadata = {"render_modes": []}
 
-    def __init__(self, flight_mode: int = 0, agent_hz: int = 40, render: bool = False, seed: int = 0, device=None, **cfg_overrides):
+    def __init__(self, flight_mode: int = 0, agent_hz: int = 40, render: bool = False, seed: int = 0, device=None,
+                 honour_flight_mode: bool = False, **cfg_overrides):
         self.flight_mode = flight_mode
         self.agent_hz = agent_hz
         cfg = default_config(QX_TASK_HOVER)
+        if honour_flight_mode:
+            cfg_overrides.setdefault("flight_mode", int(flight_mode))
         cfg.update(auto_reset=0, render=int(render), agent_dt=1.0 / agent_hz,
                    aviary_steps_per_step=int(cfg.physics_hz / agent_hz), **cfg_overrides)
         self.sim = QuadXSim(1, cfg, seed=seed, device=device)

@@ -28,12 +28,13 @@
 extern "C" {
 #endif
 
-#define QX_VERSION 1
+#define QX_VERSION 2
 #define QX_OBS_DIM_HOVER 20 /* hover.py:67 */
 #define QX_OBS_DIM_YAW 12   /* yaw.py:41-45 */
 #define QX_ACT_DIM_HOVER 4  /* hover.py:59-61 */
 #define QX_ACT_DIM_YAW 1    /* yaw.py:37 */
 #define QX_STATE_WORDS 44   /* carried words per env (11 float4 planes) */
+#define QX_STATE_WORDS_CASCADE 68 /* ... when flight_mode != 0: + 6 planes of outer-loop PID memory */
 
 enum { QX_OK = 0, QX_EINVAL = -1, QX_ECUDA = -2, QX_ENOMEM = -3, QX_EARCH = -4 };
 enum { QX_TASK_HOVER = 0, QX_TASK_YAW = 1 };
@@ -99,6 +100,19 @@ typedef struct QxConfig {
   int32_t render;             /* hover.py:283: floor rule off when rendering   */
   int32_t auto_reset;         /* SB3 VecEnv semantics (train_hover.py:42)      */
   int32_t noise;              /* motor noise on/off                            */
+  /* --- flight modes: hover.py:13,19 takes flight_mode and never uses it (set_mode(0) is literal at :92), so 0
+   * is the reference's behaviour.  Non-zero selects the rest of PyFlyt's QuadX.set_mode cascade over the
+   * gains of cf2x.yaml:21-53 (hover task only):  -1 motor pwm | 0 vp,vq,vr,T | 1 p,q,r,vz | 2 vp,vq,vr,z |
+   * 3 p,q,r,z | 4 u,v,vr,z | 5 u,v,vr,vz | 6 vx,vy,vr,vz | 7 x,y,r,z.  setpoint = (action_scale * a[0..2],
+   * thrust_scale * a[3] + thrust_bias); in mode -1 all four channels use the thrust mapping. ---------------- */
+  int32_t flight_mode;
+  float thrust_scale;         /* hover.py:341 (a3 + 1) / 2  ->  0.5                */
+  float thrust_bias;          /*                               0.5                */
+  float att_pid[12];          /* ang_pos kp[3] ki[3] kd[3] lim[3], cf2x.yaml:21-26 */
+  float vel_pid[8];           /* lin_vel kp[2] ki[2] kd[2] lim[2], cf2x.yaml:28-33 */
+  float pos_pid[8];           /* lin_pos kp[2] ki[2] kd[2] lim[2], cf2x.yaml:35-40 */
+  float zpos_pid[4];          /* z_pos kp ki kd lim,               cf2x.yaml:42-47 */
+  float zvel_pid[4];          /* z_vel kp ki kd lim,               cf2x.yaml:49-54 */
 } QxConfig;
 
 typedef struct QxHandle QxHandle;
@@ -151,10 +165,12 @@ int qx_reset_host(QxHandle* h, const uint8_t* mask_host, float* obs_host);
 int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
                  uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host);
 
-/* Carried state as QX_STATE_WORDS planes of n_envs 32-bit words (layout in
- * DESIGN.md); for parity tests and checkpoint/resume. */
+/* Carried state as qx_state_words(h) planes of n_envs 32-bit words (layout in
+ * DESIGN.md; QX_STATE_WORDS, or QX_STATE_WORDS_CASCADE when cfg.flight_mode != 0);
+ * for parity tests and checkpoint/resume. */
 int qx_get_state(QxHandle* h, void* planes_host);
 int qx_set_state(QxHandle* h, const void* planes_host);
+int32_t qx_state_words(const QxHandle* h);
 
 /* Replaces: SB3 Monitor's info["episode"] (train_hover.py:42 make_vec_env):
  * sums over the episodes finished since the last call with clear != 0. */
@@ -167,7 +183,7 @@ int qx_nonfinite_count(QxHandle* h, int64_t* count);
 int64_t qx_num_envs(const QxHandle* h);
 int32_t qx_obs_dim(const QxHandle* h);
 int32_t qx_act_dim(const QxHandle* h);
-/* device pointer to the 11 float4 state planes (plane stride = n_envs) */
+/* device pointer to the qx_state_words(h) / 4 float4 state planes (plane stride = n_envs) */
 void* qx_state_ptr(QxHandle* h);
 /* number of kernels this library has launched in the calling process */
 int64_t qx_launch_count(void);

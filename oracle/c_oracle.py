@@ -31,6 +31,8 @@ class OrcConfig(C.Structure):
         ("agent_dt", f64), ("flight_dome_size", f64), ("floor_threshold", f64), ("target_area", f64), ("target_ratio", f64),
         ("action_scale", f64 * 3), ("start_pos", f64 * 3), ("start_rpy", f64 * 3), ("spawn_throttle", f64),
         ("spawn_pos_noise", f64), ("spawn_yaw_noise", f64), ("render", i32), ("auto_reset", i32), ("noise", i32),
+        ("flight_mode", i32), ("thrust_scale", f64), ("thrust_bias", f64),
+        ("att", f64 * 12), ("vel", f64 * 8), ("lpos", f64 * 8), ("zpos", f64 * 4), ("zvel", f64 * 4),
     ]
 
 
@@ -65,6 +67,11 @@ def make_config(p: QuadXParams, h: HoverConfig, auto_reset: bool, noise: bool) -
     c.start_pos, c.start_rpy = _arr(f64 * 3, h.start_pos), _arr(f64 * 3, h.start_rpy)
     c.spawn_throttle, c.spawn_pos_noise, c.spawn_yaw_noise = h.spawn_throttle, h.spawn_pos_noise, h.spawn_yaw_noise
     c.render, c.auto_reset, c.noise = int(h.render), int(auto_reset), int(noise)
+    c.flight_mode, c.thrust_scale, c.thrust_bias = int(p.flight_mode), h.thrust_scale, h.thrust_bias
+    c.att = _arr(f64 * 12, [*p.att_kp, *p.att_ki, *p.att_kd, *p.att_lim])
+    c.vel = _arr(f64 * 8, [*p.vel_kp, *p.vel_ki, *p.vel_kd, *p.vel_lim])
+    c.lpos = _arr(f64 * 8, [*p.pos_kp, *p.pos_ki, *p.pos_kd, *p.pos_lim])
+    c.zpos, c.zvel = _arr(f64 * 4, p.zpos_pid), _arr(f64 * 4, p.zvel_pid)
     return c
 
 

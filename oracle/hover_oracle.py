@@ -22,6 +22,7 @@ from .quadx_model import (
     QuadXState,
     aviary_step,
     euler_to_quat,
+    mode_preset_setpoint,
     spawn,
     u01,
 )
@@ -40,6 +41,8 @@ class HoverConfig:
     target_area: float = 0.013  # hover.py:50
     target_ratio: float = 1.53  # hover.py:51
     action_scale: tuple = (30.0, 30.0, -30.0)  # hover.py:338-340
+    thrust_scale: float = 0.5  # hover.py:341: (a3 + 1) / 2 == a3 * 0.5 + 0.5
+    thrust_bias: float = 0.5
     start_pos: tuple = (0.0, 0.0, 0.0)  # hover.py:78
     start_rpy: tuple = (0.0, 0.0, 0.0)  # hover.py:79
     reset_idle_steps: int = 10  # hover.py:109
@@ -190,7 +193,7 @@ class HoverVecOracle:
         sub_state = self.st.select(mask)
         key = NoiseSource(self.noise.seed, self.env_ids[mask], self.noise.enabled)
         ctr = self.rng_ctr[mask]
-        sp = np.zeros((int(mask.sum()), 4))
+        sp = mode_preset_setpoint(sub_state, p)  # zeros in mode 0
         sub = 0
         for _ in range(cfg.reset_idle_steps):
             sub = aviary_step(sub_state, sp, p, key.normals, sub, STREAM_RESET, ctr)
@@ -218,9 +221,12 @@ class HoverVecOracle:
         a = np.asarray(actions, float).reshape(self.n, 4)
         self.action = a.copy()  # hover.py:335
         sp = np.stack(
-            [a[:, 0] * cfg.action_scale[0], a[:, 1] * cfg.action_scale[1], a[:, 2] * cfg.action_scale[2], (a[:, 3] + 1) / 2],
+            [a[:, 0] * cfg.action_scale[0], a[:, 1] * cfg.action_scale[1], a[:, 2] * cfg.action_scale[2],
+             a[:, 3] * cfg.thrust_scale + cfg.thrust_bias],
             axis=1,
         )  # hover.py:337-341
+        if p.flight_mode == -1:  # four motor pwm commands: all of them through the throttle mapping
+            sp = a * cfg.thrust_scale + cfg.thrust_bias
         reward = np.full(self.n, -0.1)  # hover.py:343
         live = ~(self.terminated | self.truncated)  # hover.py:347-348
         if live.any():

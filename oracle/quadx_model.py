@@ -1,4 +1,5 @@
-"""Batched float64 restatement of PyFlyt 0.21.0 ``QuadX`` (mode 0) on top of a
+"""Batched float64 restatement of PyFlyt 0.21.0 ``QuadX`` (mode 0, the only mode
+hover.py:92 reaches, plus the rest of its PID cascade: flight modes -1..7) on top of a
 free-flight restatement of pybullet 3.2.7's multibody integrator.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  **Parity unpinned** for this
@@ -43,6 +44,23 @@ class QuadXParams:
     rate_ki: tuple = (2.5e-7, 2.5e-7, 1.35e-4)
     rate_kd: tuple = (5.0e-5, 5.0e-5, 0.0)
     rate_lim: tuple = (1.0, 1.0, 1.0)
+    # cf2x.yaml:21-53: the rest of the cascade (unused by hover.py, which hard-codes set_mode(0) at :92)
+    flight_mode: int = 0  # PyFlyt QuadX.set_mode: -1 pwm | 0 vp,vq,vr,T | 1 p,q,r,vz | 2 vp,vq,vr,z | 3 p,q,r,z
+    #                        | 4 u,v,vr,z | 5 u,v,vr,vz | 6 vx,vy,vr,vz | 7 x,y,r,z
+    att_kp: tuple = (1.0, 1.0, 1.0)  # ang_pos, cf2x.yaml:21-26
+    att_ki: tuple = (0.0, 0.0, 0.0)
+    att_kd: tuple = (0.0, 0.0, 0.0)
+    att_lim: tuple = (2.0, 2.0, 2.0)
+    vel_kp: tuple = (0.4, 0.4)  # lin_vel, cf2x.yaml:28-33
+    vel_ki: tuple = (0.15, 0.15)
+    vel_kd: tuple = (0.25, 0.25)
+    vel_lim: tuple = (0.3, 0.3)
+    pos_kp: tuple = (0.5, 0.5)  # lin_pos, cf2x.yaml:35-40
+    pos_ki: tuple = (0.0, 0.0)
+    pos_kd: tuple = (0.0, 0.0)
+    pos_lim: tuple = (1.0, 1.0)
+    zpos_pid: tuple = (0.8, 0.0, 0.0, 1.5)  # (kp, ki, kd, lim), cf2x.yaml:42-47
+    zvel_pid: tuple = (1.5, 0.3, 0.05, 1.0)  # cf2x.yaml:49-54
     # cf2x.urdf:10,12 (U6: inertia taken from the file)
     mass: float = 0.1
     inertia: tuple = (3.0e-5, 3.0e-5, 5.0e-5)
@@ -242,6 +260,11 @@ def quat_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------
 
 
+# columns of QuadXState.cpid: (integral, previous error) of ang_pos[3], lin_vel[2], lin_pos[2], z_vel, z_pos
+CP_ATT_I, CP_ATT_E, CP_VEL_I, CP_VEL_E, CP_POS_I, CP_POS_E, CP_ZV_I, CP_ZV_E, CP_ZP_I, CP_ZP_E = 0, 3, 6, 8, 10, 12, 14, 15, 16, 17
+CP_WORDS = 18
+
+
 @dataclass
 class QuadXState:
     """True rigid-body state + controller/motor state + the (possibly stale)
@@ -260,6 +283,12 @@ class QuadXState:
     s_euler: np.ndarray
     s_vb: np.ndarray
     s_pos: np.ndarray
+    # integral / previous error of the outer loops (flight modes 1..7), columns CP_*
+    cpid: np.ndarray = None
+
+    def __post_init__(self):
+        if self.cpid is None:
+            self.cpid = np.zeros((self.pos.shape[0], CP_WORDS))
 
     @classmethod
     def zeros(cls, n: int) -> "QuadXState":
@@ -308,23 +337,75 @@ def spawn(st: QuadXState, mask: np.ndarray, p: QuadXParams, pos, rpy, throttle: 
     st.thr[mask] = throttle
     st.pid_i[mask] = 0.0
     st.pid_e[mask] = 0.0
+    st.cpid[mask] = 0.0
     st.contact[mask] = pos[:, 2] <= p.floor_z
     sub = st.select(mask)
     take_snapshot(sub)
     st.s_wb[mask], st.s_euler[mask], st.s_vb[mask], st.s_pos[mask] = sub.s_wb, sub.s_euler, sub.s_vb, sub.s_pos
 
 
+def _pid(st: QuadXState, ci: int, ce: int, w: int, gains, T: float, state: np.ndarray, setpoint: np.ndarray) -> np.ndarray:
+    """PyFlyt PID.step [RECALL]: clipped integral, derivative on the error, clipped sum; memory in st.cpid[:, ci:ci+w]."""
+    kp, ki, kd, lim = (np.asarray(g, float) for g in gains)
+    err = setpoint - state
+    integ = np.clip(st.cpid[:, ci:ci + w] + ki * err * T, -lim, lim)
+    d = kd * (err - st.cpid[:, ce:ce + w]) / T
+    st.cpid[:, ci:ci + w] = integ
+    st.cpid[:, ce:ce + w] = err
+    return np.clip(kp * err + integ + d, -lim, lim)
+
+
+def mode_preset_setpoint(st: QuadXState, p: QuadXParams) -> np.ndarray:
+    """Setpoint PyFlyt's QuadX.set_mode leaves behind [RECALL] -- what the drone tracks during the idle
+    Aviary.step()s of a reset (hover.py:109-110): hold the current height (modes 2, 3, 4) / pose (mode 7), else zeros."""
+    sp = np.zeros((st.pos.shape[0], 4))
+    if p.flight_mode in (2, 3, 4):
+        sp[:, 3] = st.s_pos[:, 2]
+    elif p.flight_mode == 7:
+        sp[:, 0:2] = st.s_pos[:, 0:2]
+        sp[:, 2] = st.s_euler[:, 2]
+        sp[:, 3] = st.s_pos[:, 2]
+    return sp
+
+
 def control_update(st: QuadXState, setpoint: np.ndarray, p: QuadXParams) -> np.ndarray:
-    """PyFlyt QuadX.update_control, mode 0 [RECALL]: rate PID -> mix -> saturation.
-    setpoint [N,4] = (p, q, r rad/s, thrust 0..1).  Returns pwm [N,4]."""
+    """PyFlyt QuadX.update_control [RECALL]: outer loops of the flight mode -> rate PID -> mix -> saturation.
+    Mode 0 (hover.py:92): setpoint [N,4] = (p, q, r rad/s, thrust 0..1).  Returns pwm [N,4]."""
+    mode = p.flight_mode
+    if mode == -1:  # direct motor commands, no mixing / saturation
+        return setpoint.copy()
     kp, ki, kd, lim = (np.asarray(v) for v in (p.rate_kp, p.rate_ki, p.rate_kd, p.rate_lim))
     T = p.ctrl_period
-    e = setpoint[:, :3] - st.s_wb
+    a_out = setpoint[:, :3].copy()
+    z_out = setpoint[:, 3].copy()
+    att2 = tuple(g[:2] for g in (p.att_kp, p.att_ki, p.att_kd, p.att_lim))
+    if mode in (1, 3):  # angles -> rates
+        a_out = _pid(st, CP_ATT_I, CP_ATT_E, 3, (p.att_kp, p.att_ki, p.att_kd, p.att_lim), T, st.s_euler, a_out)
+    elif mode in (4, 5, 6, 7):
+        if mode == 7:  # ground-frame position -> ground-frame velocity
+            a_out[:, :2] = _pid(st, CP_POS_I, CP_POS_E, 2, (p.pos_kp, p.pos_ki, p.pos_kd, p.pos_lim), T, st.s_pos[:, :2], a_out[:, :2])
+        if mode in (6, 7):  # ground frame -> local (yaw-rotated) frame
+            c, s_ = np.cos(st.s_euler[:, 2]), np.sin(st.s_euler[:, 2])
+            a_out[:, 0], a_out[:, 1] = c * a_out[:, 0] + s_ * a_out[:, 1], -s_ * a_out[:, 0] + c * a_out[:, 1]
+        # local velocity -> tilt angles; +x needs +pitch, +y needs -roll
+        ang = _pid(st, CP_VEL_I, CP_VEL_E, 2, (p.vel_kp, p.vel_ki, p.vel_kd, p.vel_lim), T, st.s_vb[:, :2], a_out[:, :2])
+        a_out[:, 0], a_out[:, 1] = -ang[:, 1], ang[:, 0]
+        if mode == 7:  # all three are angles
+            a_out = _pid(st, CP_ATT_I, CP_ATT_E, 3, (p.att_kp, p.att_ki, p.att_kd, p.att_lim), T, st.s_euler, a_out)
+        else:  # roll / pitch angles, yaw stays a rate
+            a_out[:, :2] = _pid(st, CP_ATT_I, CP_ATT_E, 2, att2, T, st.s_euler[:, :2], a_out[:, :2])
+    # height: z -> vz -> thrust
+    if mode in (2, 3, 4, 7):
+        z_out = _pid(st, CP_ZP_I, CP_ZP_E, 1, tuple((g,) for g in p.zpos_pid), T, st.s_pos[:, 2:3], z_out[:, None])[:, 0]
+    if mode != 0:
+        z_out = _pid(st, CP_ZV_I, CP_ZV_E, 1, tuple((g,) for g in p.zvel_pid), T, st.s_vb[:, 2:3], z_out[:, None])[:, 0]
+    z_out = np.clip(z_out, 0.0, 1.0)
+    e = a_out - st.s_wb
     st.pid_i = np.clip(st.pid_i + ki * e * T, -lim, lim)
     d = kd * (e - st.pid_e) / T
     out = np.clip(kp * e + st.pid_i + d, -lim, lim)
     st.pid_e = e
-    cmd = np.concatenate([out, setpoint[:, 3:4]], axis=1)
+    cmd = np.concatenate([out, z_out[:, None]], axis=1)
     pwm = cmd @ np.asarray(p.motor_map).T
     high = pwm.max(axis=1, keepdims=True)
     pwm = np.where(high > 1.0, pwm / np.where(high > 1.0, high, 1.0), pwm)

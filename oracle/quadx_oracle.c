@@ -8,7 +8,8 @@
  * (oracle/quadx_model.py, oracle/vision.py, oracle/hover_oracle.py), i.e.
  *   - /root/reference/simulation/hover.py:72-113 (reset), :224-272 (obs),
  *     :274-332 (reward / termination), :334-358 (step)
- *   - PyFlyt 0.21.0 QuadX mode 0 + pybullet 3.2.7 free-flight integration as
+ *   - PyFlyt 0.21.0 QuadX (mode 0 as hover.py:92 sets it, plus the outer loops of
+ *     flight modes -1..7, cf2x.yaml:21-53) + pybullet 3.2.7 free-flight integration as
  *     restated in SURVEY.md section 9 (third-party; PARITY UNPINNED), with the
  *     parameters of cf2x.yaml:1-19 and cf2x.urdf:10-68.
  * tests/test_c_oracle.py pins it against the numpy oracle (which is pinned
@@ -36,10 +37,15 @@ typedef struct {
   double agent_dt, flight_dome_size, floor_threshold, target_area, target_ratio, action_scale[3];
   double start_pos[3], start_rpy[3], spawn_throttle, spawn_pos_noise, spawn_yaw_noise;
   int32_t render, auto_reset, noise;
+  /* PyFlyt QuadX.set_mode (-1..7) and the outer loops' gains (kp[w] ki[w] kd[w] lim[w]), cf2x.yaml:21-53 */
+  int32_t flight_mode;
+  double thrust_scale, thrust_bias;
+  double att[12], vel[8], lpos[8], zpos[4], zvel[4];
 } OrcConfig;
 
 typedef struct {
   double pos[3], quat[4], vel[3], omega[3], thr[4], pid_i[3], pid_e[3];
+  double cpid[18]; /* outer-loop (integral, previous error): att 0/3, vel 6/8, pos 10/12, z_vel 14/15, z_pos 16/17 */
   double s_wb[3], s_euler[3], s_vb[3], s_pos[3];
   double action[4], prev_action[4], prev_centre[2], prev_area, prev_ratio, prev_euler[3], ep_return;
   int64_t step_count;
@@ -130,26 +136,59 @@ static void snapshot(OrcEnv* e) {
   memcpy(e->s_pos, e->pos, sizeof(e->pos));
 }
 
-/* ---- QuadX.update_control, mode 0 ------------------------------------------- */
+/* ---- PyFlyt PID.step: w channels, gains g = kp[w] ki[w] kd[w] lim[w], memory mi / me --------------------- */
+static void pid(const double* g, int w, double T, double* mi, double* me, const double* state, const double* sp, double* out) {
+  for (int a = 0; a < w; ++a) {
+    double err = sp[a] - state[a], lim = g[3 * w + a];
+    mi[a] = clampd(mi[a] + g[w + a] * err * T, -lim, lim);
+    double d = g[2 * w + a] * (err - me[a]) / T;
+    me[a] = err;
+    out[a] = clampd(g[a] * err + mi[a] + d, -lim, lim);
+  }
+}
+
+/* ---- QuadX.update_control: outer loops of the flight mode -> rate PID -> mix -> saturation ------------------- */
 static void control(const OrcConfig* c, OrcEnv* e, const double sp[4], double pwm[4]) {
-  double T = 1.0 / c->control_hz, cmd[4];
-  for (int a = 0; a < 3; ++a) {
-    double err = sp[a] - e->s_wb[a];
-    e->pid_i[a] = clampd(e->pid_i[a] + c->ki[a] * err * T, -c->lim[a], c->lim[a]);
-    double d = c->kd[a] * (err - e->pid_e[a]) / T;
-    cmd[a] = clampd(c->kp[a] * err + e->pid_i[a] + d, -c->lim[a], c->lim[a]);
-    e->pid_e[a] = err;
+  double T = 1.0 / c->control_hz, cmd[4], a[3] = {sp[0], sp[1], sp[2]}, z = sp[3];
+  int mode = c->flight_mode;
+  double* m = e->cpid;
+  if (mode == -1) { for (int k = 0; k < 4; ++k) pwm[k] = sp[k]; return; }
+  if (mode == 1 || mode == 3) pid(c->att, 3, T, m + 0, m + 3, e->s_euler, a, a);
+  else if (mode >= 4) {
+    if (mode == 7) pid(c->lpos, 2, T, m + 10, m + 12, e->s_pos, a, a);
+    if (mode >= 6) {
+      double cy = cos(e->s_euler[2]), sy = sin(e->s_euler[2]), gx = a[0], gy = a[1];
+      a[0] = cy * gx + sy * gy; a[1] = -sy * gx + cy * gy;
+    }
+    double ang[2];
+    pid(c->vel, 2, T, m + 6, m + 8, e->s_vb, a, ang);
+    a[0] = -ang[1]; a[1] = ang[0];
+    if (mode == 7) pid(c->att, 3, T, m + 0, m + 3, e->s_euler, a, a);
+    else {
+      double g2[8] = {c->att[0], c->att[1], c->att[3], c->att[4], c->att[6], c->att[7], c->att[9], c->att[10]};
+      pid(g2, 2, T, m + 0, m + 3, e->s_euler, a, a);
+    }
   }
-  cmd[3] = sp[3];
+  if (mode == 2 || mode == 3 || mode == 4 || mode == 7) pid(c->zpos, 1, T, m + 16, m + 17, e->s_pos + 2, &z, &z);
+  if (mode != 0) pid(c->zvel, 1, T, m + 14, m + 15, e->s_vb + 2, &z, &z);
+  z = clampd(z, 0.0, 1.0);
+  for (int k = 0; k < 3; ++k) {
+    double err = a[k] - e->s_wb[k];
+    e->pid_i[k] = clampd(e->pid_i[k] + c->ki[k] * err * T, -c->lim[k], c->lim[k]);
+    double d = c->kd[k] * (err - e->pid_e[k]) / T;
+    cmd[k] = clampd(c->kp[k] * err + e->pid_i[k] + d, -c->lim[k], c->lim[k]);
+    e->pid_e[k] = err;
+  }
+  cmd[3] = z;
   double high = -1e300, low = 1e300;
-  for (int m = 0; m < 4; ++m) {
-    pwm[m] = 0;
-    for (int j = 0; j < 4; ++j) pwm[m] += cmd[j] * c->motor_map[4 * m + j];
-    if (pwm[m] > high) high = pwm[m];
+  for (int k = 0; k < 4; ++k) {
+    pwm[k] = 0;
+    for (int j = 0; j < 4; ++j) pwm[k] += cmd[j] * c->motor_map[4 * k + j];
+    if (pwm[k] > high) high = pwm[k];
   }
-  if (high > 1.0) for (int m = 0; m < 4; ++m) pwm[m] /= high;
-  for (int m = 0; m < 4; ++m) if (pwm[m] < low) low = pwm[m];
-  if (low < c->pwm_idle) for (int m = 0; m < 4; ++m) pwm[m] = pwm[m] + (1.0 - pwm[m]) / (1.0 - low) * (c->pwm_idle - low);
+  if (high > 1.0) for (int k = 0; k < 4; ++k) pwm[k] /= high;
+  for (int k = 0; k < 4; ++k) if (pwm[k] < low) low = pwm[k];
+  if (low < c->pwm_idle) for (int k = 0; k < 4; ++k) pwm[k] = pwm[k] + (1.0 - pwm[k]) / (1.0 - low) * (c->pwm_idle - low);
 }
 
 /* ---- update_physics + update_state + stepSimulation, one sub-step ------------ */
@@ -292,13 +331,15 @@ static void reset_env(const Orc* o, int64_t i, OrcEnv* e, double* obs) {
   euler_to_quat(rpy, e->quat);
   memset(e->vel, 0, sizeof(e->vel)); memset(e->omega, 0, sizeof(e->omega));
   for (int m = 0; m < 4; ++m) e->thr[m] = c->spawn_throttle;
-  memset(e->pid_i, 0, sizeof(e->pid_i)); memset(e->pid_e, 0, sizeof(e->pid_e));
+  memset(e->pid_i, 0, sizeof(e->pid_i)); memset(e->pid_e, 0, sizeof(e->pid_e)); memset(e->cpid, 0, sizeof(e->cpid));
   e->contact = pos[2] <= c->floor_z;
   snapshot(e);
   e->step_count = 0; e->terminated = e->truncated = e->oob = e->on_floor = 0;
   memset(e->action, 0, sizeof(e->action));
   e->prev_centre[0] = e->prev_centre[1] = e->prev_area = e->prev_ratio = 0; e->ep_return = 0;
-  double sp[4] = {0, 0, 0, 0};
+  double sp[4] = {0, 0, 0, 0}; /* QuadX.set_mode's preset: hold the current height (modes 2-4) / pose (mode 7) */
+  if (c->flight_mode == 2 || c->flight_mode == 3 || c->flight_mode == 4) sp[3] = e->s_pos[2];
+  if (c->flight_mode == 7) { sp[0] = e->s_pos[0]; sp[1] = e->s_pos[1]; sp[2] = e->s_euler[2]; sp[3] = e->s_pos[2]; }
   aviary_steps(o, i, e, sp, c->reset_idle_steps, STREAM_RESET, e->rng_ctr);
   memcpy(e->prev_euler, e->s_euler, sizeof(e->prev_euler));
   compute_state(c, e, obs);
@@ -310,7 +351,8 @@ static void step_env(Orc* o, int64_t i, const double* act, double* obs, double* 
   const OrcConfig* c = &o->c;
   OrcEnv* e = &o->e[i];
   memcpy(e->action, act, 4 * sizeof(double));
-  double sp[4] = {act[0] * c->action_scale[0], act[1] * c->action_scale[1], act[2] * c->action_scale[2], (act[3] + 1) / 2};
+  double sp[4] = {act[0] * c->action_scale[0], act[1] * c->action_scale[1], act[2] * c->action_scale[2], act[3] * c->thrust_scale + c->thrust_bias};
+  if (c->flight_mode == -1) for (int a = 0; a < 3; ++a) sp[a] = act[a] * c->thrust_scale + c->thrust_bias; /* four motor pwm commands */
   double r = -0.1;
   if (!(e->terminated || e->truncated)) aviary_steps(o, i, e, sp, c->env_step_ratio, STREAM_STEP, e->rng_ctr);
   e->rng_ctr += 1;

@@ -68,7 +68,35 @@ def run_scenario(hover, name, seed, noise, n_steps, action_fn, env_id=0, second_
           f"truncated at {np.argmax(out['truncated']) if out['truncated'].any() else None}, return {out['reward'].sum():.3f} -> {path}")
 
 
+def drone_params(ref_root="/root/reference") -> dict:
+    """The numbers of simulation/drone_models/cf2x/cf2x.yaml and cf2x.urdf, parsed from the
+    reference's own files, as a flat dict of lists."""
+    import xml.etree.ElementTree as ET
+
+    import yaml
+
+    d = os.path.join(ref_root, "simulation", "drone_models", "cf2x")
+    y = yaml.safe_load(open(os.path.join(d, "cf2x.yaml")))
+    out = {f"motor.{k}": float(v) for k, v in y["motor_params"].items()}
+    out.update({f"drag.{k}": float(v) for k, v in y["drag_params"].items()})
+    for loop, g in y["control_params"].items():
+        for k in ("kp", "ki", "kd", "lim"):
+            out[f"{loop}.{k}"] = [float(x) for x in np.atleast_1d(g[k])]
+    base = ET.parse(os.path.join(d, "cf2x.urdf")).getroot().find("link[@name='base_link']")
+    inert = base.find("inertial")
+    out["urdf.mass"] = float(inert.find("mass").get("value"))
+    out["urdf.inertia_diag"] = [float(inert.find("inertia").get(k)) for k in ("ixx", "iyy", "izz")]
+    out["urdf.collision_box"] = [float(x) for x in base.find("collision/geometry/box").get("size").split()]
+    root = ET.parse(os.path.join(d, "cf2x.urdf")).getroot()
+    out["urdf.prop_xyz"] = [[float(x) for x in root.find(f"link[@name='prop{i}_link']/inertial/origin").get("xyz").split()] for i in (1, 2, 3, 4)]
+    return out
+
+
 def main():
+    import json
+
+    with open(os.path.join(OUT, "cf2x_params.json"), "w") as f:
+        json.dump(drone_params(), f, indent=1, sort_keys=True)
     hover = af.import_reference_hover("/root/reference")
     rng = np.random.default_rng(2024)
     tgt = np.array([[0.4, -0.3, 0.9]])

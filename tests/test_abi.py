@@ -43,7 +43,7 @@ def test_config_layout_and_defaults(built):
     from oracle.quadx_model import QuadXParams
 
     L = built.lib()
-    assert L.qx_version() == 1
+    assert L.qx_version() == 2
     assert L.qx_sizeof_config() == ctypes.sizeof(built.QxConfig)
     c = built.default_config(built.QX_TASK_HOVER)
     p, h = QuadXParams(), HoverConfig()
@@ -65,6 +65,11 @@ def test_config_layout_and_defaults(built):
     assert c.floor_grace_steps == h.floor_grace_steps and c.agent_dt == f(h.agent_dt)
     assert c.flight_dome_size == h.flight_dome_size and c.floor_threshold == f(h.floor_threshold)
     assert c.target_area == f(h.target_area) and c.target_ratio == f(h.target_ratio) and list(c.action_scale) == list(h.action_scale)
+    # flight modes: mode 0 like hover.py:92, (a3 + 1) / 2 thrust mapping, outer-loop gains of cf2x.yaml:21-54
+    assert c.flight_mode == p.flight_mode == 0 and c.thrust_scale == h.thrust_scale and c.thrust_bias == h.thrust_bias
+    assert list(c.att_pid) == f([*p.att_kp, *p.att_ki, *p.att_kd, *p.att_lim]) and list(c.vel_pid) == f([*p.vel_kp, *p.vel_ki, *p.vel_kd, *p.vel_lim])
+    assert list(c.pos_pid) == f([*p.pos_kp, *p.pos_ki, *p.pos_kd, *p.pos_lim])
+    assert list(c.zpos_pid) == f(list(p.zpos_pid)) and list(c.zvel_pid) == f(list(p.zvel_pid))
 
 
 def test_no_gpu_means_loud_failure(built):

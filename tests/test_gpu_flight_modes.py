@@ -1,0 +1,109 @@
+"""GPU: PyFlyt flight modes -1..7 (the rest of the rate/attitude PID cascade, cf2x.yaml:21-54) in the
+CUDA env step, through the C-ABI, against the float64 oracle on the same seeded action sequences.
+
+The reference env never leaves mode 0 (hover.py:92), so this is parity with the restated oracle only (PyFlyt itself
+is not installable here: parity unpinned).  Tolerances as in test_gpu_parity.py: state error / full scale <= 1e-3
+(3 m for position, 1 otherwise; 3e-3 for the open-loop mode -1), non-camera observation columns 2e-3, flags identical."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import FLIGHT_MODE_SCALING, NONVISION_COLS, kernel_state_arrays
+
+pytestmark = pytest.mark.gpu
+HOVER_THR = float(np.sqrt(0.1 * 9.81 / 4.0))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import fpv_drone_rl_agent_b200 as pkg
+
+    return pkg
+
+
+def _pair(pkg, mode, n, seed, noise=True, **extra):
+    from oracle.hover_oracle import HoverConfig, HoverVecOracle
+    from oracle.quadx_model import QuadXParams
+
+    kw = dict(start_pos=(0.0, 0.0, 1.5), spawn_throttle=HOVER_THR, spawn_pos_noise=0.2, spawn_yaw_noise=1.0, **FLIGHT_MODE_SCALING[mode])
+    kw.update(extra)
+    cfg = pkg.default_config()
+    cfg.update(flight_mode=mode, auto_reset=1, noise=int(noise), **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()})
+    sim = pkg.QuadXSim(n, cfg, seed=seed, env_id0=5)
+    orc = HoverVecOracle(n, QuadXParams(flight_mode=mode), HoverConfig(**kw), seed=seed, env_id0=5, auto_reset=True, noise=noise)
+    return sim, orc
+
+
+def _rel(a, b, scale):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float((np.abs(a - b) / np.maximum(scale, np.abs(b))).max()) if a.size else 0.0
+
+
+@pytest.mark.parametrize("mode", sorted(FLIGHT_MODE_SCALING))
+def test_flight_mode_matches_oracle(pkg, mode):
+    # mode -1 has no controller in the loop: 2 % motor noise alone tumbles the drone into the floor within a second,
+    # and contact is chaotic -- that mode is compared with the noise off
+    n, steps = 192, 100
+    sim, orc = _pair(pkg, mode, n, seed=21 + mode, noise=mode != -1)
+    assert len(sim.state_fields) == (44 if mode == 0 else 68)
+    d = sim.device
+    obs = torch.zeros(n, 20, device=d); rew = torch.zeros(n, device=d)
+    te = torch.zeros(n, dtype=torch.uint8, device=d); tr = torch.zeros(n, dtype=torch.uint8, device=d)
+    sim.reset(obs)
+    torch.cuda.synchronize()
+    o2 = orc.reset()  # includes the 10 idle Aviary.step() tracking set_mode's preset setpoint
+    assert _rel(obs.cpu().numpy()[:, NONVISION_COLS], o2[:, NONVISION_COLS], 1.0) <= 2e-3
+    rng = np.random.default_rng(100 + mode)
+    a = rng.uniform(-1, 1, (n, 4))
+    worst = {}
+    for k in range(steps):
+        if k % 10 == 0:  # hold every command for 10 agent steps (0.5 s) so the outer loops act on it
+            a = rng.uniform(-1, 1, (n, 4))
+            if mode in (1, 5, 6):
+                a[:, 3] *= 0.3  # climb-rate command
+        sim.step(torch.as_tensor(a, dtype=torch.float32, device=d).contiguous(), obs, rew, te, tr, None)
+        torch.cuda.synchronize()
+        o2, r2, te2, tr2, _ = orc.step(a.astype(np.float32).astype(np.float64))
+        assert np.array_equal(te.cpu().numpy().astype(bool), te2) and np.array_equal(tr.cpu().numpy().astype(bool), tr2), (mode, k)
+        assert _rel(obs.cpu().numpy()[:, NONVISION_COLS], o2[:, NONVISION_COLS], 1.0) <= 2e-3, (mode, k)
+        if k % 20 == 19:
+            s = sim.get_state()
+            pos, quat, vel, om, thr = kernel_state_arrays(s)
+            sgn = np.sign((quat * orc.st.quat).sum(1, keepdims=True))
+            for name, x, y, sc in (("pos", pos, orc.st.pos, 3.0), ("quat", quat * sgn, orc.st.quat, 1.0), ("vel", vel, orc.st.vel, 1.0),
+                                   ("omega", om, orc.st.omega, 1.0), ("thr", thr, orc.st.thr, 1.0)):
+                worst[name] = max(worst.get(name, 0.0), _rel(x, y, sc))
+            if mode not in (0, -1):
+                from fpv_drone_rl_agent_b200.hover_env import CASCADE_FIELDS
+
+                cp = np.stack([s[f] for f in CASCADE_FIELDS[:18]], 1)
+                worst["outer-loop memory"] = max(worst.get("outer-loop memory", 0.0), _rel(cp, orc.st.cpid, 1.0))
+                worst["snapshot pos"] = max(worst.get("snapshot pos", 0.0), _rel(np.stack([s["s_px"], s["s_py"], s["s_pz"]], 1), orc.st.s_pos, 3.0))
+    print(f"mode {mode}: worst error / full scale over {steps} steps:", {k: f"{v:.2e}" for k, v in worst.items()})
+    # mode -1 is open loop (no controller pulls the two trajectories together): its bound is 3e-3
+    assert max(worst.values()) <= (3e-3 if mode == -1 else 1e-3), worst
+    if mode in (2, 3, 4, 7):  # the height loop did its job: the fleet holds its altitude band
+        assert np.median(orc.st.pos[:, 2]) > 0.8 and not orc.st.contact.any()
+    sim.close()
+
+
+def test_mode0_thrust_command_is_clipped(pkg):
+    """QuadX.update_control clips the mode-0 thrust to [0, 1]: out-of-Box actions (hover.py does not check them) saturate."""
+    n = 64
+    sim, orc = _pair(pkg, 0, n, seed=2, noise=False, spawn_pos_noise=0.0, spawn_yaw_noise=0.0)
+    d = sim.device
+    obs = torch.zeros(n, 20, device=d); rew = torch.zeros(n, device=d)
+    te = torch.zeros(n, dtype=torch.uint8, device=d); tr = torch.zeros(n, dtype=torch.uint8, device=d)
+    sim.reset(obs); orc.reset()
+    a = np.zeros((n, 4)); a[:, 3] = np.linspace(-3, 3, n)
+    for _ in range(3):
+        sim.step(torch.as_tensor(a, dtype=torch.float32, device=d).contiguous(), obs, rew, te, tr, None)
+        orc.step(a)
+    torch.cuda.synchronize()
+    thr = kernel_state_arrays(sim.get_state())[4]
+    assert _rel(thr, orc.st.thr, 1.0) <= 1e-3
+    assert thr.max() <= 1.1 and np.allclose(thr[-1], thr[n * 2 // 3 + 1], atol=0.05)  # a3 = 3 flies like a3 = 1
+    sim.close()

@@ -116,3 +116,27 @@ def test_analytic_vision_close_to_rasterised():
     assert np.abs(C - c)[both].max() * 64 <= 1.5  # pixels
     assert (np.abs(A - a)[both] / A[both]).max() <= 0.10
     assert np.abs(R - r)[both].max() <= 0.35  # one pixel row/column on a ~5 px high quad
+
+
+def test_drone_parameters_match_reference_files(golden_dir):
+    """every number the oracle (and, via tests/test_abi.py, qx_default_config) uses for the drone
+    is the one in the reference's cf2x.yaml / cf2x.urdf (fixture written by tests/golden/make_golden.py:drone_params)."""
+    import json
+
+    g = json.load(open(os.path.join(golden_dir, "cf2x_params.json")))
+    p = QuadXParams()
+    for k in ("total_thrust", "thrust_coef", "torque_coef", "noise_ratio", "tau"):
+        assert getattr(p, k) == g[f"motor.{k}"], k
+    for k in ("drag_coef_xyz", "drag_area_xyz", "drag_coef_pqr"):
+        assert getattr(p, k) == g[f"drag.{k}"], k
+    for ours, loop in (("rate", "ang_vel"), ("att", "ang_pos"), ("vel", "lin_vel"), ("pos", "lin_pos")):
+        for k in ("kp", "ki", "kd", "lim"):
+            assert list(getattr(p, f"{ours}_{k}")) == g[f"{loop}.{k}"], (loop, k)
+    assert list(p.zpos_pid) == [g[f"z_pos.{k}"][0] for k in ("kp", "ki", "kd", "lim")]
+    assert list(p.zvel_pid) == [g[f"z_vel.{k}"][0] for k in ("kp", "ki", "kd", "lim")]
+    assert p.mass == g["urdf.mass"] and list(p.inertia) == g["urdf.inertia_diag"]
+    assert [list(m) for m in p.motor_xy] == [xyz[:2] for xyz in g["urdf.prop_xyz"]] and all(xyz[2] == 0 for xyz in g["urdf.prop_xyz"])
+    assert p.floor_z == g["urdf.collision_box"][2] / 2  # the floor stand-in is the rest height of the collision box
+    # the motor map is derived from the prop positions: tau = r x F = (y F, -x F)
+    for (x, y), row in zip(p.motor_xy, p.motor_map):
+        assert row[0] == np.sign(y) and row[1] == -np.sign(x) and row[3] == 1.0

@@ -32,6 +32,17 @@ def test_reference_constants(hover):
     assert env.action_space.shape == (4,) and env.observation_space.shape == (20,)
 
 
+def test_drone_parameter_fixture_is_current(golden_dir):
+    """tests/golden/cf2x_params.json is what the reference's cf2x.yaml / cf2x.urdf say today."""
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    assert mg.drone_params("/root/reference") == json.load(open(os.path.join(golden_dir, "cf2x_params.json")))
+
+
 def test_golden_vectors_are_current(hover, golden_dir):
     from oracle import aviary_facade as af
     from oracle.quadx_model import NoiseSource, QuadXParams

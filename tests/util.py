@@ -52,3 +52,17 @@ def kernel_state_arrays(s: dict):
 # obs columns produced by the camera (hover.py:257-263)
 VISION_COLS = [7, 8, 9, 10, 11, 12, 13, 14, 15]
 NONVISION_COLS = [0, 1, 2, 3, 4, 5, 6, 16, 17, 18, 19]
+
+# PyFlyt flight modes (-1..7): how a Box(-1, 1) action is scaled into each mode's setpoint in the tests
+# (action_scale for the first three channels, thrust_scale * a3 + thrust_bias for the fourth)
+FLIGHT_MODE_SCALING = {
+    -1: dict(action_scale=(0.0, 0.0, 0.0), thrust_scale=0.0003, thrust_bias=0.53),  # four motor pwm, all via thrust_scale / bias (open loop: keep it gentle)
+    0: dict(action_scale=(30.0, 30.0, -30.0), thrust_scale=0.5, thrust_bias=0.5),  # hover.py:337-341
+    1: dict(action_scale=(0.3, 0.3, 1.0), thrust_scale=1.0, thrust_bias=0.0),      # p, q, r [rad], vz [m/s]
+    2: dict(action_scale=(0.3, 0.3, 1.0), thrust_scale=0.5, thrust_bias=1.2),      # vp, vq, vr [rad/s], z [m]
+    3: dict(action_scale=(0.3, 0.3, 1.0), thrust_scale=0.5, thrust_bias=1.2),      # p, q, r, z
+    4: dict(action_scale=(1.0, 1.0, 1.0), thrust_scale=0.5, thrust_bias=1.2),      # u, v [m/s], vr, z
+    5: dict(action_scale=(1.0, 1.0, 1.0), thrust_scale=1.0, thrust_bias=0.0),      # u, v, vr, vz
+    6: dict(action_scale=(1.0, 1.0, 1.0), thrust_scale=1.0, thrust_bias=0.0),      # vx, vy, vr, vz
+    7: dict(action_scale=(1.0, 1.0, 1.5), thrust_scale=0.5, thrust_bias=1.2),      # x, y [m], r [rad], z
+}

@@ -20,7 +20,9 @@ FLOP_PER_SAMPLE = 77056  # [128,128] pi and vf nets on 20-D obs
 GAE_BYTES = 17  # r, V, done in; adv, ret out
 
 
-def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, world: int = 1, rollout_only: bool = False) -> dict:
+def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, world: int = 1, rollout_only: bool = False,
+            task: int = 0) -> dict:
+    """task 0 = hover (20-D obs, 4-D action); task 1 = yaw (12-D obs, 1-D action; BASELINE configs[2], rollout only)."""
     import torch
 
     from fpv_drone_rl_agent_b200 import ppo
@@ -33,7 +35,7 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, w
     tflops_peak = peaks.get("bf16_tflops", 1590.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     cfg = ppo.PPOConfig(n_envs=envs, n_steps=steps, seed=0, use_cuda_graph=True)
-    tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world)
+    tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world, task=task)
     ro = tr.rollout
 
     def timed(fn, reps=reps):
@@ -48,10 +50,10 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, w
     ro.collect(); ro.collect()
     torch.cuda.synchronize()
     ms = timed(ro.collect)
-    out = {"envs": envs, "n_steps": steps,
+    out = {"task": "yaw" if task else "hover", "envs": envs, "n_steps": steps,
            "rollout": {"samples_per_s": envs * steps / (ms * 1e-3), "ms_per_rollout": ms, "launches_per_rollout": ro.launches_per_rollout,
                        "what": "env step + reset + obs/reward normalisation + policy forward + sampling + time-limit bootstrap, x n_steps, + GAE; one CUDA graph replay"}}
-    if rollout_only:
+    if rollout_only or task != 0:
         tr.sim.close()
         return out
     # stand-alone policy forward over a batch larger than L2 is pointless (weights are tiny; activations stay on chip):
@@ -84,8 +86,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=131072)
     ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--task", choices=["hover", "yaw"], default="hover")
     a = ap.parse_args()
     import __graft_entry__ as ge
 
     ge.build()
-    print(json.dumps(measure(a.envs, a.steps)))
+    print(json.dumps(measure(a.envs, a.steps, task=1 if a.task == "yaw" else 0)))
