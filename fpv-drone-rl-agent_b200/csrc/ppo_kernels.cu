@@ -526,26 +526,86 @@ __global__ void __launch_bounds__(1024) gae_warpscan_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------
-// K4: VecNormalize running statistics.  Stage 1: per-block fp64 sums of x and
-// x^2 per column; stage 2 (one block): batch moments -> parallel-Welford merge
-// into {mean[dim], var[dim], count} and refresh the fp32 mean / inv_std.
+// K4: VecNormalize running statistics, one launch: every block leaves fp64 sums
+// of x and x^2 per column in the scratch buffer; the block that finishes last
+// (a ticket in the tail of the scratch buffer) turns them into batch moments
+// and does the parallel-Welford merge into {mean[dim], var[dim], count}, and
+// refreshes the fp32 mean / inv_std the policy kernel reads.
 // ---------------------------------------------------------------------------
-constexpr int kStatBlocks = 296, kStatThreads = 256, kStatMaxDim = 32;
+constexpr int kStatBlocks = 148, kStatThreads = 1024, kRetThreads = 1024, kStatMaxDim = 32;  // one wave of full-SM blocks
+constexpr size_t kStatTicketOffset = (size_t)kStatBlocks * 2 * kStatMaxDim;  // in doubles
+
+// true in exactly one block per launch: the last one to arrive; it re-arms the ticket for the next launch / graph replay
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+  __shared__ bool is_last;
+  __threadfence();  // this block's partial sums are visible device-wide before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// one warp per column: lanes stride over the per-block partial sums (at most kStatBlocks / 32 = 5 each, all loads issued
+// before the first add), shuffle-reduce, lane 0 does the Welford merge
+__device__ __forceinline__ void welford_merge_block(const double* part, int nblocks, int64_t n, int dim, double* __restrict__ stats, float eps,
+                                                    float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const double count = stats[2 * dim], bc = (double)n, tot = count + bc;
+  const double inv_bc = 1.0 / bc, inv_tot = 1.0 / tot;
+  __syncthreads();  // every warp has the old count before thread 0 replaces it
+  constexpr int kPer = (kStatBlocks + 31) / 32;
+  for (int j = w; j < dim; j += nw) {
+    double sv[kPer], qv[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int b = lane + 32 * k;
+      sv[k] = b < nblocks ? __ldcg(part + (size_t)b * 2 * kStatMaxDim + j) : 0.0;
+      qv[k] = b < nblocks ? __ldcg(part + (size_t)b * 2 * kStatMaxDim + kStatMaxDim + j) : 0.0;
+    }
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { s += sv[k]; q += qv[k]; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+      const double bm = s * inv_bc, bv = fmax(q * inv_bc - bm * bm, 0.0);
+      const double mean = stats[j], var = stats[dim + j];
+      const double delta = bm - mean;
+      const double new_mean = mean + delta * bc * inv_tot;
+      const double new_var = (var * count + bv * bc + delta * delta * count * bc * inv_tot) * inv_tot;
+      stats[j] = new_mean;
+      stats[dim + j] = new_var;
+      if (mean_f32) mean_f32[j] = (float)new_mean;
+      if (inv_std_f32) inv_std_f32[j] = (float)(1.0 / sqrt(new_var + (double)eps));
+    }
+  }
+  if (threadIdx.x == 0) stats[2 * dim] = tot;
+}
 
 // lane = column (dim <= 32), each warp strides over rows: a row is one coalesced load, no cross-lane reduction is needed;
-// the 8 warps of a block are combined through shared memory
-__global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float* __restrict__ x, int64_t stride, int64_t n, int dim, double* __restrict__ part) {
+// 32 warps per block keep enough loads in flight (the kernel is latency-, not bandwidth-bound: 10 MB at 131 072 x 20);
+// the warps of a block are combined through shared memory
+__global__ void __launch_bounds__(kStatThreads) running_stats_kernel(const float* __restrict__ x, int64_t stride, int64_t n, int dim,
+                                                                    double* __restrict__ scratch, double* __restrict__ stats, float eps,
+                                                                    float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
   __shared__ double sh[kStatThreads / 32][2 * kStatMaxDim];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warp_id = (int64_t)blockIdx.x * (kStatThreads / 32) + w, n_warps = (int64_t)gridDim.x * (kStatThreads / 32);
   double s = 0.0, q = 0.0;
   if (lane < dim) {
     int64_t i = warp_id;
-    for (; i + 3 * n_warps < n; i += 4 * n_warps) {  // four independent loads in flight
-      const float v0 = x[i * stride + lane], v1 = x[(i + n_warps) * stride + lane], v2 = x[(i + 2 * n_warps) * stride + lane],
-                  v3 = x[(i + 3 * n_warps) * stride + lane];
-      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
-      q += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+    for (; i + 7 * n_warps < n; i += 8 * n_warps) {  // eight independent loads in flight per lane
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = x[(i + k * n_warps) * stride + lane];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        s += (double)v[k] + (double)v[k + 1];
+        q += (double)v[k] * v[k] + (double)v[k + 1] * v[k + 1];
+      }
     }
     for (; i < n; i += n_warps) { const double v = (double)x[i * stride + lane]; s += v; q += v * v; }
   }
@@ -553,44 +613,21 @@ __global__ void __launch_bounds__(kStatThreads) stats_partial_kernel(const float
   __syncthreads();
   if (threadIdx.x < 2 * kStatMaxDim) {
     double a = 0.0;
+#pragma unroll
     for (int k = 0; k < kStatThreads / 32; ++k) a += sh[k][threadIdx.x];
-    part[(size_t)blockIdx.x * 2 * kStatMaxDim + threadIdx.x] = a;
+    scratch[(size_t)blockIdx.x * 2 * kStatMaxDim + threadIdx.x] = a;
   }
+  if (last_block_done(reinterpret_cast<unsigned int*>(scratch + kStatTicketOffset)))
+    welford_merge_block(scratch, (int)gridDim.x, n, dim, stats, eps, mean_f32, inv_std_f32);
 }
 
-// one warp per column: lanes stride over the per-block partial sums, shuffle-reduce, lane 0 does the Welford merge
-__global__ void __launch_bounds__(kStatMaxDim * 32) stats_merge_kernel(const double* __restrict__ part, int nblocks, int64_t n, int dim, double* __restrict__ stats,
-                                                                      float eps, float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
-  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool on = j < dim;
+// reward path, first half fused: ret = ret * gamma + r (VecNormalize.step_wait), the per-block sums of ret, ret^2, and -- in
+// the block that finishes last -- the merge into the running variance of the discounted return
+__global__ void __launch_bounds__(kRetThreads) returns_stats_kernel(const float* __restrict__ r, float* __restrict__ acc, int64_t n, float gamma,
+                                                                   double* __restrict__ scratch, double* __restrict__ ret_stats, float eps) {
+  __shared__ double sh[kRetThreads / 32][2];
   double s = 0.0, q = 0.0;
-  if (on)
-    for (int b = lane; b < nblocks; b += 32) { s += part[(size_t)b * 2 * kStatMaxDim + j]; q += part[(size_t)b * 2 * kStatMaxDim + kStatMaxDim + j]; }
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  double new_mean = 0.0, new_var = 1.0, tot = 0.0;
-  if (on) {
-    const double bc = (double)n, bm = s / bc, bv = fmax(q / bc - bm * bm, 0.0);
-    const double mean = stats[j], var = stats[dim + j], count = stats[2 * dim];
-    const double delta = bm - mean;
-    tot = count + bc;
-    new_mean = mean + delta * bc / tot;
-    new_var = (var * count + bv * bc + delta * delta * count * bc / tot) / tot;
-  }
-  __syncthreads();  // every warp has read the old count before warp 0 replaces it
-  if (!on || lane != 0) return;
-  stats[j] = new_mean;
-  stats[dim + j] = new_var;
-  if (j == 0) stats[2 * dim] = tot;
-  if (mean_f32) mean_f32[j] = (float)new_mean;
-  if (inv_std_f32) inv_std_f32[j] = (float)(1.0 / sqrt(new_var + (double)eps));
-}
-
-// reward path, first half fused: ret = ret * gamma + r (VecNormalize.step_wait) and the per-block sums of ret, ret^2
-__global__ void __launch_bounds__(kStatThreads) returns_partial_kernel(const float* __restrict__ r, float* __restrict__ acc, int64_t n, float gamma,
-                                                                      double* __restrict__ part) {
-  __shared__ double sh[kStatThreads / 32][2];
-  double s = 0.0, q = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStatThreads) {
+  for (int64_t i = (int64_t)blockIdx.x * kRetThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRetThreads) {
     const float v = fmaf(acc[i], gamma, r[i]);
     acc[i] = v;
     s += (double)v; q += (double)v * (double)v;
@@ -601,9 +638,11 @@ __global__ void __launch_bounds__(kStatThreads) returns_partial_kernel(const flo
   __syncthreads();
   if (threadIdx.x < 2) {
     double a = 0.0;
-    for (int k = 0; k < kStatThreads / 32; ++k) a += sh[k][threadIdx.x];
-    part[(size_t)blockIdx.x * 2 * kStatMaxDim + (threadIdx.x ? kStatMaxDim : 0)] = a;
+    for (int k = 0; k < kRetThreads / 32; ++k) a += sh[k][threadIdx.x];
+    scratch[(size_t)blockIdx.x * 2 * kStatMaxDim + (threadIdx.x ? kStatMaxDim : 0)] = a;
   }
+  if (last_block_done(reinterpret_cast<unsigned int*>(scratch + kStatTicketOffset)))
+    welford_merge_block(scratch, (int)gridDim.x, n, 1, ret_stats, eps, nullptr, nullptr);
 }
 
 __global__ void __launch_bounds__(256) reward_norm_kernel(const float* __restrict__ r, const uint8_t* __restrict__ te, const uint8_t* __restrict__ tr, float* __restrict__ acc,
@@ -688,15 +727,17 @@ extern "C" int ppo_gae(const float* rewards, const float* values, const uint8_t*
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_gae: launch failed");
 }
 
-extern "C" int64_t ppo_running_stats_scratch_bytes(int32_t dim) { (void)dim; return (int64_t)ppo::kStatBlocks * 2 * ppo::kStatMaxDim * sizeof(double); }
+extern "C" int64_t ppo_running_stats_scratch_bytes(int32_t dim) {
+  (void)dim;
+  return (int64_t)(ppo::kStatTicketOffset + 8) * sizeof(double);  // per-block partial sums + the last-block ticket
+}
 
 extern "C" int ppo_running_stats_update(const float* x, int64_t stride, int64_t n, int32_t dim, double* stats, float eps, float* mean_f32,
                                         float* inv_std_f32, void* scratch, void* stream) {
   if (!x || !stats || !scratch || n <= 0 || dim < 1 || dim > ppo::kStatMaxDim || stride < dim) return pfail(QX_EINVAL, "ppo_running_stats_update: bad arguments");
-  int64_t want = (n + ppo::kStatThreads / 32 * 4 - 1) / (ppo::kStatThreads / 32 * 4);  // >= 4 rows per warp
+  int64_t want = (n + ppo::kStatThreads / 32 * 8 - 1) / (ppo::kStatThreads / 32 * 8);  // >= 8 rows per warp
   const int blocks = (int)(want < ppo::kStatBlocks ? (want < 1 ? 1 : want) : ppo::kStatBlocks);
-  ppo::stats_partial_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(x, stride, n, dim, (double*)scratch);
-  ppo::stats_merge_kernel<<<1, ppo::kStatMaxDim * 32, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, dim, stats, eps, mean_f32, inv_std_f32);
+  ppo::running_stats_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(x, stride, n, dim, (double*)scratch, stats, eps, mean_f32, inv_std_f32);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_running_stats_update: launch failed");
 }
 
@@ -705,10 +746,9 @@ extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminat
   if (!reward || !terminated || !truncated || !returns_acc || !ret_stats || !reward_out || !scratch || n <= 0)
     return pfail(QX_EINVAL, "ppo_reward_normalize: bad arguments");
   const unsigned grid = (unsigned)((n + 255) / 256);
-  int64_t want = (n + ppo::kStatThreads - 1) / ppo::kStatThreads;
+  int64_t want = (n + ppo::kRetThreads - 1) / ppo::kRetThreads;
   const int blocks = (int)(want < ppo::kStatBlocks ? want : ppo::kStatBlocks);
-  ppo::returns_partial_kernel<<<blocks, ppo::kStatThreads, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma, (double*)scratch);
-  ppo::stats_merge_kernel<<<1, ppo::kStatMaxDim * 32, 0, (cudaStream_t)stream>>>((const double*)scratch, blocks, n, 1, ret_stats, eps, nullptr, nullptr);
+  ppo::returns_stats_kernel<<<blocks, ppo::kRetThreads, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma, (double*)scratch, ret_stats, eps);
   ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_reward_normalize: launch failed");
 }

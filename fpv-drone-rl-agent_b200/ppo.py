@@ -341,7 +341,7 @@ class RolloutEngine:
 
     @property
     def launches_per_rollout(self) -> int:
-        per_step = 2 + 1 + 2 + 1 + (3 if self.cfg.norm_reward else 2)  # stats, forward, env step/reset, bootstrap, reward path
+        per_step = (1 if self.cfg.norm_obs else 0) + 1 + 2 + 1 + 2  # obs stats, forward, env step/reset, bootstrap, reward path
         return self.T * per_step + 3
 
 

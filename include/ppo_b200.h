@@ -65,7 +65,10 @@ int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, con
 
 /* VecNormalize running statistics: merge the batch moments of x [n, dim] (row stride `stride`) into
  * stats = {mean[dim], var[dim], count} (fp64, device) with the parallel-Welford update, then refresh
- * mean_f32[dim] / inv_std_f32[dim] = 1/sqrt(var + eps). */
+ * mean_f32[dim] / inv_std_f32[dim] = 1/sqrt(var + eps).  One launch (the last block to finish does the merge).
+ * `scratch`: ppo_running_stats_scratch_bytes(dim) bytes of device memory, ZERO-FILLED once before the first call and
+ * owned by one stats object (it holds the per-block sums and the launch ticket); calls sharing a scratch buffer must be
+ * stream-ordered. */
 int ppo_running_stats_update(const float* x, int64_t stride, int64_t n, int32_t dim, double* stats, float eps, float* mean_f32,
                              float* inv_std_f32, void* scratch, void* stream);
 int64_t ppo_running_stats_scratch_bytes(int32_t dim);
