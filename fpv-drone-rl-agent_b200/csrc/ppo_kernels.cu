@@ -596,18 +596,20 @@ __global__ void __launch_bounds__(kStatThreads) running_stats_kernel(const float
   const int64_t warp_id = (int64_t)blockIdx.x * (kStatThreads / 32) + w, n_warps = (int64_t)gridDim.x * (kStatThreads / 32);
   double s = 0.0, q = 0.0;
   if (lane < dim) {
-    int64_t i = warp_id;
-    for (; i + 7 * n_warps < n; i += 8 * n_warps) {  // eight independent loads in flight per lane
-      float v[8];
+    // 16 independent row loads in flight per lane: at 131 072 rows over 148 x 32 warps that is two trips to L2 / HBM in all
+    for (int64_t i = warp_id; i < n; i += 16 * n_warps) {
+      float v[16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = x[(i + k * n_warps) * stride + lane];
+      for (int k = 0; k < 16; ++k) {
+        const int64_t r = i + k * n_warps;
+        v[k] = r < n ? x[r * stride + lane] : 0.f;
+      }
 #pragma unroll
-      for (int k = 0; k < 8; k += 2) {
+      for (int k = 0; k < 16; k += 2) {
         s += (double)v[k] + (double)v[k + 1];
         q += (double)v[k] * v[k] + (double)v[k + 1] * v[k + 1];
       }
     }
-    for (; i < n; i += n_warps) { const double v = (double)x[i * stride + lane]; s += v; q += v * v; }
   }
   sh[w][lane] = s; sh[w][kStatMaxDim + lane] = q;
   __syncthreads();
