@@ -313,6 +313,8 @@ def main_ours(args):
                     "steps": e2e_steps, "api": "qx_step_host (C-ABI, pinned host buffers, synchronous)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "kernels": ("reference-constant instantiation (model constants of the reference's own parameter set as literals)"
+                        if sim.lib.qx_uses_reference_constants(sim._h) else "generic (every constant read from the config)"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "qx::quadx_step_kernel<MODE_STEP_DEFER, HOVER> (+ the reset-queue launch, both inside the step time)", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},

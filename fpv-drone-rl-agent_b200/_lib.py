@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
         "qx_act_dim": (i32, [vp]),
         "qx_state_ptr": (vp, [vp]),
         "qx_state_words": (i32, [vp]),
+        "qx_uses_reference_constants": (i32, [vp]),
+        "qx_config_matches_reference_constants": (i32, [C.POINTER(QxConfig)]),
         "qx_launch_count": (i64, []),
         "qx_sizeof_config": (i64, []),
         "qx_last_error": (C.c_char_p, []),
@@ -123,7 +125,7 @@ def lib() -> C.CDLL:
 
 EXPORTED = [
     "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
-    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words",
+    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words", "qx_uses_reference_constants", "qx_config_matches_reference_constants",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -117,8 +118,12 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, i
 
 constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
 
-template <int MODE, int TASK, bool CASC = false>
-__global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig c, const StepArgs a) {
+// REF: the model constants are the reference's literals (qx_ref_constants.cuh) instead of kernel parameters
+template <int MODE, int TASK, bool CASC = false, bool REF = false>
+__global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig cparam, const StepArgs a) {
+  DevConfig cref = cparam;  // scalar-replaced by the compiler: untouched fields stay parameter reads
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
   if (MODE == MODE_RESET_QUEUE) {
     // Every block reads the count before any block can zero it: the zeroing
     // block is the last one to take a ticket, after its own __syncthreads.
@@ -401,6 +406,7 @@ struct QxHandle {
   int64_t n;
   int device;
   int planes;  // float4 state planes: 11, or 17 when flight_mode != 0
+  bool ref_constants;  // the model constants equal the reference's literals bit for bit: run the specialised kernels
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
@@ -512,7 +518,10 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
     d->start_pos[a] = s.start_pos[a]; d->start_rpy[a] = s.start_rpy[a];
   }
   d->inv_mass = (float)(1.0 / s.mass); d->g = s.gravity; d->vmax = s.max_coord_vel; d->floor_z = s.floor_z;
-  for (int a = 0; a < 3; ++a) d->hI[a] = (float)(h / s.inertia[a]);
+  for (int a = 0; a < 3; ++a) {
+    d->hI[a] = (float)(h / s.inertia[a]);
+    d->gk[a] = s.gyro ? (float)(-(h / s.inertia[a]) * ((double)s.inertia[(a + 2) % 3] - (double)s.inertia[(a + 1) % 3])) : 0.f;
+  }
   d->hm = (float)(h / s.mass); d->hg = (float)(h * s.gravity); d->hh = (float)(0.5 * h); d->hh2 = (float)(0.25 * h * h);
   d->kq1 = (float)(-0.5 * h / 6.0); d->kq2 = (float)(0.5 * h / 120.0);
   d->ndrag_c = -(float)(0.5 * s.air_density * s.drag_coef_xyz * s.drag_area_xyz); d->ndrag_pqr = -s.drag_coef_pqr;
@@ -538,6 +547,8 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   return QX_OK;
 }
 
+static bool matches_ref_constants(const qx::DevConfig& d);
+
 extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uint64_t env_id0, int device, QxHandle** out) {
   if (!cfg || !out || n_envs <= 0) return fail(QX_EINVAL, "qx_create: bad arguments");
   int ndev = 0;
@@ -556,6 +567,7 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   cudaGetDevice(&prev);
   cudaSetDevice(device);
   h->planes = cfg->flight_mode != 0 ? qx::kCascadePlanes : qx::kBasePlanes;
+  h->ref_constants = !getenv("QX_FORCE_GENERIC") && matches_ref_constants(h->dev);
   cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaMalloc(&h->queue, sizeof(qx::ResetQueue) + sizeof(unsigned int) * n_envs);
@@ -619,17 +631,36 @@ extern "C" int32_t qx_obs_dim(const QxHandle* h) { return h ? h->dev.obs_dim : 0
 extern "C" int32_t qx_act_dim(const QxHandle* h) { return h ? h->dev.act_dim : 0; }
 extern "C" void* qx_state_ptr(QxHandle* h) { return h ? h->state : nullptr; }
 extern "C" int32_t qx_state_words(const QxHandle* h) { return h ? 4 * h->planes : 0; }
+static bool matches_ref_constants(const qx::DevConfig& d) {
+  qx::DevConfig lit = d;
+  qx::apply_ref_constants(lit);
+  return QX_HAVE_REF_CONSTANTS && d.task == QX_TASK_HOVER && d.flight_mode == 0 && memcmp(&lit, &d, sizeof(lit)) == 0;
+}
+extern "C" int32_t qx_uses_reference_constants(const QxHandle* h) { return h && h->ref_constants ? 1 : 0; }
+// does this config take the specialised kernels?  (no GPU needed; -1 on a bad config)
+extern "C" int32_t qx_config_matches_reference_constants(const QxConfig* cfg) {
+  qx::DevConfig d;
+  if (!cfg || derive(*cfg, 0, 0, &d) != QX_OK) return -1;
+  return matches_ref_constants(d) ? 1 : 0;
+}
+// generator / test hook (not in the public header): the kernel-side constants derive() makes of a config; needs no GPU
+extern "C" int64_t qx_debug_dev_config(const QxConfig* cfg, uint64_t seed, uint64_t env_id0, void* out, int64_t cap) {
+  qx::DevConfig d;
+  if (!cfg || derive(*cfg, seed, env_id0, &d) != QX_OK) return -1;
+  if (out && cap >= (int64_t)sizeof(d)) memcpy(out, &d, sizeof(d));
+  return (int64_t)sizeof(d);
+}
 
-template <int TASK, bool CASC>
+template <int TASK, bool CASC, bool REF>
 static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.env_count + qx::kBlock - 1) / qx::kBlock);
   switch (mode) {
-    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
-    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK, CASC><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     default: {
       const unsigned g = grid < (unsigned)qx::kResetQueueBlocks ? grid : (unsigned)qx::kResetQueueBlocks;
-      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE, TASK, CASC><<<g, qx::kBlock, 0, s>>>(h->dev, a);
+      qx::quadx_step_kernel<qx::MODE_RESET_QUEUE, TASK, CASC, REF><<<g, qx::kBlock, 0, s>>>(h->dev, a);
       break;
     }
   }
@@ -637,9 +668,10 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
 
 static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
-  if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false>(h, mode, a, s);
-  else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true>(h, mode, a, s);
-  else launch_task<QX_TASK_HOVER, false>(h, mode, a, s);
+  if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false, false>(h, mode, a, s);
+  else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true, false>(h, mode, a, s);
+  else if (h->ref_constants) launch_task<QX_TASK_HOVER, false, true>(h, mode, a, s);
+  else launch_task<QX_TASK_HOVER, false, false>(h, mode, a, s);
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;

@@ -185,6 +185,11 @@ int32_t qx_obs_dim(const QxHandle* h);
 int32_t qx_act_dim(const QxHandle* h);
 /* device pointer to the qx_state_words(h) / 4 float4 state planes (plane stride = n_envs) */
 void* qx_state_ptr(QxHandle* h);
+/* 1 when the handle runs the kernels specialised for the reference's own parameter set (the model constants of
+ * qx_default_config(QX_TASK_HOVER) compiled in as literals); any other configuration -- or QX_FORCE_GENERIC=1 in the
+ * environment at qx_create -- runs the generic kernels that read every constant from the config.  Same results. */
+int32_t qx_uses_reference_constants(const QxHandle* h);
+int32_t qx_config_matches_reference_constants(const QxConfig* cfg);
 /* number of kernels this library has launched in the calling process */
 int64_t qx_launch_count(void);
 /* sizeof(QxConfig) as compiled into the library (binding self-check) */

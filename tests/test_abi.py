@@ -72,6 +72,24 @@ def test_config_layout_and_defaults(built):
     assert list(c.zpos_pid) == f(list(p.zpos_pid)) and list(c.zvel_pid) == f(list(p.zvel_pid))
 
 
+def test_reference_constants_header_is_current(built):
+    """csrc/qx_ref_constants.cuh (tools/gen_ref_constants.py) still equals what derive() makes of the default config, so the
+    reference's own parameter set takes the specialised kernels; anything else takes the generic ones."""
+    import ctypes as C
+
+    L = built.lib()
+    c = built.default_config(built.QX_TASK_HOVER)
+    assert L.qx_config_matches_reference_constants(C.byref(c)) == 1
+    c.update(start_pos=[0, 0, 1.0], spawn_throttle=0.4952, reset_idle_steps=0, max_steps=1000, auto_reset=0, noise=0)  # run-time switches
+    assert L.qx_config_matches_reference_constants(C.byref(c)) == 1
+    for change in (dict(mass=0.11), dict(rate_kp=[0.03, 0.02, 0.04]), dict(control_hz=240.0), dict(gyro=0), dict(cam_tilt_up_deg=20.0),
+                   dict(flight_mode=3), dict(target_area=0.02)):
+        c2 = built.default_config(built.QX_TASK_HOVER)
+        c2.update(**change)
+        assert L.qx_config_matches_reference_constants(C.byref(c2)) == 0, change
+    assert L.qx_config_matches_reference_constants(C.byref(built.default_config(built.QX_TASK_YAW))) == 0
+
+
 def test_no_gpu_means_loud_failure(built):
     import torch
 

@@ -176,3 +176,37 @@ def test_chunked_host_pipeline_equals_device_path(pkg):
     for key in sa:
         assert np.array_equal(sa[key], sb[key]), key
     assert sim_h.episode_stats()[1:] == sim_d.episode_stats()[1:] == (32 * n, n)
+
+
+def test_reference_constant_kernels_equal_generic_kernels(pkg, monkeypatch):
+    """The kernels specialised for the reference's own parameter set (model constants as literals, qx_ref_constants.cuh)
+    against the generic kernels that read every constant from the config: same config, same seeds, same actions.  The
+    arithmetic is the same IEEE operations on the same values; only constant folding (x * 1, x * -1, fused constants) may
+    differ, so the bound is a few ulp of the observation scale, and the flags are identical."""
+    n, steps = 1 << 16, 96
+    cfg = pkg.default_config()  # floor start, 10 idle steps per reset, auto-reset: every kernel mode runs
+    g = torch.Generator(device="cuda").manual_seed(7)
+    acts = (torch.rand(steps, n, 4, device="cuda", generator=g) * 2 - 1) * torch.tensor([0.3, 0.3, 0.3, 1.0], device="cuda")
+    acts[..., 3] = acts[..., 3] * 0.3 + 0.1
+    out = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("QX_FORCE_GENERIC", "1")
+        sim = pkg.QuadXSim(n, cfg, seed=99)
+        assert sim.lib.qx_uses_reference_constants(sim._h) == (0 if generic else 1)
+        d = sim.device
+        obs = torch.zeros(n, 20, device=d); rew = torch.zeros(steps, n, device=d)
+        te = torch.zeros(steps, n, dtype=torch.uint8, device=d); tr = torch.zeros(steps, n, dtype=torch.uint8, device=d)
+        allobs = torch.zeros(steps, n, 20, device=d)
+        sim.reset(obs)
+        for k in range(steps):
+            sim.step(acts[k], allobs[k], rew[k], te[k], tr[k])
+        torch.cuda.synchronize()
+        out.append((allobs.clone(), rew.clone(), te.clone(), tr.clone(), sim.episode_stats()))
+        sim.close()
+    (o1, r1, te1, tr1, s1), (o2, r2, te2, tr2, s2) = out
+    assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and s1[1:] == s2[1:]
+    assert int(te1.sum()) > n  # episodes ended and restarted along the way
+    do, dr = float((o1 - o2).abs().max()), float((r1 - r2).abs().max())
+    print(f"specialised vs generic kernels: max |obs diff| {do:.3e}, max |reward diff| {dr:.3e}, bitwise equal: {torch.equal(o1, o2) and torch.equal(r1, r2)}")
+    assert do <= 1e-4 and dr <= 1e-3
