@@ -62,11 +62,11 @@ __global__ void __launch_bounds__(128) test_gemm_kernel(const __nv_bfloat16* __r
 
 
 // ---------------------------------------------------------------------------
-// K2: ActorCriticPolicy.forward.  Persistent CTAs, one per SM, 512 threads = two
+// K2: ActorCriticPolicy.forward.  Persistent CTAs, one per SM, 768 threads = three
 // independent "slots" of 256 threads; each slot walks its own sequence of
-// 128-row tiles, so while one slot waits for its tcgen05.mma chain the other
-// runs its bias + tanh epilogue (the tensor pipe and the MUFU pipe overlap
-// without any explicit software pipeline).  All weights stay resident in
+// 128-row tiles, so while one slot waits for its tcgen05.mma chain the others
+// run their bias + tanh epilogues (tensor pipe, TMEM reads and the MUFU pipe
+// overlap across slots).  All weights stay resident in
 // shared memory in the interleaved K-major layout; per tile and slot
 //   [L1p]      X[128x32]    . W1p^T          -> acc (TMEM 128 cols)
 //   [L2p]      H1p[128x128] . W2p^T          -> acc
