@@ -113,3 +113,23 @@ def test_mode0_thrust_command_is_clipped(pkg):
     assert _rel(thr, orc.st.thr, 1.0) <= 1e-3
     assert thr.max() <= 1.1 and np.allclose(thr[-1], thr[n * 2 // 3 + 1], atol=0.05)  # a3 = 3 flies like a3 = 1
     sim.close()
+
+
+def test_facade_honours_flight_mode_on_request(pkg):
+    """QuadXHoverEnv(flight_mode=...) ignores the argument like the reference (hover.py:19 vs :92) unless told otherwise;
+    with honour_flight_mode=True the drone flies PyFlyt's mode 7 (x, y, yaw, z setpoints) and goes where it is sent."""
+    kw = dict(start_pos=[0.0, 0.0, 1.0], spawn_throttle=HOVER_THR, reset_idle_steps=0, noise=0, max_steps=1000)
+    ref_like = pkg.QuadXHoverEnv(flight_mode=7, **kw)
+    assert ref_like.sim.cfg.flight_mode == 0 and len(ref_like.sim.state_fields) == 44
+    ref_like.close()
+    env = pkg.QuadXHoverEnv(flight_mode=7, honour_flight_mode=True, action_scale=[1.0, 1.0, 1.5], thrust_scale=0.5, thrust_bias=1.2, **kw)
+    assert env.sim.cfg.flight_mode == 7 and len(env.sim.state_fields) == 68
+    env.reset()
+    a = np.array([0.6, -0.4, 0.5, 0.4])  # -> x 0.6 m, y -0.4 m, yaw 0.75 rad, z 1.4 m
+    for _ in range(240):  # 12 s
+        obs, r, te, tr, info = env.step(a)
+        assert not te and not tr
+    s = env.sim.get_state()
+    assert abs(s["px"][0] - 0.6) < 0.05 and abs(s["py"][0] + 0.4) < 0.05 and abs(s["pz"][0] - 1.4) < 0.1
+    assert abs(s["prev_yaw"][0] - 0.75) < 0.03
+    env.close()
