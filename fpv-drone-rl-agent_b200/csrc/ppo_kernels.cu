@@ -202,6 +202,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   const int ecol0 = (int)(swarp >> 2) * 64;        // and its 64 columns
   const uint32_t xrow = st & 127, xh = st >> 7;    // X-tile staging: row, pair of 8-column chunks
   const int obs_dim = a.p.obs_dim, act_dim = a.p.act_dim;
+#ifdef PPO_K2_TRACE  // tuning builds only (QX_NVCC_EXTRA=-DPPO_K2_TRACE, tools/k2_phases.py): kernel entry / prologue / exit stamps of CTA 0
+#define K2_TRACE(slot_) do { if (g_phase_clk && blockIdx.x == 0 && tid == 0) g_phase_clk[slot_] = clock64(); } while (0)
+#else
+#define K2_TRACE(slot_) do { } while (0)
+#endif
+  K2_TRACE(127);
   // gather mode (time-limit bootstrap): most steps have no truncated env at all -- leave before staging 88 KB of weights
   if (a.gather_idx && (int64_t)blockIdx.x * kSlots * 128 >= (int64_t)*a.gather_count) return;
   // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barriers
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, kFwdThreads);
   stage_weight(smem + kSmW2v, (const __nv_bfloat16*)a.p.w2v, kHid, kHid, tid, kFwdThreads);
   stage_weight(smem + kSmW3, (const __nv_bfloat16*)a.p.w3, kHead, 2 * kHid, tid, kFwdThreads);
+  K2_TRACE(125);  // weights staged
   float* sB1 = reinterpret_cast<float*>(smem + kSmB1);
   float* sB2 = reinterpret_cast<float*>(smem + kSmB2);
   float* sB3 = reinterpret_cast<float*>(smem + kSmB3);
@@ -225,10 +232,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
     for (int sidx = 0; sidx < kSlots; ++sidx) mbar_init(&bars[sidx], 1);
     mbar_fence_init();
   }
+  K2_TRACE(124);  // biases, TMEM allocation, barrier init
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  K2_TRACE(123);  // CTA-wide sync passed
   uint64_t* bar = &bars[slot];
   const uint32_t tacc = tmem_slot + slot * kSlotTmem;             // MMA destination (lane field 0)
   const uint32_t tacc_row = tacc + (((swarp & 3) * 32u) << 16);   // this warp's lane quarter
@@ -342,8 +351,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   // fence.proxy.async and the barrier that precedes an MMA issue.
   if (tile0 < n_tiles) {
     float xbuf[16];
+    K2_TRACE(122);  // per-slot setup
     load_obs_chunks(a, tile0, n_rows, xrow, xh, obs_dim, xbuf);
     stage_x(tile0, xbuf);
+    K2_TRACE(121);  // first X tile loaded + staged
     load_obs_chunks(a, tile0 + tile_stride, n_rows, xrow, xh, obs_dim, xbuf);
     fence_async_smem();
     fence_before_sync();
@@ -438,6 +449,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
     fence_before_sync();
   }
   __syncthreads();
+  K2_TRACE(126);
   if (tid < 32) tmem_dealloc(tmem_slot, kTmemCols);
 }
 
