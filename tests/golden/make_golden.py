@@ -31,11 +31,11 @@ from oracle.test_policy import hover_actions  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def run_scenario(hover, name, seed, noise, n_steps, action_fn, env_id=0, second_episode=0):
+def run_scenario(hover, name, seed, noise, n_steps, action_fn, env_id=0, second_episode=0, render=False, agent_hz=40):
     p = QuadXParams()
     src = NoiseSource(seed, np.array([env_id], np.uint64), enabled=noise)
-    af.NOISE_CONTEXT.update(source=src, rng_ctr=0, params=p, idle_steps=10, ratio=6)
-    env = hover.QuadXHoverEnv()
+    af.NOISE_CONTEXT.update(source=src, rng_ctr=0, params=p, idle_steps=10, ratio=int(240 / agent_hz))
+    env = hover.QuadXHoverEnv(agent_hz=agent_hz, render=render)
     rec = {k: [] for k in ("actions", "obs", "reward", "terminated", "truncated", "state", "episode_start")}
     reset_obs = []
 
@@ -62,6 +62,8 @@ def run_scenario(hover, name, seed, noise, n_steps, action_fn, env_id=0, second_
     out["seed"] = np.int64(seed)
     out["noise"] = np.bool_(noise)
     out["env_id"] = np.int64(env_id)
+    out["render"] = np.bool_(render)
+    out["agent_hz"] = np.int64(agent_hz)
     path = os.path.join(OUT, f"hover_ref_{name}.npz")
     np.savez_compressed(path, **out)
     print(f"{name}: {len(rec['reward'])} steps, terminated at {np.argmax(out['terminated']) if out['terminated'].any() else None}, "
@@ -118,6 +120,11 @@ def main():
     run_scenario(hover, "floor", seed=7, noise=True, n_steps=40, action_fn=idle)
     # (d) full throttle: leaves the 3 m dome (hover.py:278-281)
     run_scenario(hover, "dome", seed=9, noise=False, n_steps=40, action_fn=rocket)
+    # (e) render=True switches the floor rule off (hover.py:283 `and not self.render`): the same idle drone is never terminated
+    run_scenario(hover, "render_idle", seed=7, noise=True, n_steps=40, action_fn=idle, render=True)
+    # (f) agent_hz=60 (hover.py:14,24-25): env_step_ratio = int(240 / 60) = 4 Aviary.step per agent step, agent_dt = 1/60
+    rng60 = np.random.default_rng(77)
+    run_scenario(hover, "agent_hz60", seed=21, noise=True, n_steps=60, action_fn=lambda k, state: hover_actions(state[None], tgt, rng60, 0.05)[0], agent_hz=60)
 
 
 if __name__ == "__main__":

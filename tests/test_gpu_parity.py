@@ -146,7 +146,7 @@ def test_vision_columns_match_analytic_oracle(pkg):
     assert mism / tot < 1e-3 and n_vis > 0.3 * tot
 
 
-GOLDEN = ["fly_quiet", "fly_noisy", "floor", "dome"]
+GOLDEN = ["fly_quiet", "fly_noisy", "floor", "dome", "render_idle", "agent_hz60"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -154,7 +154,9 @@ def test_golden_reference_trajectories(pkg, golden_dir, name):
     """Replay the action sequences recorded with the reference's own hover.py in
     the loop through the gymnasium-shaped facade; compare every output."""
     g = np.load(os.path.join(golden_dir, f"hover_ref_{name}.npz"))
-    env = pkg.QuadXHoverEnv(seed=int(g["seed"]), noise=int(bool(g["noise"])))
+    render = bool(g["render"]) if "render" in g.files else False  # hover.py:283: rendering switches the floor rule off
+    agent_hz = int(g["agent_hz"]) if "agent_hz" in g.files else 40  # hover.py:14,24-25
+    env = pkg.QuadXHoverEnv(agent_hz=agent_hz, render=render, seed=int(g["seed"]), noise=int(bool(g["noise"])))
     # the facade creates env id 0; golden env ids other than 0 need the raw sim
     if int(g["env_id"]) != 0:
         env.sim.close()
@@ -189,6 +191,8 @@ def test_golden_reference_trajectories(pkg, golden_dir, name):
         assert info["on_floor"] and not info["out_of_bounds"]
     if name == "dome":
         assert info["out_of_bounds"]
+    if name == "render_idle":
+        assert not info["on_floor"] and not bool(g["terminated"].any())  # 40 steps on the floor, never terminated
     env.close()
 
 

@@ -8,7 +8,7 @@ import pytest
 from oracle.hover_oracle import HoverConfig, HoverVecOracle
 from oracle.quadx_model import QuadXParams
 
-SCENARIOS = ["fly_quiet", "fly_noisy", "floor", "dome"]
+SCENARIOS = ["fly_quiet", "fly_noisy", "floor", "dome", "render_idle", "agent_hz60"]
 
 
 def _load(golden_dir, name):
@@ -19,7 +19,7 @@ def _load(golden_dir, name):
 def test_oracle_reproduces_reference_hover(golden_dir, name):
     g = _load(golden_dir, name)
     orc = HoverVecOracle(
-        1, QuadXParams(), HoverConfig(), seed=int(g["seed"]), env_id0=int(g["env_id"]),
+        1, QuadXParams(), HoverConfig(render=bool(g["render"]) if "render" in g.files else False, agent_hz=int(g["agent_hz"]) if "agent_hz" in g.files else 40), seed=int(g["seed"]), env_id0=int(g["env_id"]),
         auto_reset=False, noise=bool(g["noise"]), vision_mode="raster",
     )
     ep = -1

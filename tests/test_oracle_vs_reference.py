@@ -43,14 +43,18 @@ def test_drone_parameter_fixture_is_current(golden_dir):
     assert mg.drone_params("/root/reference") == json.load(open(os.path.join(golden_dir, "cf2x_params.json")))
 
 
-def test_golden_vectors_are_current(hover, golden_dir):
+@pytest.mark.parametrize("name", ["fly_noisy", "floor", "dome", "render_idle", "agent_hz60"])
+def test_golden_vectors_are_current(hover, golden_dir, name):
+    """Re-run the reference's hover.py on the recorded actions: the committed fixtures are what it produces today."""
     from oracle import aviary_facade as af
     from oracle.quadx_model import NoiseSource, QuadXParams
 
-    g = np.load(os.path.join(golden_dir, "hover_ref_fly_noisy.npz"))
-    src = NoiseSource(int(g["seed"]), np.array([int(g["env_id"])], np.uint64), enabled=True)
-    af.NOISE_CONTEXT.update(source=src, rng_ctr=0, params=QuadXParams(), idle_steps=10, ratio=6)
-    env = hover.QuadXHoverEnv()
+    g = np.load(os.path.join(golden_dir, f"hover_ref_{name}.npz"))
+    agent_hz = int(g["agent_hz"]) if "agent_hz" in g.files else 40
+    render = bool(g["render"]) if "render" in g.files else False
+    src = NoiseSource(int(g["seed"]), np.array([int(g["env_id"])], np.uint64), enabled=bool(g["noise"]))
+    af.NOISE_CONTEXT.update(source=src, rng_ctr=0, params=QuadXParams(), idle_steps=10, ratio=int(240 / agent_hz))
+    env = hover.QuadXHoverEnv(agent_hz=agent_hz, render=render)
     ep = -1
     for k in range(g["actions"].shape[0]):
         if g["episode_start"][k]:
