@@ -719,9 +719,21 @@ extern "C" int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_
   return launch(h, qx::MODE_RESET_QUEUE, a, (cudaStream_t)stream);
 }
 
-// two launches: the step proper, then the reset of whatever finished, in full warps
+// two launches: the step proper, then the reset of whatever finished, in full warps.  Small batches are latency-bound
+// (4 096 envs = one warp per SM sub-partition on 32 SMs), where the second launch costs more than the divergence it
+// avoids: below kInlineResetMaxEnvs the finished envs are reset inside the step launch instead.
+constexpr int64_t kInlineResetMaxEnvs = 16384;
 extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
                        float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
+  if (h && h->cfg.auto_reset && h->n <= kInlineResetMaxEnvs) {
+    if (!actions_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(QX_EINVAL, "qx_step: bad arguments");
+    if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step: obs_stride < obs_dim");
+    qx::StepArgs a{};
+    a.state = h->state; a.actions = actions_dev; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
+    a.reward = reward_dev; a.terminated = terminated_dev; a.truncated = truncated_dev; a.terminal_obs = terminal_obs_dev;
+    a.stats = h->stats; a.n = h->n; a.k = 1;
+    return launch(h, qx::MODE_STEP_INLINE, a, (cudaStream_t)stream);
+  }
   int rc = qx_step_begin(h, actions_dev, obs_dev, obs_dtype, obs_stride, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, stream);
   if (rc) return rc;
   return qx_step_end(h, obs_dev, obs_dtype, obs_stride, stream);
@@ -811,11 +823,11 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.reward = h->d_rew;
     a.terminated = h->d_flags; a.truncated = h->d_flags + n; a.terminal_obs = terminal_obs_host ? h->d_tobs : nullptr;
     a.stats = h->stats; a.queue = h->queue; a.n = n; a.k = 1; a.env_begin = b; a.env_count = cnt;
-    if (h->cfg.auto_reset) {
+    if (h->cfg.auto_reset && n > kInlineResetMaxEnvs) {
       rc = launch(h, qx::MODE_STEP_DEFER, a, h->stream);
       if (rc) return rc;
       rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);
-    } else {
+    } else {  // no auto-reset, or a small batch: one launch (see qx_step)
       rc = launch(h, qx::MODE_STEP_INLINE, a, h->stream);
     }
     if (rc) return rc;

@@ -128,8 +128,10 @@ class QuadXSim:
         check(self.lib.qx_reset(self._h, _ptr(mask), _ptr(obs), code, stride, self._stream()))
 
     def step(self, actions: torch.Tensor, obs: torch.Tensor | None, reward: torch.Tensor, terminated: torch.Tensor,
-             truncated: torch.Tensor, terminal_obs: torch.Tensor | None = None) -> None:
-        """qx_step on the current stream; all buffers are caller-owned device tensors."""
+             truncated: torch.Tensor, terminal_obs: torch.Tensor | None = None, split: bool = False) -> None:
+        """qx_step on the current stream; all buffers are caller-owned device tensors.  ``split=True`` issues the two
+        halves qx_step_begin + qx_step_end (the deferred reset-queue path the PPO rollout uses) instead of qx_step, which
+        resets finished envs inside the step launch for small batches."""
         self._check(actions, (self.n, self.act_dim), torch.float32, "actions")
         self._check(reward, (self.n,), torch.float32, "reward")
         self._check(terminated, (self.n,), torch.uint8, "terminated")
@@ -141,6 +143,11 @@ class QuadXSim:
             stride, code = obs.stride(0), self._dtype_code(obs)
         if terminal_obs is not None:
             self._check(terminal_obs, (self.n, self.obs_dim), torch.float32, "terminal_obs")
+        if split:
+            check(self.lib.qx_step_begin(self._h, _ptr(actions), _ptr(obs), code, stride, _ptr(reward), _ptr(terminated),
+                                         _ptr(truncated), _ptr(terminal_obs), self._stream()))
+            check(self.lib.qx_step_end(self._h, _ptr(obs), code, stride, self._stream()))
+            return
         check(self.lib.qx_step(self._h, _ptr(actions), _ptr(obs), code, stride, _ptr(reward), _ptr(terminated),
                                _ptr(truncated), _ptr(terminal_obs), self._stream()))
 

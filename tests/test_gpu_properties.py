@@ -210,3 +210,32 @@ def test_reference_constant_kernels_equal_generic_kernels(pkg, monkeypatch):
     do, dr = float((o1 - o2).abs().max()), float((r1 - r2).abs().max())
     print(f"specialised vs generic kernels: max |obs diff| {do:.3e}, max |reward diff| {dr:.3e}, bitwise equal: {torch.equal(o1, o2) and torch.equal(r1, r2)}")
     assert do <= 1e-4 and dr <= 1e-3
+
+
+def test_inline_reset_equals_reset_queue_path(pkg):
+    """qx_step resets finished envs inside the step launch for small batches (<= 16 384 envs) and through the deferred
+    reset queue (qx_step_begin + qx_step_end, what the PPO rollout always uses) otherwise: same flags, same episode
+    accounting, observations / rewards equal up to the rounding of two instantiations, through two mass terminations."""
+    n, steps = 4096, 70
+    cfg = pkg.default_config()  # floor start: every env is terminated by the floor rule on its 32nd step
+    a = torch.tensor([[0.0, 0.0, 0.0, -1.0]], device="cuda").repeat(n, 1)
+    outs = []
+    for split in (False, True):
+        sim = pkg.QuadXSim(n, cfg, seed=17)
+        d = sim.device
+        obs = torch.zeros(steps, n, 20, device=d); tobs = torch.zeros(steps, n, 20, device=d)
+        rew = torch.zeros(steps, n, device=d)
+        te = torch.zeros(steps, n, dtype=torch.uint8, device=d); tr = torch.zeros(steps, n, dtype=torch.uint8, device=d)
+        o0 = torch.zeros(n, 20, device=d)
+        sim.reset(o0)
+        for k in range(steps):
+            sim.step(a, obs[k], rew[k], te[k], tr[k], tobs[k], split=split)
+        torch.cuda.synchronize()
+        outs.append((obs, rew, te, tr, tobs, sim.episode_stats()))
+        sim.close()
+    (o1, r1, te1, tr1, t1, s1), (o2, r2, te2, tr2, t2, s2) = outs
+    assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and int(te1.sum()) == 2 * n
+    assert s1[1:] == s2[1:] and abs(s1[0] - s2[0]) <= 1e-4 * abs(s2[0])
+    assert float((o1 - o2).abs().max()) <= 1e-4 and float((r1 - r2).abs().max()) <= 1e-3
+    done = te1.bool()
+    assert float((t1[done] - t2[done]).abs().max()) <= 1e-4  # terminal observations of the finished envs
