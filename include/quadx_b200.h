@@ -146,7 +146,8 @@ int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dt
 
 /* qx_step in two halves, for callers that need the finished envs between the step and their reset (the PPO
  * rollout bootstraps truncated episodes from terminal_obs there): qx_step_begin runs the step and queues the
- * finished envs, qx_step_end re-creates them and writes their first observation.  qx_step == begin + end.
+ * finished envs, qx_step_end re-creates them and writes their first observation.  qx_step == begin + end in effect;
+ * for batches of <= 16 384 envs (latency-bound) qx_step does both in one launch instead of two.
  * qx_done_queue gives the device addresses of the queue (count, env indices) valid between the two calls. */
 int qx_step_begin(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
                   float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream);
