@@ -299,12 +299,20 @@ def main_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kern_ms = statistics.mean(per)
         achieved = E * ALG_BYTES_PER_ENV_STEP / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, compute_side = None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if tj.get("envs") == E:
                 traffic = tj.get("dram_bytes_per_launch")
+                if "thread_instructions_per_env_step" in tj:
+                    # the kernel sits on the compute side of the ridge: at 4 warp-instructions per clock per SM the instruction
+                    # count alone caps it below the HBM roofline (numbers from the committed ncu capture, not measured live)
+                    ipe = tj["thread_instructions_per_env_step"]
+                    cap = 148 * 4 * 32 * 1.965e9 / ipe
+                    compute_side = {"thread_instructions_per_env_step": ipe, "issue_active_pct_ncu": tj.get("issue_active_pct"),
+                                    "issue_bound_env_steps_per_s": cap, "issue_bound_as_frac_of_hbm_roofline": cap * ALG_BYTES_PER_ENV_STEP / (peak * 1e9),
+                                    "source": tj.get("source")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -315,7 +323,7 @@ def main_ours(args):
             "clocks": clocks,
             "kernels": ("reference-constant instantiation (model constants of the reference's own parameter set as literals)"
                         if sim.lib.qx_uses_reference_constants(sim._h) else "generic (every constant read from the config)"),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "compute_side": compute_side,
                          "kernel": "qx::quadx_step_kernel<MODE_STEP_DEFER, HOVER> (+ the reset-queue launch, both inside the step time)", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
         }

@@ -55,6 +55,11 @@ for r in sorted(rows[2:], key=lambda r: -_dur(r)):  # the longest instance of ev
         wr = tobytes(vals["dram__bytes_write.sum"], units[hdr.index("dram__bytes_write.sum")])
         traffic = {"kernel": name, "envs": envs, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                    "per_env_step": (rd + wr) / envs, "source": f"ncu --set full, profiles/{prefix}_{tag}.md"}
+        if "smsp__inst_executed.sum" in vals:  # the compute side of the ridge: what actually bounds the hover step
+            traffic["warp_instructions_per_launch"] = float(vals["smsp__inst_executed.sum"])
+            traffic["thread_instructions_per_env_step"] = float(vals["smsp__inst_executed.sum"]) * 32 / envs
+            traffic["issue_active_pct"] = float(vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan"))
+            traffic["kernel_us_under_ncu"] = float(vals["gpu__time_duration.sum"])
 if os.path.exists(launches):
     out.append("\n## launch list (gpu__time_duration, cold-cache, serialised)\n")
     tot = {}
