@@ -104,6 +104,42 @@ def export_vecnormalize(obs_stats: "RunningStats", ret_stats: "RunningStats", cf
             "gamma": cfg.gamma, "epsilon": obs_stats.eps, "norm_obs": cfg.norm_obs, "norm_reward": cfg.norm_reward}
 
 
+def export_sb3_zip(model: "ActorCritic", path: str, vecnormalize: dict | None = None, sb3_version: str = "2.7.0") -> None:
+    """Write the policy the way stable-baselines3's `save_to_zip_file` lays out a model archive -- `policy.pth` (the
+    `ActorCriticPolicy` state dict under SB3's parameter names) and `_stable_baselines3_version` (the version the
+    reference pins, uv.lock:990) -- so that the reference's side can do [RECALL]
+
+        model = PPO("MlpPolicy", env, policy_kwargs=dict(net_arch=[128, 128]))     # train_hover.py:47-58 with PPO
+        model.set_parameters("hover_b200.zip", exact_match=False)                   # policy weights; optimiser state is not exported
+
+    and play it back like test_hover.py:8-21.  The archive has no `data` entry (SB3 pickles Python classes of gymnasium /
+    SB3 in there, neither of which exists here), so `PPO.load()` is not the entry point.  `vecnormalize`
+    (export_vecnormalize) is added as `vecnormalize.npz` -- SB3's own `VecNormalize.load` needs a pickle of its class; the
+    arrays are what to assign to `obs_rms` / `ret_rms`."""
+    import io
+    import zipfile
+
+    import numpy as np
+
+    with zipfile.ZipFile(path, "w") as z:
+        buf = io.BytesIO()
+        torch.save(export_sb3_state_dict(model), buf)
+        z.writestr("policy.pth", buf.getvalue())
+        z.writestr("_stable_baselines3_version", sb3_version)
+        z.writestr("system_info.txt", "exported by fpv_drone_rl_agent_b200 (B200 on-device PPO); weights only\n")
+        if vecnormalize is not None:
+            buf = io.BytesIO()
+            flat = {}
+            for k, v in vecnormalize.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        flat[f"{k}.{kk}"] = np.asarray(vv)
+                else:
+                    flat[k] = np.asarray(v)
+            np.savez(buf, **flat)
+            z.writestr("vecnormalize.npz", buf.getvalue())
+
+
 class PackedPolicy:
     """bf16 copy of an ``ActorCritic`` in the layout of ``struct PpoPolicy``."""
 
@@ -480,6 +516,10 @@ class PPOTrainer:
                     "ret_stats": self.rollout.ret_stats.state_dict(), "num_timesteps": self.num_timesteps, "cfg": self.cfg.__dict__,
                     "sb3_policy_state_dict": export_sb3_state_dict(self.model),
                     "sb3_vecnormalize": export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg)}, path)
+
+    def save_sb3(self, path: str) -> None:
+        """The policy as an SB3-style archive (policy.pth + version + VecNormalize statistics), see export_sb3_zip."""
+        export_sb3_zip(self.model, path, export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg))
 
     def load(self, path: str) -> None:
         sd = torch.load(path, map_location=self.device, weights_only=False)

@@ -111,3 +111,32 @@ def test_sb3_compatible_export_roundtrip():
     rs, rr = ppo.RunningStats(20, "cpu"), ppo.RunningStats(1, "cpu")
     vn = ppo.export_vecnormalize(rs, rr, ppo.PPOConfig())
     assert vn["obs_rms"]["mean"].shape == (20,) and vn["obs_rms"]["count"] == 1e-4 and vn["clip_obs"] == 10.0 and vn["gamma"] == 0.99
+
+
+def test_sb3_style_archive(tmp_path):
+    """export_sb3_zip lays the policy out like SB3's save_to_zip_file (policy.pth + version file), plus the VecNormalize
+    statistics as arrays; what comes back out of the archive is the same network."""
+    import io
+    import zipfile
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    from fpv_drone_rl_agent_b200 import ppo
+
+    torch.manual_seed(5)
+    m = ppo.ActorCritic(log_std_init=-1.0)
+    rs, rr = ppo.RunningStats(20, "cpu"), ppo.RunningStats(1, "cpu")
+    path = str(tmp_path / "hover_b200.zip")
+    ppo.export_sb3_zip(m, path, ppo.export_vecnormalize(rs, rr, ppo.PPOConfig()))
+    with zipfile.ZipFile(path) as z:
+        assert {"policy.pth", "_stable_baselines3_version", "vecnormalize.npz"} <= set(z.namelist())
+        assert z.read("_stable_baselines3_version").decode() == "2.7.0"  # the reference's pin, uv.lock
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), weights_only=True)
+        vn = np.load(io.BytesIO(z.read("vecnormalize.npz")))
+    assert sum(v.numel() for v in sd.values()) == 39049 and float(sd["log_std"][0]) == -1.0
+    m2 = ppo.ActorCritic()
+    ppo.import_sb3_state_dict(m2, sd)
+    x = torch.randn(7, 20)
+    assert torch.equal(m(x)[0], m2(x)[0]) and torch.equal(m(x)[1], m2(x)[1])
+    assert vn["obs_rms.mean"].shape == (20,) and vn["ret_rms.var"].shape == (1,) and float(vn["clip_obs"]) == 10.0

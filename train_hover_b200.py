@@ -96,6 +96,7 @@ def main():
             break
     if rank == 0:
         trainer.save("hover.pt")  # train_hover.py:62-63
+        trainer.save_sb3("hover_sb3.zip")  # policy.pth under SB3's parameter names + VecNormalize statistics (ppo.export_sb3_zip)
         if args.json:
             json.dump(log, open(args.json, "w"))
         print("Training complete.")
