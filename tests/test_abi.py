@@ -104,3 +104,38 @@ def test_no_gpu_means_loud_failure(built):
     cfg = built.default_config()
     rc = built.lib().qx_create(ctypes.byref(cfg), 4, 0, 0, 0, ctypes.byref(h))
     assert rc < 0 and built.lib().qx_last_error()
+
+
+def test_argument_validation_needs_no_gpu(built):
+    """Error behaviour of the boundary: bad arguments come back as negative QX_E* codes with
+    qx_last_error() set, never as exceptions or crashes -- and are rejected before anything touches CUDA."""
+    import ctypes as C
+
+    L = built.lib()
+    L.qx_last_error.restype = C.c_char_p
+    cfg = built.default_config(built.QX_TASK_HOVER)
+    h = C.c_void_p()
+    QX_EINVAL = -1
+    # empty / negative batches, missing out-parameter, missing config
+    for n in (0, -5):
+        assert L.qx_create(C.byref(cfg), n, C.c_uint64(0), C.c_uint64(0), 0, C.byref(h)) == QX_EINVAL and not h.value
+    assert b"bad arguments" in L.qx_last_error()
+    assert L.qx_create(None, 4, C.c_uint64(0), C.c_uint64(0), 0, C.byref(h)) == QX_EINVAL
+    assert L.qx_create(C.byref(cfg), 4, C.c_uint64(0), C.c_uint64(0), 0, None) == QX_EINVAL
+    assert L.qx_default_config(7, C.byref(cfg)) == QX_EINVAL and L.qx_default_config(0, None) == QX_EINVAL
+    # null handles
+    assert L.qx_reset(None, None, None, 0, 0, None) == QX_EINVAL
+    assert L.qx_step(None, None, None, 0, 0, None, None, None, None, None) == QX_EINVAL
+    assert L.qx_step_k(None, 1, None, None, None, None, None, None) == QX_EINVAL
+    assert L.qx_step_host(None, None, None, None, None, None, None) == QX_EINVAL
+    assert L.qx_get_state(None, None) == QX_EINVAL and L.qx_set_state(None, None) == QX_EINVAL
+    assert L.qx_nonfinite_count(None, None) == QX_EINVAL and L.qx_done_queue(None, None, None) == QX_EINVAL
+    assert L.qx_destroy(None) == 0 and L.qx_num_envs(None) == 0 and L.qx_obs_dim(None) == 0 and L.qx_state_words(None) == 0
+    assert L.qx_uses_reference_constants(None) == 0 and L.qx_config_matches_reference_constants(None) == -1
+    # rollout kernels: null buffers, empty batches, too many columns
+    assert L.ppo_gae(None, None, None, None, 8, 16, 0.99, 0.95, None, None, None) == QX_EINVAL
+    assert L.ppo_running_stats_update(None, 20, 16, 20, None, 1e-8, None, None, None, None) == QX_EINVAL
+    assert L.ppo_reward_normalize(None, None, None, None, 16, 0.99, 10.0, 1e-8, None, None, None, None, None) == QX_EINVAL
+    assert L.ppo_policy_forward(None, None, 20, 16, None, None, 10.0, 0, 0, 0, None, 0, None, None, None, None, None, None) == QX_EINVAL
+    assert b"ppo_policy_forward" in L.qx_last_error()
+    assert L.ppo_running_stats_scratch_bytes(20) >= 148 * 64 * 8
