@@ -123,6 +123,10 @@ def main():
     # (e) render=True switches the floor rule off (hover.py:283 `and not self.render`): the same idle drone is never terminated
     run_scenario(hover, "render_idle", seed=7, noise=True, n_steps=40, action_fn=idle, render=True)
     # (f) agent_hz=60 (hover.py:14,24-25): env_step_ratio = int(240 / 60) = 4 Aviary.step per agent step, agent_dt = 1/60
+    # (g) actions outside the Box(-1, 1): hover.py neither checks nor clips them (it relies on SB3 doing so, hover.py:59-61,
+    #     334-341) -- the raw values reach the setpoint and the last four observation columns (oracle-only fixture)
+    rngw = np.random.default_rng(5)
+    run_scenario(hover, "wild_actions", seed=3, noise=True, n_steps=24, action_fn=lambda k, state: rngw.uniform(-2.5, 2.5, 4))
     rng60 = np.random.default_rng(77)
     run_scenario(hover, "agent_hz60", seed=21, noise=True, n_steps=60, action_fn=lambda k, state: hover_actions(state[None], tgt, rng60, 0.05)[0], agent_hz=60)
 

@@ -8,7 +8,7 @@ import pytest
 from oracle.hover_oracle import HoverConfig, HoverVecOracle
 from oracle.quadx_model import QuadXParams
 
-SCENARIOS = ["fly_quiet", "fly_noisy", "floor", "dome", "render_idle", "agent_hz60"]
+SCENARIOS = ["fly_quiet", "fly_noisy", "floor", "dome", "render_idle", "agent_hz60", "wild_actions"]
 
 
 def _load(golden_dir, name):

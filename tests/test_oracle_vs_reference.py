@@ -43,7 +43,7 @@ def test_drone_parameter_fixture_is_current(golden_dir):
     assert mg.drone_params("/root/reference") == json.load(open(os.path.join(golden_dir, "cf2x_params.json")))
 
 
-@pytest.mark.parametrize("name", ["fly_noisy", "floor", "dome", "render_idle", "agent_hz60"])
+@pytest.mark.parametrize("name", ["fly_noisy", "floor", "dome", "render_idle", "agent_hz60", "wild_actions"])
 def test_golden_vectors_are_current(hover, golden_dir, name):
     """Re-run the reference's hover.py on the recorded actions: the committed fixtures are what it produces today."""
     from oracle import aviary_facade as af
