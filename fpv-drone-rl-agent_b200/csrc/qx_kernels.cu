@@ -120,7 +120,7 @@ constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-drai
 
 // REF: the model constants are the reference's literals (qx_ref_constants.cuh) instead of kernel parameters
 template <int MODE, int TASK, bool CASC = false, bool REF = false>
-__global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig cparam, const StepArgs a) {
+__global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig cparam, const __grid_constant__ StepArgs a) {
   DevConfig cref = cparam;  // scalar-replaced by the compiler: untouched fields stay parameter reads
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
@@ -154,9 +154,157 @@ __device__ __forceinline__ void respawn_cascade(Env& e, const DevConfig& c, floa
   if (c.flight_mode == 7) { sp[0] = e.spx; sp[1] = e.spy; sp[2] = seul[2]; sp[3] = e.spz; }
 }
 
+template <int TASK> struct ObsDim { static constexpr int value = TASK == QX_TASK_HOVER ? QX_OBS_DIM_HOVER : QX_OBS_DIM_YAW; };
+struct ObsAux { float er, ep, ey, cx, cy, area, ratio; bool vis; };
+
+// ---- compute_attitude / compute_state, hover.py:224-272 (phase 0: after an agent step, 1: first observation of an episode)
+template <int TASK>
+__device__ __forceinline__ void build_obs(Env& e, const DevConfig& c, const float act[4], const int phase, const bool live,
+                                          float (&obs)[ObsDim<TASK>::value], ObsAux& x) {
+  float er, ep, ey;
+  if (phase == 0 && !live) {
+    er = e.peul[0]; ep = e.peul[1]; ey = e.peul[2];  // frozen after the episode ended
+  } else {
+    quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, er, ep, ey);
+  }
+  if (phase == 1) { e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey; }  // hover.py:112
+  const float two_pi = 6.28318530718f, pi = 3.14159265359f;
+  float d0 = er - e.peul[0] + pi, d1 = ep - e.peul[1] + pi, d2 = ey - e.peul[2] + pi;
+  d0 = d0 - two_pi * floorf(d0 * (1.f / two_pi)) - pi;  // hover.py:229 (python floor-mod)
+  d1 = d1 - two_pi * floorf(d1 * (1.f / two_pi)) - pi;
+  d2 = d2 - two_pi * floorf(d2 * (1.f / two_pi)) - pi;
+  bool vis;
+  float cx, cy, area = 0.f, ratio = 0.f;
+  if (TASK == QX_TASK_HOVER) {
+    vision(e, c, vis, cx, cy, area, ratio);
+    obs[0] = d0 * c.inv_agent_dt; obs[1] = d1 * c.inv_agent_dt; obs[2] = d2 * c.inv_agent_dt;
+    euler_to_quat(er, ep, ey, obs[3], obs[4], obs[5], obs[6]);  // hover.py:233
+    obs[7] = cx; obs[8] = cy; obs[9] = e.pcx; obs[10] = e.pcy;
+    obs[11] = area; obs[12] = e.parea; obs[13] = vis ? 1.f : 0.f; obs[14] = ratio; obs[15] = e.pratio;
+    obs[16] = act[0]; obs[17] = act[1]; obs[18] = act[2]; obs[19] = act[3];
+    e.pcx = cx; e.pcy = cy; e.parea = area; e.pratio = ratio;  // hover.py:270-272
+  } else {
+    // yaw.py:57-74: [euler / pi (3) | sphere centre (2) | angular velocity (3) | last 4 yaw actions (4)].  The
+    // reference's sphere detector and calculate_angular_velocity are missing; declared stand-ins: the analytic
+    // projection of the sphere centre, and the wrapped Euler finite difference of hover.py:228-230 scaled by the
+    // 30 rad/s command range into the Box(-1, 1) of yaw.py:41-45.
+    vision_point(e, c, vis, cx, cy);
+    const float k = c.inv_agent_dt * (1.f / 30.f);
+    obs[0] = er * (1.f / pi); obs[1] = ep * (1.f / pi); obs[2] = ey * (1.f / pi);
+    obs[3] = cx; obs[4] = cy;
+    obs[5] = clampf(d0 * k, -1.f, 1.f); obs[6] = clampf(d1 * k, -1.f, 1.f); obs[7] = clampf(d2 * k, -1.f, 1.f);
+    obs[8] = e.pa[0]; obs[9] = e.pa[1]; obs[10] = e.pa[2]; obs[11] = e.pa[3];
+    e.pcx = cx; e.pcy = cy;
+  }
+  x.er = er; x.ep = ep; x.ey = ey; x.cx = cx; x.cy = cy; x.area = area; x.ratio = ratio; x.vis = vis;
+}
+
+// ---- compute_term_trunc_reward (hover.py:274-332) / yaw.py:138-149 + the end-of-step bookkeeping (hover.py:354-357).
+// Writes reward and flags of this step; returns true when the episode ended and the env must be re-created.
+template <int TASK, bool CASC>
+__device__ __forceinline__ bool reward_and_flags(Env& e, const DevConfig& c, const StepArgs& a, const int64_t row, const float act[4],
+                                                 const bool live, float (&obs)[ObsDim<TASK>::value], const ObsAux& x) {
+  constexpr int OBS_DIM = ObsDim<TASK>::value;
+  if (TASK == QX_TASK_YAW) {
+    // calculate_reward is missing from the reference; declared stand-in:
+    // keep the sphere horizontally centred, 1 - |cx| when seen else -1, minus 0.05 |a_t - a_(t-1)|.
+    uint32_t fl = e.flags;
+    if (e.step_count >= c.max_steps) fl |= F_TRUNC;  // yaw.py:138-139
+    if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB | F_TERM;  // yaw.py:141-143
+    const float reward = (x.vis ? 1.f - fabsf(x.cx) : -1.f) - 0.05f * fabsf(e.pa[3] - e.pa[2]);
+    e.flags = fl;
+    e.peul[0] = x.er; e.peul[1] = x.ep; e.peul[2] = x.ey;
+    e.step_count += 1;  // yaw.py:145
+    e.rng_ctr += 1u;
+    e.ep_ret += reward;
+    a.reward[row] = reward;
+    a.terminated[row] = (fl & F_TERM) ? 1 : 0;
+    a.truncated[row] = (fl & F_TRUNC) ? 1 : 0;
+    return c.auto_reset && (fl & (F_TERM | F_TRUNC));
+  }
+  float reward = -0.1f;  // hover.py:343
+  uint32_t fl = e.flags;
+  if (e.step_count > c.max_steps) fl |= F_TRUNC;  // hover.py:275-276
+  if (live) {
+    fl &= ~(F_LOWZ);
+    if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB;
+    if (e.spz < c.floor_thr) fl |= F_LOWZ;
+  }
+  bool bad = false;
+  // failure containment (no counterpart in the reference): a state that is no longer finite ends the episode like
+  // an out-of-bounds flight, is counted, and the env is re-created by the auto-reset -- it cannot poison the batch
+  if (live && !(fabsf(e.px) + fabsf(e.py) + fabsf(e.pz) + fabsf(e.vx) + fabsf(e.vy) + fabsf(e.vz) + fabsf(e.wx) + fabsf(e.wy) + fabsf(e.wz) +
+                fabsf(e.qw) < 3.0e38f)) {
+    fl |= F_OOB;
+    bad = true;
+    atomicAdd(&a.stats->n_nonfinite, 1ull);
+    e.px = e.py = 0.f; e.pz = c.floor_z; e.vx = e.vy = e.vz = 0.f; e.wx = e.wy = e.wz = 0.f; e.qx = e.qy = e.qz = 0.f; e.qw = 1.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) e.thr[m] = 0.f;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) { e.pi[ax] = e.pe[ax] = e.swb[ax] = e.svb[ax] = 0.f; }
+    if (CASC) {
+#pragma unroll
+      for (int k = 0; k < 18; ++k) e.cp[k] = 0.f;
+      e.spx = e.spy = 0.f; e.spz = c.floor_z;
+    }
+  }
+  if (fl & F_OOB) { reward = -100.f; fl |= F_TERM; }  // hover.py:278-281
+  if (e.step_count > c.floor_grace && !c.render && (fl & F_LOWZ)) {  // hover.py:283-290
+    reward = -100.f; fl |= F_TERM | F_ONFLOOR;
+  }
+  const float target_reward =
+      x.vis ? -(fsqrt(x.cx * x.cx + x.cy * x.cy) + fabsf(x.area - c.target_area) + fabsf(x.ratio - c.target_ratio)) : -2.0f;
+  reward -= 0.01f * e.swb[2] * e.swb[2];                        // hover.py:322-324
+  reward += target_reward - fsqrt(x.er * x.er + x.ep * x.ep);  // hover.py:326-327
+  const float a0 = act[0] - e.pa[0], a1 = act[1] - e.pa[1], a2 = act[2] - e.pa[2], a3 = act[3] - e.pa[3];
+  reward -= 0.2f * fsqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
+  reward += 1.0f;                                               // hover.py:332
+  if (bad) {  // nothing derived from the broken state may leave the kernel
+    reward = -100.f;
+#pragma unroll
+    for (int j = 0; j < OBS_DIM; ++j) obs[j] = 0.f;
+  }
+  e.flags = fl;
+  e.peul[0] = x.er; e.peul[1] = x.ep; e.peul[2] = x.ey;  // hover.py:354
+  e.step_count += 1;                                     // hover.py:356
+  e.pa[0] = act[0]; e.pa[1] = act[1]; e.pa[2] = act[2]; e.pa[3] = act[3];  // hover.py:357
+  e.rng_ctr += 1u;
+  e.ep_ret += reward;
+  const bool term = fl & F_TERM, trunc = fl & F_TRUNC;
+  a.reward[row] = reward;
+  a.terminated[row] = term ? 1 : 0;
+  a.truncated[row] = trunc ? 1 : 0;
+  return c.auto_reset && (term || trunc);
+}
+
+// ---- SB3 VecEnv auto-reset + Monitor episode statistics.  The lanes of the warp that finished together aggregate: one
+// atomic per counter per warp (a mass termination -- e.g. every env hitting the floor rule on its 32nd step -- would
+// otherwise serialise ~4 atomics per env on four L2 addresses).  DEFER: the env is handed to the reset kernel, which
+// writes the next observation.
+template <bool DEFER, int OBS_DIM>
+__device__ __forceinline__ void episode_end(const Env& e, const StepArgs& a, const int64_t i, const float (&obs)[OBS_DIM]) {
+  namespace cg = cooperative_groups;
+  const auto g = cg::coalesced_threads();
+  const double sr = cg::reduce(g, (double)e.ep_ret, cg::plus<double>());
+  const unsigned long long sl = cg::reduce(g, (unsigned long long)e.step_count, cg::plus<unsigned long long>());
+  unsigned int base = 0;
+  if (g.thread_rank() == 0) {
+    atomicAdd(&a.stats->sum_ret, sr);
+    atomicAdd(&a.stats->sum_len, sl);
+    atomicAdd(&a.stats->n_done, (unsigned long long)g.size());
+    if (DEFER) base = atomicAdd(&a.queue->count, (unsigned int)g.size());
+  }
+  if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, OBS_DIM, false);
+  if (DEFER) {
+    base = g.shfl(base, 0);
+    a.queue->idx[base + g.thread_rank()] = (unsigned int)i;
+  }
+}
+
 template <int MODE, int TASK, bool CASC>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
-  constexpr int OBS_DIM = TASK == QX_TASK_HOVER ? QX_OBS_DIM_HOVER : QX_OBS_DIM_YAW;
+  constexpr int OBS_DIM = ObsDim<TASK>::value;
   constexpr bool RESET_ONLY = MODE == MODE_RESET_MASK || MODE == MODE_RESET_QUEUE;
   Env e;
   load_env(e, a.state, a.n, i);
@@ -216,16 +364,16 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
 #pragma unroll kPairUnroll
         for (int j = 0; j < nsub; j += 2) {
           if (CASC) control_update_cascade(e, c, sp, seul, pwm);
-          else control_update(e, c, sp, pwm);
+          else control_update<float>(e, c, sp, pwm);
           float nz[4] = {0.f, 0.f, 0.f, 0.f};
           uint4 bits = make_uint4(0u, 0u, 0u, 0u);
           if (c.noise) {
-            bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
-            normal4_scaled(bits.x, bits.y, c.noise_k, nz);
+            bits = env_philox(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
+            normal4_scaled<float>(bits.x, bits.y, c.noise_k, nz);
           }
-          physics_substep(e, c, pwm, nz, false);
-          if (c.noise) normal4_scaled(bits.z, bits.w, c.noise_k, nz);
-          physics_substep(e, c, pwm, nz, CASC || j + 2 == nsub);  // the outer loops read the snapshot pose at every control update
+          physics_substep<float>(e, c, pwm, nz, false);
+          if (c.noise) normal4_scaled<float>(bits.z, bits.w, c.noise_k, nz);
+          physics_substep<float>(e, c, pwm, nz, CASC || j + 2 == nsub);  // the outer loops read the snapshot pose at every control update
           if (CASC && c.need_euler) quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, seul[0], seul[1], seul[2]);
         }
       } else {
@@ -236,152 +384,24 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
               if (j > 0 && c.need_euler) quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, seul[0], seul[1], seul[2]);
               control_update_cascade(e, c, sp, seul, pwm);
             } else {
-              control_update(e, c, sp, pwm);
+              control_update<float>(e, c, sp, pwm);
             }
           }
           if (++cc == c.ctrl_every) cc = 0;
           float nz[4] = {0.f, 0.f, 0.f, 0.f};
-          if (c.noise) {  // one Philox4x32-10 call feeds two sub-steps
-            if ((j & 1) == 0) bits = philox4x32_10(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
-            normal4_scaled((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, c.noise_k, nz);
+          if (c.noise) {  // one Philox call feeds two sub-steps
+            if ((j & 1) == 0) bits = env_philox(make_uint4((uint32_t)j >> 1, stream, e.rng_ctr, 0u), k0, k1);
+            normal4_scaled<float>((j & 1) ? bits.z : bits.x, (j & 1) ? bits.w : bits.y, c.noise_k, nz);
           }
-          physics_substep(e, c, pwm, nz, CASC || j + 1 == nsub);
+          physics_substep<float>(e, c, pwm, nz, CASC || j + 1 == nsub);
         }
       }
-      // ---- compute_attitude / compute_state, hover.py:224-272
-      float er, ep, ey;
-      if (phase == 0 && !live) {
-        er = e.peul[0]; ep = e.peul[1]; ey = e.peul[2];  // frozen after the episode ended
-      } else {
-        quat_to_euler(e.sqx, e.sqy, e.sqz, e.sqw, er, ep, ey);
-      }
-      if (phase == 1) { e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey; }  // hover.py:112
-      const float two_pi = 6.28318530718f, pi = 3.14159265359f;
-      float d0 = er - e.peul[0] + pi, d1 = ep - e.peul[1] + pi, d2 = ey - e.peul[2] + pi;
-      d0 = d0 - two_pi * floorf(d0 * (1.f / two_pi)) - pi;  // hover.py:229 (python floor-mod)
-      d1 = d1 - two_pi * floorf(d1 * (1.f / two_pi)) - pi;
-      d2 = d2 - two_pi * floorf(d2 * (1.f / two_pi)) - pi;
-      bool vis;
-      float cx, cy, area = 0.f, ratio = 0.f;
-      if (TASK == QX_TASK_HOVER) {
-        vision(e, c, vis, cx, cy, area, ratio);
-        obs[0] = d0 * c.inv_agent_dt; obs[1] = d1 * c.inv_agent_dt; obs[2] = d2 * c.inv_agent_dt;
-        euler_to_quat(er, ep, ey, obs[3], obs[4], obs[5], obs[6]);  // hover.py:233
-        obs[7] = cx; obs[8] = cy; obs[9] = e.pcx; obs[10] = e.pcy;
-        obs[11] = area; obs[12] = e.parea; obs[13] = vis ? 1.f : 0.f; obs[14] = ratio; obs[15] = e.pratio;
-        obs[16] = act[0]; obs[17] = act[1]; obs[18] = act[2]; obs[19] = act[3];
-        e.pcx = cx; e.pcy = cy; e.parea = area; e.pratio = ratio;  // hover.py:270-272
-      } else {
-        // yaw.py:57-74: [euler / pi (3) | sphere centre (2) | angular velocity (3) | last 4 yaw actions (4)].  The
-        // reference's sphere detector and calculate_angular_velocity are missing; declared stand-ins: the analytic
-        // projection of the sphere centre, and the wrapped Euler finite difference of hover.py:228-230 scaled by the
-        // 30 rad/s command range into the Box(-1, 1) of yaw.py:41-45.
-        vision_point(e, c, vis, cx, cy);
-        const float k = c.inv_agent_dt * (1.f / 30.f);
-        obs[0] = er * (1.f / pi); obs[1] = ep * (1.f / pi); obs[2] = ey * (1.f / pi);
-        obs[3] = cx; obs[4] = cy;
-        obs[5] = clampf(d0 * k, -1.f, 1.f); obs[6] = clampf(d1 * k, -1.f, 1.f); obs[7] = clampf(d2 * k, -1.f, 1.f);
-        obs[8] = e.pa[0]; obs[9] = e.pa[1]; obs[10] = e.pa[2]; obs[11] = e.pa[3];
-        e.pcx = cx; e.pcy = cy;
-      }
+      ObsAux x;
+      build_obs<TASK>(e, c, act, phase, live, obs, x);
       if (phase == 1) break;
-
-      if (TASK == QX_TASK_YAW) {
-        // ---- yaw.py:138-149.  calculate_reward is missing from the reference; declared stand-in:
-        // keep the sphere horizontally centred, 1 - |cx| when seen else -1, minus 0.05 |a_t - a_(t-1)|.
-        uint32_t fl = e.flags;
-        if (e.step_count >= c.max_steps) fl |= F_TRUNC;  // yaw.py:138-139
-        if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB | F_TERM;  // yaw.py:141-143
-        const float reward = (vis ? 1.f - fabsf(cx) : -1.f) - 0.05f * fabsf(e.pa[3] - e.pa[2]);
-        e.flags = fl;
-        e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;
-        e.step_count += 1;  // yaw.py:145
-        e.rng_ctr += 1u;
-        e.ep_ret += reward;
-        a.reward[row] = reward;
-        a.terminated[row] = (fl & F_TERM) ? 1 : 0;
-        a.truncated[row] = (fl & F_TRUNC) ? 1 : 0;
-        if (!(c.auto_reset && (fl & (F_TERM | F_TRUNC)))) break;
-      } else {
-      // ---- compute_term_trunc_reward, hover.py:274-332
-      float reward = -0.1f;  // hover.py:343
-      uint32_t fl = e.flags;
-      if (e.step_count > c.max_steps) fl |= F_TRUNC;  // hover.py:275-276
-      if (live) {
-        fl &= ~(F_LOWZ);
-        if (e.spx * e.spx + e.spy * e.spy + e.spz * e.spz > c.dome2) fl |= F_OOB;
-        if (e.spz < c.floor_thr) fl |= F_LOWZ;
-      }
-      bool bad = false;
-      // failure containment (no counterpart in the reference): a state that is no longer finite ends the episode like
-      // an out-of-bounds flight, is counted, and the env is re-created by the auto-reset -- it cannot poison the batch
-      if (live && !(fabsf(e.px) + fabsf(e.py) + fabsf(e.pz) + fabsf(e.vx) + fabsf(e.vy) + fabsf(e.vz) + fabsf(e.wx) + fabsf(e.wy) + fabsf(e.wz) +
-                    fabsf(e.qw) < 3.0e38f)) {
-        fl |= F_OOB;
-        bad = true;
-        atomicAdd(&a.stats->n_nonfinite, 1ull);
-        e.px = e.py = 0.f; e.pz = c.floor_z; e.vx = e.vy = e.vz = 0.f; e.wx = e.wy = e.wz = 0.f; e.qx = e.qy = e.qz = 0.f; e.qw = 1.f;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) e.thr[m] = 0.f;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) { e.pi[ax] = e.pe[ax] = e.swb[ax] = e.svb[ax] = 0.f; }
-        if (CASC) {
-#pragma unroll
-          for (int k = 0; k < 18; ++k) e.cp[k] = 0.f;
-          e.spx = e.spy = 0.f; e.spz = c.floor_z;
-        }
-      }
-      if (fl & F_OOB) { reward = -100.f; fl |= F_TERM; }  // hover.py:278-281
-      if (e.step_count > c.floor_grace && !c.render && (fl & F_LOWZ)) {  // hover.py:283-290
-        reward = -100.f; fl |= F_TERM | F_ONFLOOR;
-      }
-      const float target_reward =
-          vis ? -(fsqrt(cx * cx + cy * cy) + fabsf(area - c.target_area) + fabsf(ratio - c.target_ratio)) : -2.0f;
-      reward -= 0.01f * e.swb[2] * e.swb[2];                        // hover.py:322-324
-      reward += target_reward - fsqrt(er * er + ep * ep);          // hover.py:326-327
-      const float a0 = act[0] - e.pa[0], a1 = act[1] - e.pa[1], a2 = act[2] - e.pa[2], a3 = act[3] - e.pa[3];
-      reward -= 0.2f * fsqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3);  // hover.py:329-331
-      reward += 1.0f;                                               // hover.py:332
-      if (bad) {  // nothing derived from the broken state may leave the kernel
-        reward = -100.f;
-#pragma unroll
-        for (int j = 0; j < OBS_DIM; ++j) obs[j] = 0.f;
-      }
-      e.flags = fl;
-      e.peul[0] = er; e.peul[1] = ep; e.peul[2] = ey;  // hover.py:354
-      e.step_count += 1;                               // hover.py:356
-      e.pa[0] = act[0]; e.pa[1] = act[1]; e.pa[2] = act[2]; e.pa[3] = act[3];  // hover.py:357
-      e.rng_ctr += 1u;
-      e.ep_ret += reward;
-      const bool term = fl & F_TERM, trunc = fl & F_TRUNC;
-      a.reward[row] = reward;
-      a.terminated[row] = term ? 1 : 0;
-      a.truncated[row] = trunc ? 1 : 0;
-      if (!(c.auto_reset && (term || trunc))) break;
-      }
-      // ---- SB3 VecEnv auto-reset + Monitor episode statistics.  The lanes of the warp that finished together
-      // aggregate: one atomic per counter per warp (a mass termination -- e.g. every env hitting the floor rule on
-      // its 32nd step -- would otherwise serialise ~4 atomics per env on four L2 addresses).
-      {
-        namespace cg = cooperative_groups;
-        const auto g = cg::coalesced_threads();
-        const double sr = cg::reduce(g, (double)e.ep_ret, cg::plus<double>());
-        const unsigned long long sl = cg::reduce(g, (unsigned long long)e.step_count, cg::plus<unsigned long long>());
-        unsigned int base = 0;
-        if (g.thread_rank() == 0) {
-          atomicAdd(&a.stats->sum_ret, sr);
-          atomicAdd(&a.stats->sum_len, sl);
-          atomicAdd(&a.stats->n_done, (unsigned long long)g.size());
-          if (MODE == MODE_STEP_DEFER) base = atomicAdd(&a.queue->count, (unsigned int)g.size());
-        }
-        if (a.terminal_obs) write_obs(obs, a.terminal_obs, i, OBS_DIM, false);
-        if (MODE == MODE_STEP_DEFER) {  // hand the env to the reset kernel; it writes the next obs
-          base = g.shfl(base, 0);
-          a.queue->idx[base + g.thread_rank()] = (unsigned int)i;
-          deferred = true;
-          break;
-        }
-      }
+      if (!reward_and_flags<TASK, CASC>(e, c, a, row, act, live, obs, x)) break;
+      episode_end<MODE == MODE_STEP_DEFER>(e, a, i, obs);
+      if (MODE == MODE_STEP_DEFER) { deferred = true; break; }
       respawn(e, c, k0, k1);
       act[0] = act[1] = act[2] = act[3] = 0.f;  // hover.py:101
       sp[0] = sp[1] = sp[2] = sp[3] = 0.f;      // set_mode(0): zero setpoint
@@ -393,6 +413,111 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
   }
   store_env(e, a.state, a.n, i);
   if (CASC) store_cascade(e, a.state, a.n, i);
+}
+
+// ===========================================================================
+// The two-envs-per-thread step kernel (hover task, flight mode 0, default control scheduling): thread t of a block
+// owns envs base + t and base + kPairBlock + t, one in each half of a float2, so the 12 sub-steps run as packed
+// FFMA2 / FMUL2 / FADD2 (qx_lanes.cuh).  The once-per-step epilogue (Euler angles, camera, reward, flags) runs per env
+// on the scalar code above.  One agent step per launch; finished envs go to the reset queue (auto_reset) like
+// MODE_STEP_DEFER.  An env that is already finished on entry (only possible without auto_reset, or when the caller
+// skipped qx_step_end) sends its thread through the one-env code instead.
+// ===========================================================================
+// launch shapes (threads per block, resident blocks per SM): 3 x 128 threads = 168 registers, 2 x 128 = 255 registers.
+// QX_PAIR_SHAPE at qx_create picks one (tuning / profiling); the default is the fastest measured on B200.
+template <int SHAPE> struct PairShape;
+template <> struct PairShape<0> { static constexpr int kBlock = 128, kMinBlocks = 3; };
+template <> struct PairShape<1> { static constexpr int kBlock = 128, kMinBlocks = 2; };
+template <> struct PairShape<2> { static constexpr int kBlock = 64, kMinBlocks = 6; };
+template <> struct PairShape<3> { static constexpr int kBlock = 64, kMinBlocks = 4; };
+constexpr int kPairShapes = 4;
+
+template <bool REF>
+__device__ __noinline__ void run_env_cold(const DevConfig& cparam, const StepArgs& a, const int64_t i) {
+  DevConfig cref = cparam;
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
+  if (c.auto_reset) run_env<MODE_STEP_DEFER, QX_TASK_HOVER, false>(c, a, i);
+  else run_env<MODE_STEP_INLINE, QX_TASK_HOVER, false>(c, a, i);
+}
+
+template <bool REF, int SHAPE, bool PK>
+__global__ void __launch_bounds__(PairShape<SHAPE>::kBlock, PairShape<SHAPE>::kMinBlocks) quadx_step_pair_kernel(const __grid_constant__ DevConfig cparam,
+                                                                                                                    const __grid_constant__ StepArgs a) {
+  constexpr int kPairBlock = PairShape<SHAPE>::kBlock;
+  DevConfig cref = cparam;
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
+  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
+  const int64_t end = a.env_begin + a.env_count;
+  const int64_t i0 = a.env_begin + (int64_t)blockIdx.x * (2 * kPairBlock) + threadIdx.x;
+  if (i0 >= end) return;
+  const bool has1 = i0 + kPairBlock < end;
+  const int64_t i1 = has1 ? i0 + kPairBlock : i0;  // a thread without a second env computes its first one twice, stores it once
+  Env e0, e1;
+  load_env_loop(e0, a.state, a.n, i0);
+  load_env_loop(e1, a.state, a.n, i1);
+  if ((e0.flags | e1.flags) & (F_TERM | F_TRUNC)) {  // cold: a finished env does not step (hover.py:347-348)
+    run_env_cold<REF>(cparam, a, i0);
+    if (has1) run_env_cold<REF>(cparam, a, i1);
+    return;
+  }
+  const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0), av1 = __ldg(reinterpret_cast<const float4*>(a.actions) + i1);
+  {
+    typedef P2<PK> V;
+    Core<V> p;
+    pack_core(p, e0, e1);
+    V sp[4];  // hover.py:337-341
+    sp[0] = vmul(V{av0.x, av1.x}, c.act_scale[0]);
+    sp[1] = vmul(V{av0.y, av1.y}, c.act_scale[1]);
+    sp[2] = vmul(V{av0.z, av1.z}, c.act_scale[2]);
+    sp[3] = vfma(V{av0.w, av1.w}, c.thrust_scale, c.thrust_bias);
+    sp[3] = V{__saturatef(sp[3].x), __saturatef(sp[3].y)};  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
+    const uint32_t k0a = c.seed_lo ^ (c.env_lo + (uint32_t)i0), k0b = c.seed_lo ^ (c.env_lo + (uint32_t)i1);
+    const uint32_t k1a = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
+    const uint32_t k1b = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i1) >> 32));
+    const int nsub = c.n_sub_step;
+#pragma unroll 1
+    for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call per env, two physics sub-steps
+      V apwm[4];
+      control_update<V>(p, c, sp, apwm);
+      V nz[4] = {V{0.f, 0.f}, V{0.f, 0.f}, V{0.f, 0.f}, V{0.f, 0.f}};
+      uint4 ba = make_uint4(0u, 0u, 0u, 0u), bb = ba;
+      if (c.noise) {
+        ba = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e0.rng_ctr, 0u), k0a, k1a);
+        bb = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e1.rng_ctr, 0u), k0b, k1b);
+        normal4_scaled<V>(make_uint2(ba.x, bb.x), make_uint2(ba.y, bb.y), c.noise_k, nz);
+      }
+      physics_substep<V>(p, c, apwm, nz, false);
+      if (c.noise) normal4_scaled<V>(make_uint2(ba.z, bb.z), make_uint2(ba.w, bb.w), c.noise_k, nz);
+      physics_substep<V>(p, c, apwm, nz, j + 2 == nsub);
+    }
+    unpack_core<0>(e0, p);
+    unpack_core<1>(e1, p);
+  }
+  // ---- per env: observation, reward, flags, episode end; the epilogue planes are loaded only now
+  {
+    load_env_tail(e0, a.state, a.n, i0);
+    const float act[4] = {av0.x, av0.y, av0.z, av0.w};
+    float obs[OBS_DIM];
+    ObsAux x;
+    build_obs<QX_TASK_HOVER>(e0, c, act, 0, true, obs, x);
+    const bool done = reward_and_flags<QX_TASK_HOVER, false>(e0, c, a, i0, act, true, obs, x);
+    if (done) episode_end<true>(e0, a, i0, obs);
+    else if (a.obs) write_obs(obs, a.obs, i0, a.obs_stride, a.obs_bf16 != 0);
+    store_env(e0, a.state, a.n, i0);
+  }
+  if (has1) {
+    load_env_tail(e1, a.state, a.n, i1);
+    const float act[4] = {av1.x, av1.y, av1.z, av1.w};
+    float obs[OBS_DIM];
+    ObsAux x;
+    build_obs<QX_TASK_HOVER>(e1, c, act, 0, true, obs, x);
+    const bool done = reward_and_flags<QX_TASK_HOVER, false>(e1, c, a, i1, act, true, obs, x);
+    if (done) episode_end<true>(e1, a, i1, obs);
+    else if (a.obs) write_obs(obs, a.obs, i1, a.obs_stride, a.obs_bf16 != 0);
+    store_env(e1, a.state, a.n, i1);
+  }
 }
 
 }  // namespace qx
@@ -407,6 +532,10 @@ struct QxHandle {
   int device;
   int planes;  // float4 state planes: 11, or 17 when flight_mode != 0
   bool ref_constants;  // the model constants equal the reference's literals bit for bit: run the specialised kernels
+  bool pair_ok;        // hover, flight mode 0, control every 2nd sub-step: the two-envs-per-thread step kernel applies
+  int pair_mode;       // QX_PAIR env var at qx_create: -1 default (large batches), 0 never, 1 always
+  int pair_shape;      // QX_PAIR_SHAPE env var at qx_create: launch shape of the two-env kernel
+  bool pair_packed;    // QX_PAIR_PACKED env var (default 1): FFMA2 / FMUL2 / FADD2, or the same two-env code on scalar FP instructions
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
@@ -544,6 +673,14 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
     }
   };
   gains(s.att_pid, 3, d->att); gains(s.vel_pid, 2, d->vel); gains(s.pos_pid, 2, d->lpos); gains(s.zpos_pid, 1, d->zpos); gains(s.zvel_pid, 1, d->zvel);
+  // motor geometry folded with the thrust scale; symmetric-X shortcuts when the config allows them (cf2x.urdf:35-68 does)
+  for (int m = 0; m < 4; ++m) { d->arm_x[m] = -d->thrust_k * d->mx[m]; d->arm_y[m] = d->thrust_k * d->my[m]; }
+  const float ax = d->mx[0], tq = d->torque_k[2];
+  d->x_layout = (ax > 0.f && d->mx[1] == -ax && d->mx[2] == ax && d->mx[3] == -ax && d->my[0] == -ax && d->my[1] == ax && d->my[2] == ax &&
+                 d->my[3] == -ax && d->torque_k[0] == -tq && d->torque_k[1] == -tq && d->torque_k[3] == tq) ? 1 : 0;
+  d->arm_k = d->thrust_k * ax; d->tq_k = tq;
+  static const float xmap[16] = {-1, -1, -1, 1, 1, 1, -1, 1, 1, -1, 1, 1, -1, 1, 1, 1};
+  d->x_mixer = memcmp(d->map, xmap, sizeof(xmap)) == 0 ? 1 : 0;
   return QX_OK;
 }
 
@@ -568,6 +705,14 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   cudaSetDevice(device);
   h->planes = cfg->flight_mode != 0 ? qx::kCascadePlanes : qx::kBasePlanes;
   h->ref_constants = !getenv("QX_FORCE_GENERIC") && matches_ref_constants(h->dev);
+  h->pair_ok = cfg->task == QX_TASK_HOVER && cfg->flight_mode == 0 && h->dev.ctrl_every == 2 && (h->dev.n_sub_step & 1) == 0 && h->dev.n_sub_step > 0;
+  const char* pm = getenv("QX_PAIR");
+  h->pair_mode = pm ? atoi(pm) : -1;
+  const char* ps = getenv("QX_PAIR_SHAPE");
+  h->pair_shape = ps ? atoi(ps) : 0;
+  if (h->pair_shape < 0 || h->pair_shape >= qx::kPairShapes) h->pair_shape = 0;
+  const char* pp = getenv("QX_PAIR_PACKED");
+  h->pair_packed = pp ? atoi(pp) != 0 : true;
   cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaMalloc(&h->queue, sizeof(qx::ResetQueue) + sizeof(unsigned int) * n_envs);
@@ -666,8 +811,46 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
   }
 }
 
+template <int SHAPE>
+static void launch_pair_one(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  constexpr int B = qx::PairShape<SHAPE>::kBlock;
+  const unsigned grid = (unsigned)((a.env_count + 2 * B - 1) / (2 * B));
+  if (h->pair_packed) {
+    if (h->ref_constants) qx::quadx_step_pair_kernel<true, SHAPE, true><<<grid, B, 0, s>>>(h->dev, a);
+    else qx::quadx_step_pair_kernel<false, SHAPE, true><<<grid, B, 0, s>>>(h->dev, a);
+  } else {
+    if (h->ref_constants) qx::quadx_step_pair_kernel<true, SHAPE, false><<<grid, B, 0, s>>>(h->dev, a);
+    else qx::quadx_step_pair_kernel<false, SHAPE, false><<<grid, B, 0, s>>>(h->dev, a);
+  }
+}
+static void launch_pair_shape(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  switch (h->pair_shape) {
+    case 1: launch_pair_one<1>(h, a, s); break;
+    case 2: launch_pair_one<2>(h, a, s); break;
+    case 3: launch_pair_one<3>(h, a, s); break;
+    default: launch_pair_one<0>(h, a, s); break;
+  }
+}
+// one agent step of the two-envs-per-thread kernel (replaces MODE_STEP_DEFER, or MODE_STEP_INLINE with k = 1 and no auto-reset)
+static int launch_pair(QxHandle* h, qx::StepArgs a, cudaStream_t s) {
+  if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
+  launch_pair_shape(h, a, s);
+  ++g_launches;
+  QX_CUDA(cudaGetLastError());
+  return QX_OK;
+}
+// batches above this size step two envs per thread (below it the launch is latency-bound and the one-env kernel's
+// extra warps win); QX_PAIR=0 / 1 at qx_create forces never / always
+constexpr int64_t kPairMinEnvs = 32768;
+static bool use_pair(const QxHandle* h) {  // decided per handle, not per launch: a chunked call must run the same arithmetic as a whole one
+  if (!h->pair_ok || h->pair_mode == 0) return false;
+  return h->pair_mode == 1 || h->n >= kPairMinEnvs;
+}
+
 static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
+  if (use_pair(h) && (mode == qx::MODE_STEP_DEFER || (mode == qx::MODE_STEP_INLINE && a.k == 1 && !h->cfg.auto_reset)))
+    return launch_pair(h, a, s);
   if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false, false>(h, mode, a, s);
   else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true, false>(h, mode, a, s);
   else if (h->ref_constants) launch_task<QX_TASK_HOVER, false, true>(h, mode, a, s);
@@ -725,7 +908,7 @@ extern "C" int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_
 constexpr int64_t kInlineResetMaxEnvs = 16384;
 extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
                        float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
-  if (h && h->cfg.auto_reset && h->n <= kInlineResetMaxEnvs) {
+  if (h && h->cfg.auto_reset && h->n <= kInlineResetMaxEnvs && !(h->pair_mode == 1 && h->pair_ok)) {
     if (!actions_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(QX_EINVAL, "qx_step: bad arguments");
     if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step: obs_stride < obs_dim");
     qx::StepArgs a{};
@@ -823,7 +1006,7 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.reward = h->d_rew;
     a.terminated = h->d_flags; a.truncated = h->d_flags + n; a.terminal_obs = terminal_obs_host ? h->d_tobs : nullptr;
     a.stats = h->stats; a.queue = h->queue; a.n = n; a.k = 1; a.env_begin = b; a.env_count = cnt;
-    if (h->cfg.auto_reset && n > kInlineResetMaxEnvs) {
+    if (h->cfg.auto_reset && (n > kInlineResetMaxEnvs || (h->pair_mode == 1 && h->pair_ok))) {
       rc = launch(h, qx::MODE_STEP_DEFER, a, h->stream);
       if (rc) return rc;
       rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "qx_lanes.cuh"
+
 namespace qx {
 
 // ---------------------------------------------------------------------------
@@ -36,6 +38,12 @@ struct DevConfig {
   int32_t flight_mode, need_euler;
   float thrust_scale, thrust_bias;
   float att[12], vel[8], lpos[8], zpos[4], zvel[4];
+  // motor geometry folded with the thrust scale: torque_x = sum arm_y[m] rr[m], torque_y = sum arm_x[m] rr[m]
+  // (arm_x = -thrust_k mx, arm_y = thrust_k my).  x_layout: the four props sit on a symmetric X (cf2x.urdf:35-68) with
+  // torque signs (-,-,+,+), so the sums share partial sums (arm_k = thrust_k |mx|, tq_k = torque_k[2]); x_mixer: the
+  // motor map is the +-1 matrix of that layout, so the mixer is eight adds.
+  int32_t x_layout, x_mixer;
+  float arm_x[4], arm_y[4], arm_k, tq_k;
 };
 
 }  // namespace qx
@@ -56,50 +64,71 @@ enum : uint32_t {
 };
 enum : uint32_t { STREAM_STEP = 0, STREAM_RESET = 1, STREAM_SPAWN = 2 };
 
-// The 44 carried words of one env (QX_STATE_WORDS); plane p, lane l = word 4p+l.
-struct Env {
-  float px, py, pz;           // world position
-  float qx, qy, qz, qw;       // body->world quaternion (x,y,z,w)
-  float vx, vy, vz;           // world linear velocity
-  float wx, wy, wz;           // BODY-frame angular velocity (see physics_substep)
-  float thr[4];               // motor throttle (PyFlyt Motors.throttle)
-  float pi[3], pe[3];         // rate PID integral, previous error
-  float swb[3], svb[3];       // Aviary.state rows 0 and 2 (body rates / velocity snapshot)
-  float peul[3];              // previous_ang_pos, hover.py:354
-  float pa[4];                // prev_action, hover.py:357
-  float pcx, pcy, parea, pratio;  // hover.py:270-272
+// What the physics sub-steps and the rate controller read and write, for one env (T = float) or two (T = float2).
+template <class T>
+struct Core {
+  T px, py, pz;           // world position
+  T qx, qy, qz, qw;       // body->world quaternion (x,y,z,w)
+  T vx, vy, vz;           // world linear velocity
+  T wx, wy, wz;           // BODY-frame angular velocity (see physics_substep)
+  T thr[4];               // motor throttle (PyFlyt Motors.throttle)
+  T pi[3], pe[3];         // rate PID integral, previous error
+  T swb[3], svb[3];       // Aviary.state rows 0 and 2 (body rates / velocity snapshot)
+  typename Lane<T>::mask contact;  // resting on the floor stand-in (F_CONTACT of the stored flags word)
+  // transient (not stored): pose part of the Aviary.state snapshot
+  T sqx, sqy, sqz, sqw, spx, spy, spz;
+};
+
+// The 44 carried words of one env (QX_STATE_WORDS); plane p, lane l = word 4p+l.  Planes 0..7 are what the sub-step
+// loop needs (Core + counters + flags), planes 8..10 only the once-per-step epilogue -- the two-env kernel loads those
+// after the loop, so they do not occupy registers across it.
+struct Env : Core<float> {
   int32_t step_count;         // hover.py:356
   uint32_t rng_ctr;           // env steps since creation (Philox counter word 2)
-  float ep_ret;               // Monitor: running episode return
   uint32_t flags;
-  // transient (not stored): pose part of the Aviary.state snapshot
-  float sqx, sqy, sqz, sqw, spx, spy, spz;
+  float peul[3];              // previous_ang_pos, hover.py:354
+  float ep_ret;               // Monitor: running episode return
+  float pa[4];                // prev_action, hover.py:357
+  float pcx, pcy, parea, pratio;  // hover.py:270-272
   // cascade instantiation only (planes 11..16; spx/spy/spz are carried there too): (integral, previous error) of
   // ang_pos 0/3, lin_vel 6/8, lin_pos 10/12, z_vel 14/15, z_pos 16/17
   float cp[18];
 };
 
-__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+QX_DI float4 ldg4(const float4* p) { return __ldg(p); }
 
-__device__ __forceinline__ void load_env(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
-  float4 a = ldg4(st + 0 * n + i), b = ldg4(st + 1 * n + i), c = ldg4(st + 2 * n + i), d = ldg4(st + 3 * n + i);
-  float4 f = ldg4(st + 4 * n + i), g = ldg4(st + 5 * n + i), h = ldg4(st + 6 * n + i), k = ldg4(st + 7 * n + i);
-  float4 l = ldg4(st + 8 * n + i), m = ldg4(st + 9 * n + i), o = ldg4(st + 10 * n + i);
-  e.px = a.x; e.py = a.y; e.pz = a.z; e.qx = a.w;
-  e.qy = b.x; e.qz = b.y; e.qw = b.z; e.vx = b.w;
-  e.vy = c.x; e.vz = c.y; e.wx = c.z; e.wy = c.w;
-  e.wz = d.x; e.thr[0] = d.y; e.thr[1] = d.z; e.thr[2] = d.w;
-  e.thr[3] = f.x; e.pi[0] = f.y; e.pi[1] = f.z; e.pi[2] = f.w;
-  e.pe[0] = g.x; e.pe[1] = g.y; e.pe[2] = g.z; e.swb[0] = g.w;
-  e.swb[1] = h.x; e.swb[2] = h.y; e.svb[0] = h.z; e.svb[1] = h.w;
-  e.svb[2] = k.x; e.peul[0] = k.y; e.peul[1] = k.z; e.peul[2] = k.w;
-  e.pa[0] = l.x; e.pa[1] = l.y; e.pa[2] = l.z; e.pa[3] = l.w;
-  e.pcx = m.x; e.pcy = m.y; e.parea = m.z; e.pratio = m.w;
-  e.step_count = __float_as_int(o.x); e.rng_ctr = __float_as_uint(o.y); e.ep_ret = o.z; e.flags = __float_as_uint(o.w);
+constexpr int kLoopPlanes = 8;  // planes 0..7: sub-step loop state
+QX_DI void unpack_loop_planes(Env& e, const float4 (&v)[kLoopPlanes]) {
+  e.px = v[0].x; e.py = v[0].y; e.pz = v[0].z; e.qx = v[0].w;
+  e.qy = v[1].x; e.qz = v[1].y; e.qw = v[1].z; e.vx = v[1].w;
+  e.vy = v[2].x; e.vz = v[2].y; e.wx = v[2].z; e.wy = v[2].w;
+  e.wz = v[3].x; e.thr[0] = v[3].y; e.thr[1] = v[3].z; e.thr[2] = v[3].w;
+  e.thr[3] = v[4].x; e.pi[0] = v[4].y; e.pi[1] = v[4].z; e.pi[2] = v[4].w;
+  e.pe[0] = v[5].x; e.pe[1] = v[5].y; e.pe[2] = v[5].z; e.swb[0] = v[5].w;
+  e.swb[1] = v[6].x; e.swb[2] = v[6].y; e.svb[0] = v[6].z; e.svb[1] = v[6].w;
+  e.svb[2] = v[7].x; e.step_count = __float_as_int(v[7].y); e.rng_ctr = __float_as_uint(v[7].z); e.flags = __float_as_uint(v[7].w);
+  e.contact = (e.flags & F_CONTACT) != 0u;
   e.sqx = e.qx; e.sqy = e.qy; e.sqz = e.qz; e.sqw = e.qw; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
 }
+QX_DI void load_env_loop(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  float4 v[kLoopPlanes];
+#pragma unroll
+  for (int p = 0; p < kLoopPlanes; ++p) v[p] = ldg4(st + (int64_t)p * n + i);
+  unpack_loop_planes(e, v);
+}
+QX_DI void load_env_tail(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  const float4 k = ldg4(st + 8 * n + i), l = ldg4(st + 9 * n + i), m = ldg4(st + 10 * n + i);
+  e.peul[0] = k.x; e.peul[1] = k.y; e.peul[2] = k.z; e.ep_ret = k.w;
+  e.pa[0] = l.x; e.pa[1] = l.y; e.pa[2] = l.z; e.pa[3] = l.w;
+  e.pcx = m.x; e.pcy = m.y; e.parea = m.z; e.pratio = m.w;
+}
+QX_DI void load_env(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  load_env_loop(e, st, n, i);
+  load_env_tail(e, st, n, i);
+}
 
-__device__ __forceinline__ void store_env(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
+QX_DI void store_env(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
+  const uint32_t flags = (e.flags & ~F_CONTACT) | (e.contact ? F_CONTACT : 0u);
   st[0 * n + i] = make_float4(e.px, e.py, e.pz, e.qx);
   st[1 * n + i] = make_float4(e.qy, e.qz, e.qw, e.vx);
   st[2 * n + i] = make_float4(e.vy, e.vz, e.wx, e.wy);
@@ -107,16 +136,16 @@ __device__ __forceinline__ void store_env(const Env& e, float4* __restrict__ st,
   st[4 * n + i] = make_float4(e.thr[3], e.pi[0], e.pi[1], e.pi[2]);
   st[5 * n + i] = make_float4(e.pe[0], e.pe[1], e.pe[2], e.swb[0]);
   st[6 * n + i] = make_float4(e.swb[1], e.swb[2], e.svb[0], e.svb[1]);
-  st[7 * n + i] = make_float4(e.svb[2], e.peul[0], e.peul[1], e.peul[2]);
-  st[8 * n + i] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
-  st[9 * n + i] = make_float4(e.pcx, e.pcy, e.parea, e.pratio);
-  st[10 * n + i] = make_float4(__int_as_float(e.step_count), __uint_as_float(e.rng_ctr), e.ep_ret, __uint_as_float(e.flags));
+  st[7 * n + i] = make_float4(e.svb[2], __int_as_float(e.step_count), __uint_as_float(e.rng_ctr), __uint_as_float(flags));
+  st[8 * n + i] = make_float4(e.peul[0], e.peul[1], e.peul[2], e.ep_ret);
+  st[9 * n + i] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
+  st[10 * n + i] = make_float4(e.pcx, e.pcy, e.parea, e.pratio);
 }
 
 // Flight modes != 0: six more planes -- the outer loops' PID memory and the position row of the Aviary.state
 // snapshot, which those loops read at the first control update of the next step.
 constexpr int kBasePlanes = 11, kCascadePlanes = 17;
-__device__ __forceinline__ void load_cascade(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+QX_DI void load_cascade(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
   float4 v[6];
 #pragma unroll
   for (int p = 0; p < 6; ++p) v[p] = ldg4(st + (int64_t)(kBasePlanes + p) * n + i);
@@ -125,7 +154,7 @@ __device__ __forceinline__ void load_cascade(Env& e, const float4* __restrict__ 
   for (int k = 0; k < 18; ++k) e.cp[k] = w[k];
   e.spx = w[18]; e.spy = w[19]; e.spz = w[20];
 }
-__device__ __forceinline__ void store_cascade(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
+QX_DI void store_cascade(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
   st[(int64_t)(kBasePlanes + 0) * n + i] = make_float4(e.cp[0], e.cp[1], e.cp[2], e.cp[3]);
   st[(int64_t)(kBasePlanes + 1) * n + i] = make_float4(e.cp[4], e.cp[5], e.cp[6], e.cp[7]);
   st[(int64_t)(kBasePlanes + 2) * n + i] = make_float4(e.cp[8], e.cp[9], e.cp[10], e.cp[11]);
@@ -134,12 +163,52 @@ __device__ __forceinline__ void store_cascade(const Env& e, float4* __restrict__
   st[(int64_t)(kBasePlanes + 5) * n + i] = make_float4(e.spz, 0.f, 0.f, 0.f);
 }
 
-// ---------------------------------------------------------------------------
-// Philox4x32-10: same integer stream as oracle/quadx_model.py:philox4x32_10
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+// two scalar envs <-> one two-lane Core (register renaming only)
+template <class P>
+QX_DI void pack_core(Core<P>& p, const Core<float>& a, const Core<float>& b) {
+#define mk2(u, v) P{u, v}
+  p.px = mk2(a.px, b.px); p.py = mk2(a.py, b.py); p.pz = mk2(a.pz, b.pz);
+  p.qx = mk2(a.qx, b.qx); p.qy = mk2(a.qy, b.qy); p.qz = mk2(a.qz, b.qz); p.qw = mk2(a.qw, b.qw);
+  p.vx = mk2(a.vx, b.vx); p.vy = mk2(a.vy, b.vy); p.vz = mk2(a.vz, b.vz);
+  p.wx = mk2(a.wx, b.wx); p.wy = mk2(a.wy, b.wy); p.wz = mk2(a.wz, b.wz);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int m = 0; m < 4; ++m) p.thr[m] = mk2(a.thr[m], b.thr[m]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    p.pi[k] = mk2(a.pi[k], b.pi[k]); p.pe[k] = mk2(a.pe[k], b.pe[k]);
+    p.swb[k] = mk2(a.swb[k], b.swb[k]); p.svb[k] = mk2(a.svb[k], b.svb[k]);
+  }
+  p.contact = m2{a.contact, b.contact};
+  p.sqx = mk2(a.sqx, b.sqx); p.sqy = mk2(a.sqy, b.sqy); p.sqz = mk2(a.sqz, b.sqz); p.sqw = mk2(a.sqw, b.sqw);
+  p.spx = mk2(a.spx, b.spx); p.spy = mk2(a.spy, b.spy); p.spz = mk2(a.spz, b.spz);
+#undef mk2
+}
+template <int HALF, class P>
+QX_DI void unpack_core(Core<float>& a, const Core<P>& p) {
+#define QX_H(v) (HALF ? (v).y : (v).x)
+  a.px = QX_H(p.px); a.py = QX_H(p.py); a.pz = QX_H(p.pz);
+  a.qx = QX_H(p.qx); a.qy = QX_H(p.qy); a.qz = QX_H(p.qz); a.qw = QX_H(p.qw);
+  a.vx = QX_H(p.vx); a.vy = QX_H(p.vy); a.vz = QX_H(p.vz);
+  a.wx = QX_H(p.wx); a.wy = QX_H(p.wy); a.wz = QX_H(p.wz);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) a.thr[m] = QX_H(p.thr[m]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { a.pi[k] = QX_H(p.pi[k]); a.pe[k] = QX_H(p.pe[k]); a.swb[k] = QX_H(p.swb[k]); a.svb[k] = QX_H(p.svb[k]); }
+  a.contact = HALF ? p.contact.y : p.contact.x;
+  a.sqx = QX_H(p.sqx); a.sqy = QX_H(p.sqy); a.sqz = QX_H(p.sqz); a.sqw = QX_H(p.sqw);
+  a.spx = QX_H(p.spx); a.spy = QX_H(p.spy); a.spz = QX_H(p.spz);
+#undef QX_H
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-R: same integer stream as oracle/quadx_model.py:philox4x32.  The env's motor / spawn noise uses R = 7
+// (Random123: the smallest round count that passes BigCrush); the policy's action sampling keeps R = 10.
+// ---------------------------------------------------------------------------
+constexpr int kEnvPhiloxRounds = 7;
+template <int ROUNDS>
+QX_DI uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
@@ -148,76 +217,80 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   }
   return c;
 }
-
-// MUFU-only approximations (1-2 ulp): no Newton refinement, no slow paths
-__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float frsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+QX_DI uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) { return philox4x32<10>(c, k0, k1); }
+QX_DI uint4 env_philox(uint4 c, uint32_t k0, uint32_t k1) { return philox4x32<kEnvPhiloxRounds>(c, k0, k1); }
 
 // ((x >> 9) + 0.5) * 2^-23 without an int->float conversion (reset pose noise)
-__device__ __forceinline__ float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
-// 16-bit field -> (k + 0.5) * 2^-16: field in the top of the mantissa of [1,2), minus (1 - 2^-17)
-__device__ __forceinline__ float u01_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
-__device__ __forceinline__ float u01_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u) - 0.99999237060546875f; }
-
+QX_DI float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
 // 16-bit field in the top of the mantissa of [1,2): m = 1 + k 2^-16
-__device__ __forceinline__ float m12_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u); }
-__device__ __forceinline__ float m12_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u); }
+QX_DI float m12_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u); }
+QX_DI float m12_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u); }
+template <class T> QX_DI T m12_lo(uint32_t w) { return m12_lo16(w); }
+template <class T> QX_DI T m12_hi(uint32_t w) { return m12_hi16(w); }
+template <class T> QX_DI T m12_lo(uint2 w) { return T{m12_lo16(w.x), m12_lo16(w.y)}; }
+template <class T> QX_DI T m12_hi(uint2 w) { return T{m12_hi16(w.x), m12_hi16(w.y)}; }
 
 // 4 x noise_ratio * N(0,1) from two 32-bit words, like oracle normal4(): each word is one Box-Muller pair
-// (low half -> radius, high half -> angle).  u = m - (1 - 2^-17) in (0,1);  scale folded into the radius:
-// noise_ratio sqrt(-2 ln u) = sqrt(noise_k lg2 u);  angle 2 pi u - pi = 2 pi m - (2 pi (1 - 2^-17) + pi), and
-// sin(t - pi) = -sin t, cos(t - pi) = -cos t keeps the MUFU argument in [-pi, pi].
-__device__ __forceinline__ void normal4_scaled(uint32_t w0, uint32_t w1, float noise_k, float n[4]) {
-  const float ra = -fsqrt(noise_k * __log2f(m12_lo16(w0) - 0.99999237060546875f));
-  const float rb = -fsqrt(noise_k * __log2f(m12_lo16(w1) - 0.99999237060546875f));
-  const float ta = fmaf(6.28318530718f, m12_hi16(w0), -9.42473002f);
-  const float tb = fmaf(6.28318530718f, m12_hi16(w1), -9.42473002f);
-  n[0] = ra * __cosf(ta); n[1] = ra * __sinf(ta); n[2] = rb * __cosf(tb); n[3] = rb * __sinf(tb);
+// (low half -> radius, high half -> angle).  u = m - (1 - 2^-17) = (k + 0.5) 2^-16 in (0,1);  the scale is folded into
+// the radius: noise_ratio sqrt(-2 ln u) = sqrt(noise_k lg2 u);  the angle is 2 pi u - pi in (-pi, pi), where the MUFU
+// sine / cosine are most accurate, = 2 pi m - (2 pi (1 - 2^-17) + pi).
+template <class T, class U>
+QX_DI void normal4_scaled(U w0, U w1, float noise_k, T n[4]) {
+  const T ra = vsqrt(vmul(vlg2(vadd(m12_lo<T>(w0), -0.99999237060546875f)), noise_k));
+  const T rb = vsqrt(vmul(vlg2(vadd(m12_lo<T>(w1), -0.99999237060546875f)), noise_k));
+  const T ta = vfma(m12_hi<T>(w0), 6.28318530718f, -9.42473002f);
+  const T tb = vfma(m12_hi<T>(w1), 6.28318530718f, -9.42473002f);
+  n[0] = vmul(ra, vcos(ta)); n[1] = vmul(ra, vsin(ta)); n[2] = vmul(rb, vcos(tb)); n[3] = vmul(rb, vsin(tb));
 }
-
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // ---------------------------------------------------------------------------
 // PyFlyt QuadX.update_control, mode 0: rate PID -> motor mix -> saturation
 // ---------------------------------------------------------------------------
-// pwm[] returns lag_alpha * pwm (see the end of the function)
-__device__ __forceinline__ void control_update(Env& e, const DevConfig& c, const float sp[4], float pwm[4]) {
-  float cmd[4];
+// apwm[] returns lag_alpha * pwm: the motor lag thr += alpha (pwm - thr) is applied as thr (1 - alpha) + (alpha pwm)
+template <class T>
+QX_DI void control_update(Core<T>& e, const DevConfig& c, const T sp[4], T apwm[4]) {
+  T cmd[4], pwm[4];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    const float err = sp[a] - e.swb[a];
-    e.pi[a] = clampf(fmaf(c.kiT[a], err, e.pi[a]), -c.lim[a], c.lim[a]);
-    const float d = c.kd_T[a] * (err - e.pe[a]);
-    cmd[a] = clampf(fmaf(c.kp[a], err, e.pi[a]) + d, -c.lim[a], c.lim[a]);
+    const T err = vsub(sp[a], e.swb[a]);
+    e.pi[a] = vclamp(vfma(err, c.kiT[a], e.pi[a]), -c.lim[a], c.lim[a]);
+    T u = vfma(err, c.kp[a], e.pi[a]);
+    if (c.kd_T[a] != 0.f) u = vfma(vsub(err, e.pe[a]), c.kd_T[a], u);
+    cmd[a] = vclamp(u, -c.lim[a], c.lim[a]);
     e.pe[a] = err;
   }
   cmd[3] = sp[3];
+  if (c.x_mixer) {  // rows (-,-,-,+) (+,+,-,+) (+,-,+,+) (-,+,+,+): shared sums and differences
+    const T s = vadd(cmd[0], cmd[1]), d = vsub(cmd[0], cmd[1]), a = vsub(cmd[3], cmd[2]), b = vadd(cmd[3], cmd[2]);
+    pwm[0] = vsub(a, s); pwm[1] = vadd(a, s); pwm[2] = vadd(b, d); pwm[3] = vsub(b, d);
+  } else {
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
-    pwm[m] = c.map[4 * m + 0] * cmd[0] + c.map[4 * m + 1] * cmd[1] + c.map[4 * m + 2] * cmd[2] + c.map[4 * m + 3] * cmd[3];
-  const float high = fmaxf(fmaxf(pwm[0], pwm[1]), fmaxf(pwm[2], pwm[3]));
-  if (high > 1.0f) {
-    const float inv = frcp(high);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) pwm[m] *= inv;
+    for (int m = 0; m < 4; ++m)
+      pwm[m] = vfma(cmd[3], c.map[4 * m + 3], vfma(cmd[2], c.map[4 * m + 2], vfma(cmd[1], c.map[4 * m + 1], vmul(cmd[0], c.map[4 * m + 0]))));
   }
-  const float low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
-  if (low < c.pwm_idle) {
-    const float k = (c.pwm_idle - low) * frcp(1.0f - low);
+  const T high = vmax(vmax(pwm[0], pwm[1]), vmax(pwm[2], pwm[3]));
+  const auto over = vgt(high, 1.0f);
+  if (vany(over)) {
+    const T inv = vsel(over, vrcp(high), 1.0f);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) pwm[m] = fmaf(1.0f - pwm[m], k, pwm[m]);
+    for (int m = 0; m < 4; ++m) pwm[m] = vmul(pwm[m], inv);
   }
-  // the motor lag thr += alpha (pwm - thr) is applied as thr (1 - alpha) + (alpha pwm): hoist alpha pwm out of the sub-steps
+  const T low = vmin(vmin(pwm[0], pwm[1]), vmin(pwm[2], pwm[3]));
+  const auto under = vlt(low, c.pwm_idle);
+  if (vany(under)) {
+    const T k = vsel(under, vmul(vsub(c.pwm_idle, low), vrcp(vsub(1.0f, low))), 0.f);
 #pragma unroll
-  for (int m = 0; m < 4; ++m) pwm[m] *= c.lag_alpha;
+    for (int m = 0; m < 4; ++m) pwm[m] = vfma(vsub(1.0f, pwm[m]), k, pwm[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) apwm[m] = vmul(pwm[m], c.lag_alpha);
 }
 
 // ---------------------------------------------------------------------------
 // PyFlyt PID.step for one channel; g = kp[w] ki*T[w] kd/T[w] lim[w], channel k
 // ---------------------------------------------------------------------------
 template <int W>
-__device__ __forceinline__ float pid_channel(const float* g, int k, float& mi, float& me, float state, float sp) {
+QX_DI float pid_channel(const float* g, int k, float& mi, float& me, float state, float sp) {
   const float err = sp - state, lim = g[3 * W + k];
   mi = clampf(fmaf(g[W + k], err, mi), -lim, lim);
   const float d = g[2 * W + k] * (err - me);
@@ -228,7 +301,7 @@ __device__ __forceinline__ float pid_channel(const float* g, int k, float& mi, f
 // QuadX.update_control for flight modes != 0: the outer loops turn the setpoint into (rate commands, thrust) and the
 // mode-0 controller above finishes the job.  seul = Euler row of the Aviary.state snapshot.  Mode -1 bypasses
 // everything (setpoint = motor pwm, no mixing, no saturation).
-__device__ __forceinline__ void control_update_cascade(Env& e, const DevConfig& c, const float sp[4], const float seul[3], float pwm[4]) {
+QX_DI void control_update_cascade(Env& e, const DevConfig& c, const float sp[4], const float seul[3], float pwm[4]) {
   const int mode = c.flight_mode;
   if (mode == -1) {
 #pragma unroll
@@ -262,7 +335,7 @@ __device__ __forceinline__ void control_update_cascade(Env& e, const DevConfig& 
   if (mode == 2 || mode == 3 || mode == 4 || mode == 7) a[3] = pid_channel<1>(c.zpos, 0, e.cp[16], e.cp[17], e.spz, a[3]);
   if (mode != 0) a[3] = pid_channel<1>(c.zvel, 0, e.cp[14], e.cp[15], e.svb[2], a[3]);
   a[3] = __saturatef(a[3]);
-  control_update(e, c, a, pwm);
+  control_update<float>(e, c, a, pwm);
 }
 
 // ---------------------------------------------------------------------------
@@ -276,101 +349,125 @@ __device__ __forceinline__ void control_update_cascade(Env& e, const DevConfig& 
 // (Bullet's +-100 clamp acts on world components; here on body components --
 // the two differ only beyond 100 rad/s.)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void physics_substep(Env& e, const DevConfig& c, const float apwm[4], const float nz[4], const bool last) {
+// cold path: an env at or below the floor plane -- sticky plane at floor_z (zeroes world v_xy and world w_xy)
+template <class T, class M>
+QX_DI void floor_contact(Core<T>& e, const DevConfig& c, const M below) {
+  e.pz = vsel(below, c.floor_z, e.pz);
+  e.vz = vsel(below, vmax(e.vz, splat<T>(0.f)), e.vz);
+  e.vx = vsel(below, 0.f, e.vx);
+  e.vy = vsel(below, 0.f, e.vy);
+  const T X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
+  const T a20 = vmul(vsub(vmul(X, Z), vmul(W, Y)), 2.f), a21 = vmul(vfma(Y, Z, vmul(W, X)), 2.f);
+  const T a22 = vsub(1.f, vmul(vfma(X, X, vmul(Y, Y)), 2.f));
+  const T wzw = vfma(a22, e.wz, vfma(a21, e.wy, vmul(a20, e.wx)));  // world yaw rate survives
+  e.wx = vsel(below, vmul(a20, wzw), e.wx);
+  e.wy = vsel(below, vmul(a21, wzw), e.wy);
+  e.wz = vsel(below, vmul(a22, wzw), e.wz);
+}
+
+template <class T>
+QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], const T nz[4], const bool last) {
   // motors: first-order lag, multiplicative noise, thrust and torques
-  float fz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+  T rr[4];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    float t = fmaf(e.thr[m], c.one_m_alpha, apwm[m]);
-    t = fmaf(nz[m], t, t);                // nz already scaled by noise_ratio
+    T t = vfma(e.thr[m], c.one_m_alpha, apwm[m]);
+    t = vfma(nz[m], t, t);                // nz already scaled by noise_ratio
     e.thr[m] = t;
-    const float rr = fabsf(t) * t;        // rpm |rpm| / max_rpm^2
-    fz += rr;
-    tx = fmaf(c.my[m], rr, tx);           // r x F = (y F, -x F, 0)
-    ty = fmaf(c.mx[m], rr, ty);
-    tz = fmaf(c.torque_k[m], rr, tz);
+    rr[m] = vabsmul(t, t);                // rpm |rpm| / max_rpm^2
   }
-  fz *= c.thrust_k; tx *= c.thrust_k; ty *= -c.thrust_k;
+  T fz, tx, ty, tz;                       // r x F = (y F, -x F, 0)
+  if (c.x_layout) {
+    const T a = vadd(rr[0], rr[3]), b = vadd(rr[1], rr[2]), ee = vadd(rr[0], rr[2]), f = vadd(rr[1], rr[3]);
+    const T cc = vadd(rr[0], rr[1]), d = vadd(rr[2], rr[3]);
+    fz = vadd(a, b);
+    tx = vmul(vsub(b, a), c.arm_k); ty = vmul(vsub(f, ee), c.arm_k); tz = vmul(vsub(d, cc), c.tq_k);
+  } else {
+    fz = vadd(vadd(rr[0], rr[1]), vadd(rr[2], rr[3]));
+    tx = vmul(rr[0], c.arm_y[0]); ty = vmul(rr[0], c.arm_x[0]); tz = vmul(rr[0], c.torque_k[0]);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) { tx = vfma(rr[m], c.arm_y[m], tx); ty = vfma(rr[m], c.arm_x[m], ty); tz = vfma(rr[m], c.torque_k[m], tz); }
+  }
+  if (c.thrust_k != 1.0f) fz = vmul(fz, c.thrust_k);
   // drag from the (stale) snapshot, body frame
-  const float fbx = c.ndrag_c * fabsf(e.svb[0]) * e.svb[0];
-  const float fby = c.ndrag_c * fabsf(e.svb[1]) * e.svb[1];
-  const float fbz = fmaf(c.ndrag_c * fabsf(e.svb[2]), e.svb[2], fz);
-  if (!(e.flags & F_CONTACT)) {
-    tx = fmaf(c.ndrag_pqr * fabsf(e.swb[0]), e.swb[0], tx);
-    ty = fmaf(c.ndrag_pqr * fabsf(e.swb[1]), e.swb[1], ty);
-    tz = fmaf(c.ndrag_pqr * fabsf(e.swb[2]), e.swb[2], tz);
+  const T fbx = vmul(vabsmul(e.svb[0], c.ndrag_c), e.svb[0]);
+  const T fby = vmul(vabsmul(e.svb[1], c.ndrag_c), e.svb[1]);
+  const T fbz = vfma(vabsmul(e.svb[2], c.ndrag_c), e.svb[2], fz);
+  if (vany(e.contact)) {  // no angular drag while resting on the floor (cold)
+    const T dq = vsel(e.contact, splat<T>(0.f), c.ndrag_pqr);
+    tx = vfma(vabsmul(e.swb[0], dq), e.swb[0], tx);
+    ty = vfma(vabsmul(e.swb[1], dq), e.swb[1], ty);
+    tz = vfma(vabsmul(e.swb[2], dq), e.swb[2], tz);
+  } else {
+    tx = vfma(vabsmul(e.swb[0], c.ndrag_pqr), e.swb[0], tx);
+    ty = vfma(vabsmul(e.swb[1], c.ndrag_pqr), e.swb[1], ty);
+    tz = vfma(vabsmul(e.swb[2], c.ndrag_pqr), e.swb[2], tz);
   }
   // rotation matrix of the current attitude
-  const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
-  const float x2 = x + x, y2 = y + y, z2 = z + z;
-  // 18 instructions: each diagonal entry is two dependent FFMA, each off-diagonal pair shares one product
-  const float wx = w * x2, wy = w * y2, wz = w * z2;
-  const float r00 = fmaf(-y2, y, fmaf(-z2, z, 1.f)), r11 = fmaf(-x2, x, fmaf(-z2, z, 1.f)), r22 = fmaf(-x2, x, fmaf(-y2, y, 1.f));
-  const float r01 = fmaf(x, y2, -wz), r10 = fmaf(x, y2, wz);
-  const float r02 = fmaf(x, z2, wy), r20 = fmaf(x, z2, -wy);
-  const float r12 = fmaf(y, z2, -wx), r21 = fmaf(y, z2, wx);
+  const T x = e.qx, y = e.qy, z = e.qz, w = e.qw;
+  const T x2 = vadd(x, x), y2 = vadd(y, y), z2 = vadd(z, z);
+  const T wx = vmul(w, x2), wy = vmul(w, y2), wz = vmul(w, z2);
+  const Neg<T> nx2 = mkneg(x2), ny2 = mkneg(y2), nz2 = mkneg(z2), nwx = mkneg(wx), nwy = mkneg(wy), nwz = mkneg(wz);
+  const T r00 = vfnma(y, ny2, vfnma1(z, nz2)), r11 = vfnma(x, nx2, vfnma1(z, nz2)), r22 = vfnma(x, nx2, vfnma1(y, ny2));
+  const T r01 = vfms(x, y2, nwz), r10 = vfma(x, y2, wz);
+  const T r02 = vfma(x, z2, wy), r20 = vfms(x, z2, nwy);
+  const T r12 = vfms(y, z2, nwx), r21 = vfma(y, z2, wx);
   if (c.state_stale) {  // QuadX.update_state runs before stepSimulation
     e.swb[0] = e.wx; e.swb[1] = e.wy; e.swb[2] = e.wz;
-    e.svb[0] = r00 * e.vx + r10 * e.vy + r20 * e.vz;
-    e.svb[1] = r01 * e.vx + r11 * e.vy + r21 * e.vz;
-    e.svb[2] = r02 * e.vx + r12 * e.vy + r22 * e.vz;
+    e.svb[0] = vfma(r20, e.vz, vfma(r10, e.vy, vmul(r00, e.vx)));
+    e.svb[1] = vfma(r21, e.vz, vfma(r11, e.vy, vmul(r01, e.vx)));
+    e.svb[2] = vfma(r22, e.vz, vfma(r12, e.vy, vmul(r02, e.vx)));
     if (last) { e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.px; e.spy = e.py; e.spz = e.pz; }  // only the final pose is read
   }
   // angular half, body frame
   // w x (I w) for a diagonal inertia is ((I2 - I1) wy wz, (I0 - I2) wz wx, (I1 - I0) wx wy); gk = -h / I_k times those
   // differences (0 when the gyroscopic term is off), so each axis is one product and two FFMA
-  const float wyz = e.wy * e.wz, wzx = e.wz * e.wx, wxy = e.wx * e.wy;
-  e.wx = fmaf(c.gk[0], wyz, fmaf(c.hI[0], tx, e.wx));
-  e.wy = fmaf(c.gk[1], wzx, fmaf(c.hI[1], ty, e.wy));
-  e.wz = fmaf(c.gk[2], wxy, fmaf(c.hI[2], tz, e.wz));
+  const T wyz = vmul(e.wy, e.wz), wzx = vmul(e.wz, e.wx), wxy = vmul(e.wx, e.wy);
+  e.wx = vfma(wyz, c.gk[0], vfma(tx, c.hI[0], e.wx));
+  e.wy = vfma(wzx, c.gk[1], vfma(ty, c.hI[1], e.wy));
+  e.wz = c.gk[2] != 0.f ? vfma(wxy, c.gk[2], vfma(tz, c.hI[2], e.wz)) : vfma(tz, c.hI[2], e.wz);
   // linear half, world frame: semi-implicit Euler
-  const float hm = c.hm;
-  e.vx = fmaf(hm, r00 * fbx + r01 * fby + r02 * fbz, e.vx);
-  e.vy = fmaf(hm, r10 * fbx + r11 * fby + r12 * fbz, e.vy);
-  e.vz = fmaf(hm, r20 * fbx + r21 * fby + r22 * fbz, e.vz) - c.hg;
+  e.vx = vfma(vfma(r02, fbz, vfma(r01, fby, vmul(r00, fbx))), c.hm, e.vx);
+  e.vy = vfma(vfma(r12, fbz, vfma(r11, fby, vmul(r10, fbx))), c.hm, e.vy);
+  e.vz = vadd(vfma(vfma(r22, fbz, vfma(r21, fby, vmul(r20, fbx))), c.hm, e.vz), -c.hg);
   // btMultiBody's +-max_coord_vel clamp: one max over the six components, the clamp itself is a cold path
-  if (fmaxf(fmaxf(fmaxf(fabsf(e.vx), fabsf(e.vy)), fmaxf(fabsf(e.vz), fabsf(e.wx))), fmaxf(fabsf(e.wy), fabsf(e.wz))) > c.vmax) {
-    e.vx = clampf(e.vx, -c.vmax, c.vmax); e.vy = clampf(e.vy, -c.vmax, c.vmax); e.vz = clampf(e.vz, -c.vmax, c.vmax);
-    e.wx = clampf(e.wx, -c.vmax, c.vmax); e.wy = clampf(e.wy, -c.vmax, c.vmax); e.wz = clampf(e.wz, -c.vmax, c.vmax);
+  if (vany(vgt(vmax(vmax(vabsmax(e.vx, e.vy), vabsmax(e.vz, e.wx)), vabsmax(e.wy, e.wz)), c.vmax))) {
+    e.vx = vclamp(e.vx, -c.vmax, c.vmax); e.vy = vclamp(e.vy, -c.vmax, c.vmax); e.vz = vclamp(e.vz, -c.vmax, c.vmax);
+    e.wx = vclamp(e.wx, -c.vmax, c.vmax); e.wy = vclamp(e.wy, -c.vmax, c.vmax); e.wz = vclamp(e.wz, -c.vmax, c.vmax);
   }
-  e.px = fmaf(c.h, e.vx, e.px);
-  e.py = fmaf(c.h, e.vy, e.py);
-  e.pz = fmaf(c.h, e.vz, e.pz);
+  e.px = vfma(e.vx, c.h, e.px);
+  e.py = vfma(e.vy, c.h, e.py);
+  e.pz = vfma(e.vz, c.h, e.pz);
   // q <- q exp(h w_b / 2): series in s = (|w| h / 2)^2 (no sqrt / sin / cos), then renormalise
   // sin(x)/x * h/2 and cos(x) in s = x^2, x = |w| h / 2 <= 0.37 at the +-100 rad/s clamp: truncation < 4e-9
   // The product is formed as q + q (dq - 1): the increment is ~|w| h / 2 relative to q, so its rounding is negligible and
   // each component takes one rounding at |q| scale instead of one per FFMA of the full product -- the attitude random
   // walk over thousands of sub-steps is what drives the open-loop position drift against the float64 oracle.
-  const float s = (e.wx * e.wx + e.wy * e.wy + e.wz * e.wz) * c.hh2;
-  const float kq = fmaf(s, fmaf(s, c.kq2, c.kq1), c.hh);
-  const float dwm1 = s * fmaf(s, fmaf(s, -1.f / 720.f, 1.f / 24.f), -0.5f);  // cos(|w| h / 2) - 1
-  const float dx = e.wx * kq, dy = e.wy * kq, dz = e.wz * kq;
-  const float nx = x + (w * dx + x * dwm1 + y * dz - z * dy);
-  const float ny = y + (w * dy - x * dz + y * dwm1 + z * dx);
-  const float nzq = z + (w * dz + x * dy - y * dx + z * dwm1);
-  const float nw = w + (w * dwm1 - x * dx - y * dy - z * dz);
-  const float inv = frsqrt(nx * nx + ny * ny + nzq * nzq + nw * nw);
-  e.qx = nx * inv; e.qy = ny * inv; e.qz = nzq * inv; e.qw = nw * inv;
-  // floor stand-in: sticky plane at floor_z (zeroes world v_xy and world w_xy)
-  if (e.pz < c.floor_z) {
-    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vx = 0.f; e.vy = 0.f;
-    const float X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
-    const float a20 = 2.f * (X * Z - W * Y), a21 = 2.f * (Y * Z + W * X), a22 = 1.f - 2.f * (X * X + Y * Y);
-    const float wzw = a20 * e.wx + a21 * e.wy + a22 * e.wz;  // world yaw rate survives
-    e.wx = a20 * wzw; e.wy = a21 * wzw; e.wz = a22 * wzw;
-    e.flags |= F_CONTACT;
-  } else {
-    e.flags &= ~F_CONTACT;
-  }
+  const T s = vmul(vfma(e.wz, e.wz, vfma(e.wy, e.wy, vmul(e.wx, e.wx))), c.hh2);
+  const T kq = vfma(s, vfma(s, c.kq2, c.kq1), c.hh);
+  const T dwm1 = vmul(s, vfma(s, vfma(s, -1.f / 720.f, 1.f / 24.f), -0.5f));  // cos(|w| h / 2) - 1
+  const T dx = vmul(e.wx, kq), dy = vmul(e.wy, kq), dz = vmul(e.wz, kq);
+  const Neg<T> ndx = mkneg(dx), ndy = mkneg(dy), ndz = mkneg(dz);
+  const T nx = vadd(x, vfnma(z, ndy, vfma(y, dz, vfma(x, dwm1, vmul(w, dx)))));
+  const T ny = vadd(y, vfnma(x, ndz, vfma(z, dx, vfma(y, dwm1, vmul(w, dy)))));
+  const T nzq = vadd(z, vfnma(y, ndx, vfma(x, dy, vfma(z, dwm1, vmul(w, dz)))));
+  const T nw = vadd(w, vfnma(z, ndz, vfnma(y, ndy, vfnma(x, ndx, vmul(w, dwm1)))));
+  const T inv = vrsqrt(vfma(nw, nw, vfma(nzq, nzq, vfma(ny, ny, vmul(nx, nx)))));
+  e.qx = vmul(nx, inv); e.qy = vmul(ny, inv); e.qz = vmul(nzq, inv); e.qw = vmul(nw, inv);
+  // floor stand-in
+  const auto below = vlt(e.pz, c.floor_z);
+  if (vany(below)) floor_contact(e, c, below);
+  e.contact = below;
   if (!c.state_stale) {
-    const float X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
-    const float a00 = 1.f - 2.f * (Y * Y + Z * Z), a01 = 2.f * (X * Y - W * Z), a02 = 2.f * (X * Z + W * Y);
-    const float a10 = 2.f * (X * Y + W * Z), a11 = 1.f - 2.f * (X * X + Z * Z), a12 = 2.f * (Y * Z - W * X);
-    const float a20 = 2.f * (X * Z - W * Y), a21 = 2.f * (Y * Z + W * X), a22 = 1.f - 2.f * (X * X + Y * Y);
+    const T X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
+    const T X2 = vadd(X, X), Y2 = vadd(Y, Y), Z2 = vadd(Z, Z);
+    const T a00 = vsub(1.f, vfma(Y2, Y, vmul(Z2, Z))), a01 = vsub(vmul(X, Y2), vmul(W, Z2)), a02 = vfma(X, Z2, vmul(W, Y2));
+    const T a10 = vfma(X, Y2, vmul(W, Z2)), a11 = vsub(1.f, vfma(X2, X, vmul(Z2, Z))), a12 = vsub(vmul(Y, Z2), vmul(W, X2));
+    const T a20 = vsub(vmul(X, Z2), vmul(W, Y2)), a21 = vfma(Y, Z2, vmul(W, X2)), a22 = vsub(1.f, vfma(X2, X, vmul(Y2, Y)));
     e.swb[0] = e.wx; e.swb[1] = e.wy; e.swb[2] = e.wz;
-    e.svb[0] = a00 * e.vx + a10 * e.vy + a20 * e.vz;
-    e.svb[1] = a01 * e.vx + a11 * e.vy + a21 * e.vz;
-    e.svb[2] = a02 * e.vx + a12 * e.vy + a22 * e.vz;
+    e.svb[0] = vfma(a20, e.vz, vfma(a10, e.vy, vmul(a00, e.vx)));
+    e.svb[1] = vfma(a21, e.vz, vfma(a11, e.vy, vmul(a01, e.vx)));
+    e.svb[2] = vfma(a22, e.vz, vfma(a12, e.vy, vmul(a02, e.vx)));
     if (last) { e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.px; e.spy = e.py; e.spz = e.pz; }
   }
 }
@@ -499,7 +596,7 @@ __device__ __forceinline__ void vision_point(const Env& e, const DevConfig& c, b
 __device__ __forceinline__ void respawn(Env& e, const DevConfig& c, uint32_t k0, uint32_t k1) {
   float px = c.start_pos[0], py = c.start_pos[1], pz = c.start_pos[2], yaw = c.start_rpy[2];
   if (c.spawn_pos_noise != 0.f || c.spawn_yaw_noise != 0.f) {
-    const uint4 b = philox4x32_10(make_uint4(0u, STREAM_SPAWN, e.rng_ctr, 0u), k0, k1);
+    const uint4 b = env_philox(make_uint4(0u, STREAM_SPAWN, e.rng_ctr, 0u), k0, k1);
     px = fmaf(c.spawn_pos_noise, 2.f * u01(b.x) - 1.f, px);
     py = fmaf(c.spawn_pos_noise, 2.f * u01(b.y) - 1.f, py);
     pz = fmaf(c.spawn_pos_noise, 2.f * u01(b.z) - 1.f, pz);
@@ -522,7 +619,8 @@ __device__ __forceinline__ void respawn(Env& e, const DevConfig& c, uint32_t k0,
 #pragma unroll
   for (int a = 0; a < 3; ++a) { e.pi[a] = 0.f; e.pe[a] = 0.f; e.swb[a] = 0.f; e.svb[a] = 0.f; }
   e.sqx = e.qx; e.sqy = e.qy; e.sqz = e.qz; e.sqw = e.qw; e.spx = px; e.spy = py; e.spz = pz;
-  e.flags = (pz <= c.floor_z) ? F_CONTACT : 0u;
+  e.contact = pz <= c.floor_z;
+  e.flags = 0u;
   e.step_count = 0;
   e.pcx = e.pcy = e.parea = e.pratio = 0.f;
   e.ep_ret = 0.f;

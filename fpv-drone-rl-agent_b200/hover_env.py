@@ -26,8 +26,8 @@ from ._lib import QX_OBS_BF16, QX_OBS_F32, QX_STATE_WORDS, QX_STATE_WORDS_CASCAD
 # names of the 44 carried state words, in plane order (see csrc/qx_model.cuh Env)
 STATE_FIELDS = (
     "px py pz qx qy qz qw vx vy vz wbx wby wbz thr0 thr1 thr2 thr3 pid_i0 pid_i1 pid_i2 pid_e0 pid_e1 pid_e2 "
-    "s_wb0 s_wb1 s_wb2 s_vb0 s_vb1 s_vb2 prev_roll prev_pitch prev_yaw prev_a0 prev_a1 prev_a2 prev_a3 "
-    "prev_cx prev_cy prev_area prev_ratio step_count rng_ctr ep_return flags"
+    "s_wb0 s_wb1 s_wb2 s_vb0 s_vb1 s_vb2 step_count rng_ctr flags prev_roll prev_pitch prev_yaw ep_return "
+    "prev_a0 prev_a1 prev_a2 prev_a3 prev_cx prev_cy prev_area prev_ratio"
 ).split()
 assert len(STATE_FIELDS) == QX_STATE_WORDS
 # flight_mode != 0: the outer loops' (integral, previous error) memory and the position row of the state snapshot

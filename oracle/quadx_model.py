@@ -124,7 +124,8 @@ class QuadXParams:
 
 
 # ----------------------------------------------------------------------------
-# Philox4x32-10 counter RNG (identical integer stream in numpy, C and CUDA)
+# Philox4x32-R counter RNG (identical integer stream in numpy, C and CUDA).  The env's noise uses R = 7 rounds
+# (Random123: the smallest round count that passes BigCrush; csrc/qx_model.cuh kEnvPhiloxRounds).
 # ----------------------------------------------------------------------------
 _M0 = np.uint64(0xD2511F53)
 _M1 = np.uint64(0xCD9E8D57)
@@ -137,13 +138,16 @@ STREAM_RESET = 1  # motor noise during the 10 idle Aviary.step() of a reset
 STREAM_SPAWN = 2  # reset pose noise
 
 
-def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
+ENV_PHILOX_ROUNDS = 7
+
+
+def philox4x32(ctr: np.ndarray, key: np.ndarray, rounds: int = ENV_PHILOX_ROUNDS) -> np.ndarray:
     """ctr uint32[N,4], key uint32[N,2] -> uint32[N,4]."""
     c = [ctr[:, i].astype(np.uint64) for i in range(4)]
     k0 = key[:, 0].astype(np.uint32).copy()
     k1 = key[:, 1].astype(np.uint32).copy()
     with np.errstate(over="ignore"):
-        for r in range(10):
+        for r in range(rounds):
             if r > 0:
                 k0 = (k0 + _W0).astype(np.uint32)
                 k1 = (k1 + _W1).astype(np.uint32)
@@ -178,12 +182,12 @@ def u01_16(x: np.ndarray) -> np.ndarray:
 def normal4(w: np.ndarray) -> np.ndarray:
     """Two 32-bit words [N,2] -> four N(0,1) [N,4]: each word feeds one
     Box-Muller pair, low 16 bits -> radius, high 16 bits -> angle; outputs are
-    (r_a cos, r_a sin, r_b cos, r_b sin) for motors 0..3.  One Philox4x32-10
-    call (4 words) therefore serves two physics sub-steps."""
+    (r_a cos, r_a sin, r_b cos, r_b sin) for motors 0..3, with the angle 2 pi u - pi in (-pi, pi) (where the GPU's
+    MUFU sine / cosine are most accurate).  One Philox call (4 words) therefore serves two physics sub-steps."""
     lo = w & np.uint32(0xFFFF)
     hi = w >> np.uint32(16)
     r = np.sqrt(-2.0 * np.log(u01_16(lo)))
-    t = 2.0 * np.pi * u01_16(hi)
+    t = 2.0 * np.pi * u01_16(hi) - np.pi
     return np.stack([r[:, 0] * np.cos(t[:, 0]), r[:, 0] * np.sin(t[:, 0]), r[:, 1] * np.cos(t[:, 1]), r[:, 1] * np.sin(t[:, 1])], axis=1)
 
 
@@ -488,7 +492,7 @@ class NoiseSource:
         sc = step_ctr.astype(np.uint64)
         ctr[:, 2] = (sc & _MASK).astype(np.uint32)
         ctr[:, 3] = (sc >> np.uint64(32)).astype(np.uint32)
-        return philox4x32_10(ctr, self._key)
+        return philox4x32(ctr, self._key)
 
     def normals(self, sub: int, stream: int, step_ctr: np.ndarray):
         """Motor noise of sub-step ``sub``: Philox counter word 0 is sub >> 1,

@@ -64,9 +64,9 @@ typedef struct {
 
 enum { STREAM_STEP = 0, STREAM_RESET = 1, STREAM_SPAWN = 2 };
 
-/* ---- Philox4x32-10 (oracle/quadx_model.py philox4x32_10) ------------------ */
+/* ---- Philox4x32-7 (oracle/quadx_model.py philox4x32, ENV_PHILOX_ROUNDS) ---- */
 static void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
@@ -88,7 +88,7 @@ static void normals(const Orc* o, int64_t i, int sub, uint32_t stream, uint64_t 
   env_bits(o, i, (uint32_t)(sub >> 1), stream, ctr, b);
   for (int k = 0; k < 2; ++k) {
     uint32_t w = b[2 * (sub & 1) + k];
-    double r = sqrt(-2.0 * log(u01_16(w & 0xFFFFu))), t = 2.0 * M_PI * u01_16(w >> 16);
+    double r = sqrt(-2.0 * log(u01_16(w & 0xFFFFu))), t = 2.0 * M_PI * u01_16(w >> 16) - M_PI;
     nz[2 * k] = r * cos(t);
     nz[2 * k + 1] = r * sin(t);
   }

@@ -239,3 +239,38 @@ def test_inline_reset_equals_reset_queue_path(pkg):
     assert float((o1 - o2).abs().max()) <= 1e-4 and float((r1 - r2).abs().max()) <= 1e-3
     done = te1.bool()
     assert float((t1[done] - t2[done]).abs().max()) <= 1e-4  # terminal observations of the finished envs
+
+
+def test_two_env_kernel_is_bitwise_the_one_env_kernel(pkg, monkeypatch):
+    """The sub-step code is written once over a lane type (csrc/qx_lanes.cuh): float = one env per thread, float2 = two
+    envs per thread on packed FFMA2 / FMUL2 / FADD2.  Both perform the same IEEE operations per env, so the two kernels
+    must agree bit for bit -- states, observations, rewards, flags, episode statistics -- through resets, for a batch
+    size that leaves a thread with a single env, with the reference constants and with the generic kernels."""
+    n, steps = 40000 + 77, 70
+    g = torch.Generator(device="cuda").manual_seed(11)
+    acts = (torch.rand(steps, n, 4, device="cuda", generator=g) * 2 - 1) * torch.tensor([0.5, 0.5, 0.5, 1.0], device="cuda")
+    acts[..., 3] = acts[..., 3] * 0.4 + 0.05
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("QX_FORCE_GENERIC", "1")
+        out = []
+        for pair in ("0", "1"):
+            monkeypatch.setenv("QX_PAIR", pair)
+            sim = pkg.QuadXSim(n, pkg.default_config(), seed=5)  # floor start, idle steps, auto-reset, noise
+            d = sim.device
+            obs = torch.zeros(steps, n, 20, device=d); rew = torch.zeros(steps, n, device=d)
+            te = torch.zeros(steps, n, dtype=torch.uint8, device=d); tr = torch.zeros(steps, n, dtype=torch.uint8, device=d)
+            o0 = torch.zeros(n, 20, device=d)
+            sim.reset(o0)
+            for k in range(steps):
+                sim.step(acts[k], obs[k], rew[k], te[k], tr[k], split=True)
+            torch.cuda.synchronize()
+            out.append((obs, rew, te, tr, sim.get_state(), sim.episode_stats()))
+            sim.close()
+        (o1, r1, te1, tr1, s1, e1), (o2, r2, te2, tr2, s2, e2) = out
+        assert int(te1.sum()) > n // 2  # episodes ended (floor rule) and restarted
+        assert torch.equal(te1, te2) and torch.equal(tr1, tr2) and e1[1:] == e2[1:]
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)), float((o1 - o2).abs().max())
+        assert torch.equal(r1.view(torch.int32), r2.view(torch.int32)), float((r1 - r2).abs().max())
+        for k in s1:
+            assert np.array_equal(s1[k].view(np.uint32), s2[k].view(np.uint32)), k

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Time the hover env step for the kernel variants (GPU box).  Usage: python tools/k1_variants.py [envs] [steps]
+Each variant runs in a fresh handle: QX_PAIR (0: one env per thread, 1: two) and QX_PAIR_SHAPE are read at qx_create."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build()
+import fpv_drone_rl_agent_b200 as pkg  # noqa: E402
+
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+dev = torch.device("cuda", 0)
+g = torch.Generator(device="cpu").manual_seed(0)
+acts = torch.rand(8, E, 4, generator=g) * 2 - 1
+acts[..., :3] *= 0.3
+acts[..., 3] = (2 * 0.4952 - 1) + 0.3 * acts[..., 3]
+acts = acts.to(dev)
+obs = torch.zeros(E, 20, device=dev)
+rew = torch.zeros(E, device=dev)
+te = torch.zeros(E, dtype=torch.uint8, device=dev)
+tr = torch.zeros(E, dtype=torch.uint8, device=dev)
+variants = [("one_env", {"QX_PAIR": "0"})]
+variants += [(f"pair_packed_shape{k}", {"QX_PAIR": "1", "QX_PAIR_SHAPE": str(k), "QX_PAIR_PACKED": "1"}) for k in range(4)]
+variants += [(f"pair_scalar_shape{k}", {"QX_PAIR": "1", "QX_PAIR_SHAPE": str(k), "QX_PAIR_PACKED": "0"}) for k in range(4)]
+only = os.environ.get("K1_ONLY")
+if only:
+    variants = [v for v in variants if v[0] in only.split(",")]
+res = {}
+for name, env in variants:
+    os.environ.update(env)
+    cfg = pkg.default_config()
+    cfg.update(start_pos=[0, 0, 1.0], spawn_throttle=0.4952, auto_reset=1, noise=1)
+    sim = pkg.QuadXSim(E, cfg, seed=1234, device=dev)
+    sim.reset(obs)
+    for k in range(5):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(STEPS + 1)]
+    ev[0].record()
+    for k in range(STEPS):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    per = sorted(ev[k].elapsed_time(ev[k + 1]) * 1e3 for k in range(STEPS))
+    res[name] = {"mean_us": sum(per) / len(per), "min_us": per[0], "median_us": per[len(per) // 2], "p90_us": per[int(0.9 * len(per))],
+                 "frac_of_hbm_roofline_mean": 358.0 * E / (sum(per) / len(per) * 1e-6) / 6538.6e9, "checksum": float(rew.double().sum())}
+    sim.close()
+    print(name, json.dumps(res[name]), flush=True)
