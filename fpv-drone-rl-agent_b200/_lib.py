@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         "qx_step_host": (C.c_int, [vp, f32p, f32p, f32p, u8p, u8p, f32p]),
         "qx_get_state": (C.c_int, [vp, vp]),
         "qx_set_state": (C.c_int, [vp, vp]),
+        "qx_get_flags": (C.c_int, [vp, i64, i64, vp]),
         "qx_episode_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64), i32]),
         "qx_nonfinite_count": (C.c_int, [vp, C.POINTER(i64)]),
         "qx_num_envs": (i64, [vp]),
@@ -113,6 +114,14 @@ def lib() -> C.CDLL:
         "ppo_running_stats_scratch_bytes": (i64, [i32]),
         "ppo_reward_normalize": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp]),
         "ppo_test_gemm": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+        "ppo_test_gemm_mn": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
+        "ppo_update_num_params": (i32, [i32, i32]),
+        "ppo_update_workspace_bytes": (i64, [i32, i32]),
+        "ppo_update_minibatch": (C.c_int, [C.POINTER(PpoPolicy), vp, vp, vp, vp, vp, vp, i32, i64, f32, f32, f32, i32, vp, vp, vp, vp]),
+        "ppo_update_grad_norm": (C.c_int, [vp, i32, f32, vp, vp]),
+        "ppo_update_adam": (C.c_int, [vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, C.POINTER(PpoPolicy), vp, vp]),
+        "ppo_update_step_count": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
+        "qx_debug_clock_probe": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
@@ -125,11 +134,12 @@ def lib() -> C.CDLL:
 
 EXPORTED = [
     "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
-    "qx_get_state", "qx_set_state", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words", "qx_uses_reference_constants", "qx_config_matches_reference_constants",
+    "qx_get_state", "qx_set_state", "qx_get_flags", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words", "qx_uses_reference_constants", "qx_config_matches_reference_constants",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
-                "ppo_reward_normalize", "ppo_test_gemm"]
+                "ppo_reward_normalize", "ppo_test_gemm", "ppo_test_gemm_mn", "ppo_update_num_params", "ppo_update_workspace_bytes",
+                "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count"]
 
 
 class QxError(RuntimeError):

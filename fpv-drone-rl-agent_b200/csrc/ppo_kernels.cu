@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 
 #include "../../include/ppo_b200.h"
@@ -685,13 +686,20 @@ extern "C" int ppo_test_gemm(const void* a, const void* b, float* d, int32_t n, 
 }
 
 static int launch_forward(ppo::FwdArgs& a, int64_t max_rows, void* stream) {
-  static int sms = 0;
+  // per device: SM count and the one-time opt-in to ~200 KB of dynamic shared memory (the attribute is per device; the cached
+  // value is set only after the call succeeded, so a failure is retried)
+  static std::atomic<int> sms_of[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return pfail(QX_ECUDA, "ppo_policy_forward: cannot query the current device");
+  int sms = sms_of[dev].load(std::memory_order_acquire);
   if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      return pfail(QX_ECUDA, "ppo_policy_forward: cannot query the SM count");
     if (cudaFuncSetAttribute(ppo::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppo::kSmTotal) != cudaSuccess)
       return pfail(QX_ECUDA, "ppo_policy_forward: cannot reserve shared memory");
+    sms_of[dev].store(n, std::memory_order_release);
+    sms = n;
   }
   const int64_t tiles = (max_rows + 127) / 128, ctas = (tiles + ppo::kSlots - 1) / ppo::kSlots;
   const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);

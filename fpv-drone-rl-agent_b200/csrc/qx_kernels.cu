@@ -73,10 +73,12 @@ struct StepArgs {
   int64_t obs_stride;
   int32_t k;
   int32_t obs_bf16;
+  int32_t stream_stores;    // hot kernel: 1 = observations / reward / flags with evict-first stores (write-once data), 2 = the state planes too
+  int32_t prefetch_blocks;  // hot kernel: each block asks L2 for the planes of the block this many positions ahead (0 = off)
 };
 
 template <int DIM>
-__device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int64_t row, int64_t stride, bool bf16) {
+__device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int64_t row, int64_t stride, bool bf16, bool cs = false) {
   static_assert(DIM % 4 == 0, "obs rows are written as 16-byte / 8-byte vectors");
   if (bf16) {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + row * stride;
@@ -87,7 +89,8 @@ __device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int
         uint2 v;
         v.x = *reinterpret_cast<uint32_t*>(&a);
         v.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(p + j) = v;
+        if (cs) __stcs(reinterpret_cast<uint2*>(p + j), v);
+        else *reinterpret_cast<uint2*>(p + j) = v;
       }
     } else {
 #pragma unroll
@@ -97,7 +100,10 @@ __device__ __forceinline__ void write_obs(const float (&o)[DIM], void* base, int
     float* p = reinterpret_cast<float*>(base) + row * stride;
     if ((stride & 3) == 0) {
 #pragma unroll
-      for (int j = 0; j < DIM; j += 4) *reinterpret_cast<float4*>(p + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      for (int j = 0; j < DIM; j += 4) {
+        if (cs) __stcs(reinterpret_cast<float4*>(p + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+        else *reinterpret_cast<float4*>(p + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < DIM; ++j) p[j] = o[j];
@@ -272,9 +278,15 @@ __device__ __forceinline__ bool reward_and_flags(Env& e, const DevConfig& c, con
   e.rng_ctr += 1u;
   e.ep_ret += reward;
   const bool term = fl & F_TERM, trunc = fl & F_TRUNC;
-  a.reward[row] = reward;
-  a.terminated[row] = term ? 1 : 0;
-  a.truncated[row] = trunc ? 1 : 0;
+  if (a.stream_stores) {  // write-once results: evict-first, so that they do not displace the state planes in L2
+    __stcs(a.reward + row, reward);
+    __stcs(a.terminated + row, (uint8_t)(term ? 1 : 0));
+    __stcs(a.truncated + row, (uint8_t)(trunc ? 1 : 0));
+  } else {
+    a.reward[row] = reward;
+    a.terminated[row] = term ? 1 : 0;
+    a.truncated[row] = trunc ? 1 : 0;
+  }
   return c.auto_reset && (term || trunc);
 }
 
@@ -423,14 +435,16 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
 // MODE_STEP_DEFER.  An env that is already finished on entry (only possible without auto_reset, or when the caller
 // skipped qx_step_end) sends its thread through the one-env code instead.
 // ===========================================================================
-// launch shapes (threads per block, resident blocks per SM): 3 x 128 threads = 168 registers, 2 x 128 = 255 registers.
-// QX_PAIR_SHAPE at qx_create picks one (tuning / profiling); the default is the fastest measured on B200.
-template <int SHAPE> struct PairShape;
-template <> struct PairShape<0> { static constexpr int kBlock = 128, kMinBlocks = 3; };
-template <> struct PairShape<1> { static constexpr int kBlock = 128, kMinBlocks = 2; };
-template <> struct PairShape<2> { static constexpr int kBlock = 64, kMinBlocks = 6; };
-template <> struct PairShape<3> { static constexpr int kBlock = 64, kMinBlocks = 4; };
-constexpr int kPairShapes = 4;
+// launch shapes (threads per block, resident blocks per SM -> register cap 65536 / (threads x blocks)).
+// QX_SHAPE at qx_create picks one (tuning / profiling); the defaults are the fastest measured on B200.
+template <int SHAPE> struct HotShape;
+template <> struct HotShape<0> { static constexpr int kBlock = 128, kMinBlocks = 3; };  // 168 registers
+template <> struct HotShape<1> { static constexpr int kBlock = 128, kMinBlocks = 2; };  // 255
+template <> struct HotShape<2> { static constexpr int kBlock = 64, kMinBlocks = 6; };   // 168
+template <> struct HotShape<3> { static constexpr int kBlock = 128, kMinBlocks = 4; };  // 128
+template <> struct HotShape<4> { static constexpr int kBlock = 128, kMinBlocks = 5; };  // 96
+template <> struct HotShape<5> { static constexpr int kBlock = 128, kMinBlocks = 6; };  // 80
+constexpr int kHotShapes = 6;
 
 template <bool REF>
 __device__ __noinline__ void run_env_cold(const DevConfig& cparam, const StepArgs& a, const int64_t i) {
@@ -441,38 +455,82 @@ __device__ __noinline__ void run_env_cold(const DevConfig& cparam, const StepArg
   else run_env<MODE_STEP_INLINE, QX_TASK_HOVER, false>(c, a, i);
 }
 
-template <bool REF, int SHAPE, bool PK>
-__global__ void __launch_bounds__(PairShape<SHAPE>::kBlock, PairShape<SHAPE>::kMinBlocks) quadx_step_pair_kernel(const __grid_constant__ DevConfig cparam,
-                                                                                                                    const __grid_constant__ StepArgs a) {
-  constexpr int kPairBlock = PairShape<SHAPE>::kBlock;
+// one lane of a two-lane value, or the value itself
+template <int HALF> QX_DI float half_of(float v) { return v; }
+template <int HALF, bool PK> QX_DI float half_of(P2<PK> v) { return HALF ? v.y : v.x; }
+template <class V> struct LaneOps;
+template <> struct LaneOps<float> {
+  static QX_DI float make(float a, float) { return a; }
+  static QX_DI void pack(Core<float>& p, const Core<float>& a, const Core<float>&) { p = a; }
+};
+template <bool PK> struct LaneOps<P2<PK>> {
+  static QX_DI P2<PK> make(float a, float b) { return P2<PK>{a, b}; }
+  static QX_DI void pack(Core<P2<PK>>& p, const Core<float>& a, const Core<float>& b) { pack_core(p, a, b); }
+};
+template <int HALF> QX_DI void unpack_lane(Core<float>& a, const Core<float>& p) { a = p; }
+template <int HALF, bool PK> QX_DI void unpack_lane(Core<float>& a, const Core<P2<PK>>& p) { unpack_core<HALF>(a, p); }
+
+// once-per-step epilogue of one env of the hot kernel: observation, reward, flags, episode end, state store
+template <bool REF>
+QX_DI void hot_epilogue(Env& e, const DevConfig& c, const StepArgs& a, const int64_t i, const float4 av) {
+  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
+  load_env_tail(e, a.state, a.n, i);  // the epilogue planes are loaded only now: they do not occupy registers across the sub-step loop
+  const float act[4] = {av.x, av.y, av.z, av.w};
+  float obs[OBS_DIM];
+  ObsAux x;
+  build_obs<QX_TASK_HOVER>(e, c, act, 0, true, obs, x);
+  const bool done = reward_and_flags<QX_TASK_HOVER, false>(e, c, a, i, act, true, obs, x);
+  if (done) episode_end<true>(e, a, i, obs);
+  else if (a.obs) write_obs(obs, a.obs, i, a.obs_stride, a.obs_bf16 != 0, a.stream_stores != 0);
+  if (a.stream_stores >= 2) store_env<true>(e, a.state, a.n, i);
+  else store_env(e, a.state, a.n, i);
+}
+
+// V = float: one env per thread;  V = P2<true> / P2<false>: two envs per thread, packed / scalar arithmetic
+template <bool REF, int SHAPE, class V>
+__global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMinBlocks) quadx_step_hot_kernel(const __grid_constant__ DevConfig cparam,
+                                                                                                                 const __grid_constant__ StepArgs a) {
+  constexpr int kB = HotShape<SHAPE>::kBlock, kLanes = Lane<V>::N;
   DevConfig cref = cparam;
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
-  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
   const int64_t end = a.env_begin + a.env_count;
-  const int64_t i0 = a.env_begin + (int64_t)blockIdx.x * (2 * kPairBlock) + threadIdx.x;
+  const int64_t i0 = a.env_begin + (int64_t)blockIdx.x * (kLanes * kB) + threadIdx.x;
+  // L2 prefetch (TMA, no shared memory, no barrier) of the state planes and actions of the block that will take this
+  // block's place on the SM: in steady state DRAM is busy writing back the previous step's results and the first loads
+  // of a block are its longest stall -- they become L2 hits
+  if (a.prefetch_blocks > 0 && threadIdx.x < kBasePlanes + 1) {
+    const int64_t j0 = a.env_begin + ((int64_t)blockIdx.x + a.prefetch_blocks) * (kLanes * kB);
+    if (j0 < end) {
+      const int64_t cnt = (end - j0 < (int64_t)kLanes * kB) ? end - j0 : (int64_t)kLanes * kB;
+      const void* src = threadIdx.x < kBasePlanes ? (const void*)(a.state + (int64_t)threadIdx.x * a.n + j0)
+                                                   : (const void*)(reinterpret_cast<const float4*>(a.actions) + j0);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(cnt * 16)) : "memory");
+    }
+  }
   if (i0 >= end) return;
-  const bool has1 = i0 + kPairBlock < end;
-  const int64_t i1 = has1 ? i0 + kPairBlock : i0;  // a thread without a second env computes its first one twice, stores it once
+  const bool has1 = kLanes == 2 && i0 + kB < end;
+  const int64_t i1 = has1 ? i0 + kB : i0;  // a thread without a second env computes its first one twice, stores it once
   Env e0, e1;
   load_env_loop(e0, a.state, a.n, i0);
-  load_env_loop(e1, a.state, a.n, i1);
-  if ((e0.flags | e1.flags) & (F_TERM | F_TRUNC)) {  // cold: a finished env does not step (hover.py:347-348)
+  if (kLanes == 2) load_env_loop(e1, a.state, a.n, i1);
+  if ((e0.flags | (kLanes == 2 ? e1.flags : 0u)) & (F_TERM | F_TRUNC)) {  // cold: a finished env does not step (hover.py:347-348)
     run_env_cold<REF>(cparam, a, i0);
     if (has1) run_env_cold<REF>(cparam, a, i1);
     return;
   }
-  const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0), av1 = __ldg(reinterpret_cast<const float4*>(a.actions) + i1);
+  const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0);
+  const float4 av1 = kLanes == 2 ? __ldg(reinterpret_cast<const float4*>(a.actions) + i1) : av0;
   {
-    typedef P2<PK> V;
+    typedef LaneOps<V> L;
     Core<V> p;
-    pack_core(p, e0, e1);
+    L::pack(p, e0, e1);
     V sp[4];  // hover.py:337-341
-    sp[0] = vmul(V{av0.x, av1.x}, c.act_scale[0]);
-    sp[1] = vmul(V{av0.y, av1.y}, c.act_scale[1]);
-    sp[2] = vmul(V{av0.z, av1.z}, c.act_scale[2]);
-    sp[3] = vfma(V{av0.w, av1.w}, c.thrust_scale, c.thrust_bias);
-    sp[3] = V{__saturatef(sp[3].x), __saturatef(sp[3].y)};  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
+    sp[0] = vmul(L::make(av0.x, av1.x), c.act_scale[0]);
+    sp[1] = vmul(L::make(av0.y, av1.y), c.act_scale[1]);
+    sp[2] = vmul(L::make(av0.z, av1.z), c.act_scale[2]);
+    sp[3] = vfma(L::make(av0.w, av1.w), c.thrust_scale, c.thrust_bias);
+    sp[3] = L::make(__saturatef(half_of<0>(sp[3])), __saturatef(half_of<1>(sp[3])));  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
     const uint32_t k0a = c.seed_lo ^ (c.env_lo + (uint32_t)i0), k0b = c.seed_lo ^ (c.env_lo + (uint32_t)i1);
     const uint32_t k1a = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
     const uint32_t k1b = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i1) >> 32));
@@ -481,43 +539,35 @@ __global__ void __launch_bounds__(PairShape<SHAPE>::kBlock, PairShape<SHAPE>::kM
     for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call per env, two physics sub-steps
       V apwm[4];
       control_update<V>(p, c, sp, apwm);
-      V nz[4] = {V{0.f, 0.f}, V{0.f, 0.f}, V{0.f, 0.f}, V{0.f, 0.f}};
+      V nz[4] = {splat<V>(0.f), splat<V>(0.f), splat<V>(0.f), splat<V>(0.f)};
       uint4 ba = make_uint4(0u, 0u, 0u, 0u), bb = ba;
       if (c.noise) {
         ba = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e0.rng_ctr, 0u), k0a, k1a);
-        bb = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e1.rng_ctr, 0u), k0b, k1b);
-        normal4_scaled<V>(make_uint2(ba.x, bb.x), make_uint2(ba.y, bb.y), c.noise_k, nz);
+        if (kLanes == 2) bb = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e1.rng_ctr, 0u), k0b, k1b);
+        if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.x, bb.x), make_uint2(ba.y, bb.y), c.noise_k, nz);
+        else normal4_scaled<V>(ba.x, ba.y, c.noise_k, nz);
       }
       physics_substep<V>(p, c, apwm, nz, false);
-      if (c.noise) normal4_scaled<V>(make_uint2(ba.z, bb.z), make_uint2(ba.w, bb.w), c.noise_k, nz);
+      if (c.noise) {
+        if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.z, bb.z), make_uint2(ba.w, bb.w), c.noise_k, nz);
+        else normal4_scaled<V>(ba.z, ba.w, c.noise_k, nz);
+      }
       physics_substep<V>(p, c, apwm, nz, j + 2 == nsub);
     }
-    unpack_core<0>(e0, p);
-    unpack_core<1>(e1, p);
+    unpack_lane<0>(e0, p);
+    if (kLanes == 2) unpack_lane<1>(e1, p);
   }
-  // ---- per env: observation, reward, flags, episode end; the epilogue planes are loaded only now
-  {
-    load_env_tail(e0, a.state, a.n, i0);
-    const float act[4] = {av0.x, av0.y, av0.z, av0.w};
-    float obs[OBS_DIM];
-    ObsAux x;
-    build_obs<QX_TASK_HOVER>(e0, c, act, 0, true, obs, x);
-    const bool done = reward_and_flags<QX_TASK_HOVER, false>(e0, c, a, i0, act, true, obs, x);
-    if (done) episode_end<true>(e0, a, i0, obs);
-    else if (a.obs) write_obs(obs, a.obs, i0, a.obs_stride, a.obs_bf16 != 0);
-    store_env(e0, a.state, a.n, i0);
-  }
-  if (has1) {
-    load_env_tail(e1, a.state, a.n, i1);
-    const float act[4] = {av1.x, av1.y, av1.z, av1.w};
-    float obs[OBS_DIM];
-    ObsAux x;
-    build_obs<QX_TASK_HOVER>(e1, c, act, 0, true, obs, x);
-    const bool done = reward_and_flags<QX_TASK_HOVER, false>(e1, c, a, i1, act, true, obs, x);
-    if (done) episode_end<true>(e1, a, i1, obs);
-    else if (a.obs) write_obs(obs, a.obs, i1, a.obs_stride, a.obs_bf16 != 0);
-    store_env(e1, a.state, a.n, i1);
-  }
+  hot_epilogue<REF>(e0, c, a, i0, av0);
+  if (has1) hot_epilogue<REF>(e1, c, a, i1, av1);
+}
+
+// debug / measurement hook: SM clock and wall clock of one thread, so that two samples give the average SM frequency
+// of the interval between them (clock droop under sustained load does not show in NVML's slow readings)
+__global__ void clock_probe_kernel(unsigned long long* out) {
+  unsigned long long ns;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+  out[0] = (unsigned long long)clock64();
+  out[1] = ns;
 }
 
 }  // namespace qx
@@ -532,10 +582,12 @@ struct QxHandle {
   int device;
   int planes;  // float4 state planes: 11, or 17 when flight_mode != 0
   bool ref_constants;  // the model constants equal the reference's literals bit for bit: run the specialised kernels
-  bool pair_ok;        // hover, flight mode 0, control every 2nd sub-step: the two-envs-per-thread step kernel applies
-  int pair_mode;       // QX_PAIR env var at qx_create: -1 default (large batches), 0 never, 1 always
-  int pair_shape;      // QX_PAIR_SHAPE env var at qx_create: launch shape of the two-env kernel
-  bool pair_packed;    // QX_PAIR_PACKED env var (default 1): FFMA2 / FMUL2 / FADD2, or the same two-env code on scalar FP instructions
+  bool hot_ok;         // hover, flight mode 0, control every 2nd sub-step: the lean one-step kernel applies
+  int hot_mode;        // QX_HOT env var at qx_create: -1 default (large batches), 0 never, 1 always
+  int hot_lanes;       // QX_LANES: 1 one env per thread, 2 two envs per thread on packed f32x2, 3 two envs on scalar FP instructions
+  int hot_shape;       // QX_SHAPE: launch shape (HotShape)
+  int stream_stores;   // QX_STREAM_STORES: 0 plain stores, 1 evict-first for obs / reward / flags, 2 also for the state planes
+  int prefetch_blocks; // QX_PREFETCH: L2 prefetch distance of the hot kernel in blocks (-1: one wave of resident blocks, 0: off)
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
@@ -597,8 +649,11 @@ extern "C" int qx_default_config(int32_t task, QxConfig* c) {
   c->action_scale[0] = 30.f; c->action_scale[1] = 30.f; c->action_scale[2] = -30.f;
   c->spawn_yaw_noise = task == QX_TASK_YAW ? 3.14159265f : 0.f;  /* yaw.py:79 U(-pi, pi) */
   if (task == QX_TASK_YAW) {
-    /* main.py:8-23 / yaw.py: default PyFlyt camera (20 deg up), red sphere at (2, 0, 1), one Aviary.step per env step */
-    c->cam_tilt_up_deg = 20.f;
+    /* main.py:8-23 / yaw.py: default PyFlyt camera (camera_angle_degrees = +20), red sphere at (2, 0, 1), one Aviary.step per
+       env step.  Sign: hover.py's camera_angle_degrees = -25 is read as 25 deg UP (the only reading under which the
+       panel and the reference's target_area / target_ratio are in view), i.e. PyFlyt's positive angle points DOWN -- so the
+       default +20 is 20 deg down.  From the ground (yaw.py never lifts off) the sphere then sits just above the image. */
+    c->cam_tilt_up_deg = -20.f;
     c->panel[0] = 2.f; c->panel[1] = 0.f; c->panel[2] = 1.f;
     c->agent_dt = 1.0f / 120.f;
   }
@@ -685,6 +740,7 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
 }
 
 static bool matches_ref_constants(const qx::DevConfig& d);
+constexpr int kDefaultHotLanes = 1, kDefaultShape1 = 4, kDefaultShape2 = 0, kDefaultPrefetch = 0;
 
 extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uint64_t env_id0, int device, QxHandle** out) {
   if (!cfg || !out || n_envs <= 0) return fail(QX_EINVAL, "qx_create: bad arguments");
@@ -705,14 +761,15 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   cudaSetDevice(device);
   h->planes = cfg->flight_mode != 0 ? qx::kCascadePlanes : qx::kBasePlanes;
   h->ref_constants = !getenv("QX_FORCE_GENERIC") && matches_ref_constants(h->dev);
-  h->pair_ok = cfg->task == QX_TASK_HOVER && cfg->flight_mode == 0 && h->dev.ctrl_every == 2 && (h->dev.n_sub_step & 1) == 0 && h->dev.n_sub_step > 0;
-  const char* pm = getenv("QX_PAIR");
-  h->pair_mode = pm ? atoi(pm) : -1;
-  const char* ps = getenv("QX_PAIR_SHAPE");
-  h->pair_shape = ps ? atoi(ps) : 0;
-  if (h->pair_shape < 0 || h->pair_shape >= qx::kPairShapes) h->pair_shape = 0;
-  const char* pp = getenv("QX_PAIR_PACKED");
-  h->pair_packed = pp ? atoi(pp) != 0 : true;
+  h->hot_ok = cfg->task == QX_TASK_HOVER && cfg->flight_mode == 0 && h->dev.ctrl_every == 2 && (h->dev.n_sub_step & 1) == 0 && h->dev.n_sub_step > 0;
+  auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+  h->hot_mode = env_int("QX_HOT", -1);
+  h->hot_lanes = env_int("QX_LANES", kDefaultHotLanes);
+  if (h->hot_lanes < 1 || h->hot_lanes > 3) h->hot_lanes = kDefaultHotLanes;
+  h->hot_shape = env_int("QX_SHAPE", h->hot_lanes == 1 ? kDefaultShape1 : kDefaultShape2);
+  if (h->hot_shape < 0 || h->hot_shape >= qx::kHotShapes) h->hot_shape = h->hot_lanes == 1 ? kDefaultShape1 : kDefaultShape2;
+  h->prefetch_blocks = env_int("QX_PREFETCH", kDefaultPrefetch);
+  h->stream_stores = env_int("QX_STREAM_STORES", 0);
   cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
   if (e == cudaSuccess) e = cudaMalloc(&h->queue, sizeof(qx::ResetQueue) + sizeof(unsigned int) * n_envs);
@@ -811,46 +868,47 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
   }
 }
 
-template <int SHAPE>
-static void launch_pair_one(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
-  constexpr int B = qx::PairShape<SHAPE>::kBlock;
-  const unsigned grid = (unsigned)((a.env_count + 2 * B - 1) / (2 * B));
-  if (h->pair_packed) {
-    if (h->ref_constants) qx::quadx_step_pair_kernel<true, SHAPE, true><<<grid, B, 0, s>>>(h->dev, a);
-    else qx::quadx_step_pair_kernel<false, SHAPE, true><<<grid, B, 0, s>>>(h->dev, a);
-  } else {
-    if (h->ref_constants) qx::quadx_step_pair_kernel<true, SHAPE, false><<<grid, B, 0, s>>>(h->dev, a);
-    else qx::quadx_step_pair_kernel<false, SHAPE, false><<<grid, B, 0, s>>>(h->dev, a);
+template <int SHAPE, class V>
+static void launch_hot_one(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  constexpr int B = qx::HotShape<SHAPE>::kBlock, per = B * qx::Lane<V>::N;
+  const unsigned grid = (unsigned)((a.env_count + per - 1) / per);
+  if (h->ref_constants) qx::quadx_step_hot_kernel<true, SHAPE, V><<<grid, B, 0, s>>>(h->dev, a);
+  else qx::quadx_step_hot_kernel<false, SHAPE, V><<<grid, B, 0, s>>>(h->dev, a);
+}
+template <class V>
+static void launch_hot_shape(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  switch (h->hot_shape) {
+    case 1: launch_hot_one<1, V>(h, a, s); break;
+    case 2: launch_hot_one<2, V>(h, a, s); break;
+    case 3: launch_hot_one<3, V>(h, a, s); break;
+    case 4: launch_hot_one<4, V>(h, a, s); break;
+    case 5: launch_hot_one<5, V>(h, a, s); break;
+    default: launch_hot_one<0, V>(h, a, s); break;
   }
 }
-static void launch_pair_shape(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
-  switch (h->pair_shape) {
-    case 1: launch_pair_one<1>(h, a, s); break;
-    case 2: launch_pair_one<2>(h, a, s); break;
-    case 3: launch_pair_one<3>(h, a, s); break;
-    default: launch_pair_one<0>(h, a, s); break;
-  }
-}
-// one agent step of the two-envs-per-thread kernel (replaces MODE_STEP_DEFER, or MODE_STEP_INLINE with k = 1 and no auto-reset)
-static int launch_pair(QxHandle* h, qx::StepArgs a, cudaStream_t s) {
+// one agent step of the lean kernel (replaces MODE_STEP_DEFER, or MODE_STEP_INLINE with k = 1 and no auto-reset)
+static int launch_hot(QxHandle* h, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
-  launch_pair_shape(h, a, s);
+  a.prefetch_blocks = h->prefetch_blocks;
+  a.stream_stores = h->stream_stores;
+  if (h->hot_lanes == 2) launch_hot_shape<qx::P2<true>>(h, a, s);
+  else if (h->hot_lanes == 3) launch_hot_shape<qx::P2<false>>(h, a, s);
+  else launch_hot_shape<float>(h, a, s);
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;
 }
-// batches above this size step two envs per thread (below it the launch is latency-bound and the one-env kernel's
-// extra warps win); QX_PAIR=0 / 1 at qx_create forces never / always
-constexpr int64_t kPairMinEnvs = 32768;
-static bool use_pair(const QxHandle* h) {  // decided per handle, not per launch: a chunked call must run the same arithmetic as a whole one
-  if (!h->pair_ok || h->pair_mode == 0) return false;
-  return h->pair_mode == 1 || h->n >= kPairMinEnvs;
+// batches above this size take the lean kernel; QX_HOT=0 / 1 at qx_create forces never / always
+constexpr int64_t kHotMinEnvs = 32768;
+static bool use_hot(const QxHandle* h) {  // decided per handle, not per launch: a chunked call must run the same arithmetic as a whole one
+  if (!h->hot_ok || h->hot_mode == 0) return false;
+  return h->hot_mode == 1 || h->n >= kHotMinEnvs;
 }
 
 static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
-  if (use_pair(h) && (mode == qx::MODE_STEP_DEFER || (mode == qx::MODE_STEP_INLINE && a.k == 1 && !h->cfg.auto_reset)))
-    return launch_pair(h, a, s);
+  if (use_hot(h) && (mode == qx::MODE_STEP_DEFER || (mode == qx::MODE_STEP_INLINE && a.k == 1 && !h->cfg.auto_reset)))
+    return launch_hot(h, a, s);
   if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false, false>(h, mode, a, s);
   else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true, false>(h, mode, a, s);
   else if (h->ref_constants) launch_task<QX_TASK_HOVER, false, true>(h, mode, a, s);
@@ -908,7 +966,7 @@ extern "C" int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_
 constexpr int64_t kInlineResetMaxEnvs = 16384;
 extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
                        float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream) {
-  if (h && h->cfg.auto_reset && h->n <= kInlineResetMaxEnvs && !(h->pair_mode == 1 && h->pair_ok)) {
+  if (h && h->cfg.auto_reset && h->n <= kInlineResetMaxEnvs && !(h->hot_mode == 1 && h->hot_ok)) {
     if (!actions_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(QX_EINVAL, "qx_step: bad arguments");
     if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step: obs_stride < obs_dim");
     qx::StepArgs a{};
@@ -920,6 +978,14 @@ extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int
   int rc = qx_step_begin(h, actions_dev, obs_dev, obs_dtype, obs_stride, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, stream);
   if (rc) return rc;
   return qx_step_end(h, obs_dev, obs_dtype, obs_stride, stream);
+}
+
+// debug hook (not in the public header): out_dev[0] = clock64 of one SM, out_dev[1] = globaltimer ns, enqueued on `stream`
+extern "C" int qx_debug_clock_probe(unsigned long long* out_dev, void* stream) {
+  if (!out_dev) return fail(QX_EINVAL, "qx_debug_clock_probe: null buffer");
+  qx::clock_probe_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(out_dev);
+  QX_CUDA(cudaGetLastError());
+  return QX_OK;
 }
 
 extern "C" int qx_done_queue(QxHandle* h, const uint32_t** count_dev, const uint32_t** idx_dev) {
@@ -1006,7 +1072,7 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.reward = h->d_rew;
     a.terminated = h->d_flags; a.truncated = h->d_flags + n; a.terminal_obs = terminal_obs_host ? h->d_tobs : nullptr;
     a.stats = h->stats; a.queue = h->queue; a.n = n; a.k = 1; a.env_begin = b; a.env_count = cnt;
-    if (h->cfg.auto_reset && (n > kInlineResetMaxEnvs || (h->pair_mode == 1 && h->pair_ok))) {
+    if (h->cfg.auto_reset && (n > kInlineResetMaxEnvs || (h->hot_mode == 1 && h->hot_ok))) {
       rc = launch(h, qx::MODE_STEP_DEFER, a, h->stream);
       if (rc) return rc;
       rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);
@@ -1054,6 +1120,16 @@ extern "C" int qx_get_state(QxHandle* h, void* planes_host) {
       out[(4 * p + 0) * n + i] = v.x; out[(4 * p + 1) * n + i] = v.y; out[(4 * p + 2) * n + i] = v.z; out[(4 * p + 3) * n + i] = v.w;
     }
   free(tmp);
+  return QX_OK;
+}
+
+// the flags word (QX_FLAG_*) of envs [first, first + count): a strided copy of one word per env, no full-state transfer
+extern "C" int qx_get_flags(QxHandle* h, int64_t first, int64_t count, uint32_t* flags_host) {
+  if (!h || !flags_host || first < 0 || count <= 0 || first + count > h->n) return fail(QX_EINVAL, "qx_get_flags: bad arguments");
+  DeviceGuard g(h->device);
+  const float4* plane = h->state + 7 * h->n + first;  // plane 7 = (svb2, step_count, rng_ctr, flags)
+  QX_CUDA(cudaMemcpy2D(flags_host, sizeof(uint32_t), reinterpret_cast<const char*>(plane) + 12, sizeof(float4), sizeof(uint32_t), (size_t)count,
+                       cudaMemcpyDeviceToHost));
   return QX_OK;
 }
 

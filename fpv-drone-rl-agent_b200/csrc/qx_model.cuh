@@ -127,19 +127,24 @@ QX_DI void load_env(Env& e, const float4* __restrict__ st, int64_t n, int64_t i)
   load_env_tail(e, st, n, i);
 }
 
+template <bool CS = false>
 QX_DI void store_env(const Env& e, float4* __restrict__ st, int64_t n, int64_t i) {
   const uint32_t flags = (e.flags & ~F_CONTACT) | (e.contact ? F_CONTACT : 0u);
-  st[0 * n + i] = make_float4(e.px, e.py, e.pz, e.qx);
-  st[1 * n + i] = make_float4(e.qy, e.qz, e.qw, e.vx);
-  st[2 * n + i] = make_float4(e.vy, e.vz, e.wx, e.wy);
-  st[3 * n + i] = make_float4(e.wz, e.thr[0], e.thr[1], e.thr[2]);
-  st[4 * n + i] = make_float4(e.thr[3], e.pi[0], e.pi[1], e.pi[2]);
-  st[5 * n + i] = make_float4(e.pe[0], e.pe[1], e.pe[2], e.swb[0]);
-  st[6 * n + i] = make_float4(e.swb[1], e.swb[2], e.svb[0], e.svb[1]);
-  st[7 * n + i] = make_float4(e.svb[2], __int_as_float(e.step_count), __uint_as_float(e.rng_ctr), __uint_as_float(flags));
-  st[8 * n + i] = make_float4(e.peul[0], e.peul[1], e.peul[2], e.ep_ret);
-  st[9 * n + i] = make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]);
-  st[10 * n + i] = make_float4(e.pcx, e.pcy, e.parea, e.pratio);
+  auto put = [&](int p, float4 v) {
+    if (CS) __stcs(st + (int64_t)p * n + i, v);
+    else st[(int64_t)p * n + i] = v;
+  };
+  put(0, make_float4(e.px, e.py, e.pz, e.qx));
+  put(1, make_float4(e.qy, e.qz, e.qw, e.vx));
+  put(2, make_float4(e.vy, e.vz, e.wx, e.wy));
+  put(3, make_float4(e.wz, e.thr[0], e.thr[1], e.thr[2]));
+  put(4, make_float4(e.thr[3], e.pi[0], e.pi[1], e.pi[2]));
+  put(5, make_float4(e.pe[0], e.pe[1], e.pe[2], e.swb[0]));
+  put(6, make_float4(e.swb[1], e.swb[2], e.svb[0], e.svb[1]));
+  put(7, make_float4(e.svb[2], __int_as_float(e.step_count), __uint_as_float(e.rng_ctr), __uint_as_float(flags)));
+  put(8, make_float4(e.peul[0], e.peul[1], e.peul[2], e.ep_ret));
+  put(9, make_float4(e.pa[0], e.pa[1], e.pa[2], e.pa[3]));
+  put(10, make_float4(e.pcx, e.pcy, e.parea, e.pratio));
 }
 
 // Flight modes != 0: six more planes -- the outer loops' PID memory and the position row of the Aviary.state

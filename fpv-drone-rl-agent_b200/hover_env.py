@@ -210,6 +210,14 @@ class QuadXSim:
             raw[k] = v.astype(_INT_FIELDS[name]).view(np.float32) if name in _INT_FIELDS else v.astype(np.float32)
         check(self.lib.qx_set_state(self._h, raw.ctypes.data_as(C.c_void_p)))
 
+    def flags(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        """The flags word of envs [first, first + count) (qx_get_flags): one word per env, no full-state transfer."""
+        torch.cuda.synchronize(self.device)
+        count = self.n - first if count is None else count
+        out = np.empty(count, np.uint32)
+        check(self.lib.qx_get_flags(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def nonfinite_count(self) -> int:
         """Envs terminated because their state stopped being finite (failure containment)."""
         torch.cuda.synchronize(self.device)
@@ -353,7 +361,7 @@ class QuadXHoverEnv:
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(1, 4)
         obs, rew, te, tr, _ = self.sim.step_host(a)
-        flags = int(self.sim.get_state()["flags"][0])
+        flags = int(self.sim.flags()[0])
         self.info["out_of_bounds"] = bool(flags & 8)  # hover.py:280
         self.info["on_floor"] = bool(flags & 16)  # hover.py:289
         self.state = obs[0].astype(np.float64)

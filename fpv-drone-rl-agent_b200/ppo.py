@@ -4,9 +4,13 @@ checkpoints), with the rollout half (policy forward, sampling, reward /
 observation normalisation, GAE) on the hand-written kernels of
 ``include/ppo_b200.h`` and no host round trip per env step.
 
-The update half (loss, backward, Adam) is plain PyTorch: library GEMMs on a
-39 k-parameter network; its only collective is one all-reduce of the flattened
-gradient per optimiser step (``torch.distributed``, NCCL).
+The update half (SB3 ``PPO.train``) runs on the hand-written kernels too
+(``FusedUpdater``: forward + loss + backward of both networks in one tcgen05
+kernel, gradient reduction, clip + Adam + bf16 re-pack; csrc/ppo_update_kernels.cu);
+its only collective is one all-reduce of the flat 39 049-float gradient per
+optimiser step (``torch.distributed``, NCCL), captured into the same CUDA graph
+as the kernels.  A plain-PyTorch autograd update is kept as the reference the
+tests compare against (``PPOConfig.fused_update=False``).
 
 Hyper-parameter names and defaults follow SB3 PPO / VecNormalize.
 """
@@ -104,29 +108,38 @@ def export_vecnormalize(obs_stats: "RunningStats", ret_stats: "RunningStats", cf
             "gamma": cfg.gamma, "epsilon": obs_stats.eps, "norm_obs": cfg.norm_obs, "norm_reward": cfg.norm_reward}
 
 
-def export_sb3_zip(model: "ActorCritic", path: str, vecnormalize: dict | None = None, sb3_version: str = "2.7.0") -> None:
-    """Write the policy the way stable-baselines3's `save_to_zip_file` lays out a model archive -- `policy.pth` (the
-    `ActorCriticPolicy` state dict under SB3's parameter names) and `_stable_baselines3_version` (the version the
-    reference pins, uv.lock:990) -- so that the reference's side can do [RECALL]
+def export_sb3_zip(model: "ActorCritic", path: str, vecnormalize: dict | None = None, sb3_version: str = "2.7.0", hyper: dict | None = None) -> None:
+    """Write the policy the way stable-baselines3's `save_to_zip_file` lays out a model archive: `policy.pth` (the
+    `ActorCriticPolicy` state dict under SB3's parameter names), `_stable_baselines3_version` (the version the reference
+    pins, uv.lock:990), `system_info.txt`, and a `data` entry.  SB3's own `data` holds cloudpickles of gymnasium / SB3
+    objects (spaces, schedules, the policy class); neither package exists where this runs, so `data` here is plain JSON
+    with the constructor arguments (net_arch, log_std_init, PPO hyper-parameters, spaces as shape / bounds, timesteps).
+    `vecnormalize` (export_vecnormalize) goes in as `vecnormalize.npz`.
 
-        model = PPO("MlpPolicy", env, policy_kwargs=dict(net_arch=[128, 128]))     # train_hover.py:47-58 with PPO
-        model.set_parameters("hover_b200.zip", exact_match=False)                   # policy weights; optimiser state is not exported
-
-    and play it back like test_hover.py:8-21.  The archive has no `data` entry (SB3 pickles Python classes of gymnasium /
-    SB3 in there, neither of which exists here), so `PPO.load()` is not the entry point.  `vecnormalize`
-    (export_vecnormalize) is added as `vecnormalize.npz` -- SB3's own `VecNormalize.load` needs a pickle of its class; the
-    arrays are what to assign to `obs_rms` / `ret_rms`."""
+    tools/load_into_sb3.py, run on the reference side, rebuilds `PPO("MlpPolicy", VecNormalize(DummyVecEnv(QuadXHoverEnv)))`
+    from these entries with public SB3 API and writes the `.zip` + `.pkl` pair the reference's playback loads
+    (test_hover.py:8-11)."""
     import io
+    import json
     import zipfile
 
     import numpy as np
 
+    hyper = dict(hyper or {})
+    data = {"policy_class": "stable_baselines3.common.policies.ActorCriticPolicy", "algorithm": "PPO",
+            "policy_kwargs": {"net_arch": [HID, HID], "log_std_init": float(hyper.pop("log_std_init", 0.0)), "activation_fn": "torch.nn.Tanh"},
+            "observation_space": {"type": "Box", "shape": [model.obs_dim], "low": "-inf", "high": "inf", "dtype": "float64"},  # hover.py:67-70
+            "action_space": {"type": "Box", "shape": [model.act_dim], "low": -1.0, "high": 1.0, "dtype": "float64"},           # hover.py:59-61
+            "learning_rate": 3e-4, "n_steps": 2048, "batch_size": 64, "gamma": 0.99, "gae_lambda": 0.95, "clip_range": 0.2, "ent_coef": 0.0,
+            "vf_coef": 0.5, "max_grad_norm": 0.5, "num_timesteps": 0}
+    data.update(hyper)
     with zipfile.ZipFile(path, "w") as z:
         buf = io.BytesIO()
         torch.save(export_sb3_state_dict(model), buf)
         z.writestr("policy.pth", buf.getvalue())
+        z.writestr("data", json.dumps(data, indent=1))
         z.writestr("_stable_baselines3_version", sb3_version)
-        z.writestr("system_info.txt", "exported by fpv_drone_rl_agent_b200 (B200 on-device PPO); weights only\n")
+        z.writestr("system_info.txt", "exported by fpv_drone_rl_agent_b200 (B200 on-device PPO); see tools/load_into_sb3.py\n")
         if vecnormalize is not None:
             buf = io.BytesIO()
             flat = {}
@@ -213,7 +226,7 @@ class RunningStats:
         gmean /= tot
         m2 = (var + (mean - gmean) ** 2) * cnt
         dist.all_reduce(m2)
-        self.stats[:d], self.stats[d:2 * d], self.stats[2 * d] = gmean, m2 / tot, tot / dist.get_world_size()
+        self.stats[:d], self.stats[d:2 * d], self.stats[2 * d] = gmean, m2 / tot, tot / dist.get_world_size()  # count per rank: every rank adds its own shard again next rollout
         self.mean.copy_(gmean.float())
         self.inv_std.copy_((1.0 / torch.sqrt(m2 / tot + self.eps)).float())
 
@@ -279,8 +292,9 @@ class PPOConfig:
     use_cuda_graph: bool = True
     target_kl: float = 0.0  # SB3 PPO target_kl: stop the epoch loop once the approximate KL exceeds 1.5 x this (0 = off)
     log_std_init: float = 0.0  # SB3 policy_kwargs log_std_init
-    graph_update: bool = True  # replay one captured minibatch step instead of ~25 eager launches (single GPU)
-    tf32_update: bool = True  # library GEMMs of the update in TF32 (the rollout forward is bf16 on the tensor cores anyway)
+    graph_update: bool = True  # replay captured optimiser steps instead of eager launches
+    tf32_update: bool = True  # (fused_update=False only) library GEMMs of the torch update in TF32
+    fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
 
 
 class RolloutEngine:
@@ -381,6 +395,81 @@ class RolloutEngine:
         return self.T * per_step + 3
 
 
+def module_params_in_layout_order(model: ActorCritic) -> list:
+    """The parameters in the order of the flat vector of include/ppo_b200.h (ppo_update_num_params)."""
+    m = model
+    return [m.pi1.weight, m.pi1.bias, m.pi2.weight, m.pi2.bias, m.mu.weight, m.mu.bias,
+            m.vf1.weight, m.vf1.bias, m.vf2.weight, m.vf2.bias, m.v.weight, m.v.bias, m.log_std]
+
+
+class FusedUpdater:
+    """SB3 ``PPO.train`` on the hand-written kernels (K5): per optimiser step ``ppo_update_minibatch`` (minibatch
+    statistics, forward + loss + backward on the tensor cores, gradient reduction), the gradient all-reduce when there is
+    more than one rank, and ``ppo_update_adam`` (global-norm clip, Adam, bf16 re-pack for the rollout's forward kernel).
+
+    The module's parameters become views of one flat fp32 buffer (``self.flat``), which is what the Adam kernel updates;
+    minibatches are sets of 128-row tiles of the rollout buffers (a random permutation of the tiles per epoch)."""
+
+    def __init__(self, model: ActorCritic, packed: PackedPolicy, cfg: "PPOConfig", device, world: int = 1):
+        self.model, self.packed, self.cfg, self.device, self.world = model, packed, cfg, torch.device(device), world
+        self.lib = _lib.lib()
+        od, ad = model.obs_dim, model.act_dim
+        self.n_params = int(self.lib.ppo_update_num_params(od, ad))
+        params = module_params_in_layout_order(model)
+        assert sum(p.numel() for p in params) == self.n_params and len(params) == len(list(model.parameters()))
+        with torch.no_grad():
+            self.flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+            o = 0
+            for p in params:
+                p.data = self.flat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+        f = dict(device=self.device, dtype=torch.float32)
+        self.grad = torch.zeros(self.n_params, **f)
+        self.exp_avg = torch.zeros(self.n_params, **f)
+        self.exp_avg_sq = torch.zeros(self.n_params, **f)
+        self.loss_stats = torch.zeros(8, **f)
+        self.workspace = torch.zeros(int(self.lib.ppo_update_workspace_bytes(od, ad)) // 4 + 4, **f)  # zero-filled once
+        packed.refresh()
+
+    def gradient(self, ro: "RolloutEngine", tiles: torch.Tensor, normalize_adv: bool = True) -> torch.Tensor:
+        """Mean gradient of the PPO loss over the minibatch `tiles` (int32 device tensor of 128-row tile indices)."""
+        cfg, N = self.cfg, ro.T * ro.n
+        assert tiles.dtype == torch.int32 and tiles.device == self.device and tiles.is_contiguous()
+        check(self.lib.ppo_update_minibatch(C.byref(self.packed.struct), _p(ro.obs), _p(ro.actions), _p(ro.log_probs), _p(ro.advantages),
+                                            _p(ro.returns), _p(tiles), tiles.numel(), N, cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
+                                            int(normalize_adv), _p(self.grad), _p(self.loss_stats), _p(self.workspace), _stream(self.device)))
+        return self.grad
+
+    def apply(self) -> None:
+        """All-reduce (world > 1), clip, Adam, re-pack."""
+        cfg, s = self.cfg, _stream(self.device)
+        scale = 1.0
+        if self.world > 1:
+            dist.all_reduce(self.grad)
+            scale = 1.0 / self.world
+            check(self.lib.ppo_update_grad_norm(_p(self.grad), self.n_params, scale, _p(self.workspace), s))
+        check(self.lib.ppo_update_adam(_p(self.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.n_params, cfg.learning_rate,
+                                       0.9, 0.999, 1e-5, cfg.max_grad_norm, scale, C.byref(self.packed.struct), _p(self.workspace), s))
+
+    def step(self, ro: "RolloutEngine", tiles: torch.Tensor) -> None:
+        self.gradient(ro, tiles)
+        self.apply()
+
+    @property
+    def adam_steps(self) -> int:
+        out = C.c_int64()
+        check(self.lib.ppo_update_step_count(_p(self.workspace), -1, C.byref(out), _stream(self.device)))
+        return out.value
+
+    def state_dict(self) -> dict:
+        return {"flat": self.flat.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "adam_steps": self.adam_steps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.flat.copy_(sd["flat"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        check(self.lib.ppo_update_step_count(_p(self.workspace), int(sd["adam_steps"]), None, _stream(self.device)))
+        self.packed.refresh()
+
+
 class PPOTrainer:
     """``PPO.learn`` (train_hover.py:47-60, with PPO instead of SAC as the north star asks)."""
 
@@ -400,7 +489,10 @@ class PPOTrainer:
         ecfg.update(auto_reset=1)
         self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev, task=task)
         self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=shard_env_ids(rank, cfg.n_envs))
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5, capturable=bool(cfg.graph_update and world == 1))
+        self.fused = FusedUpdater(self.model, self.packed, cfg, dev, world) if cfg.fused_update else None
+        self.opt = None if cfg.fused_update else torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5,
+                                                                   capturable=bool(cfg.graph_update and world == 1))
+        self._epoch_graph = None
         self.num_timesteps = 0
         self._flat_grad = None
         self.gen = torch.Generator(device=dev).manual_seed(cfg.seed + 1000 + rank)
@@ -437,14 +529,19 @@ class PPOTrainer:
         self.opt.step()
 
     def _build_update_graph(self, bs: int) -> None:
-        """Capture one minibatch step (gather, forward, loss, backward, grad clip, Adam) into a CUDA graph: the network has
-        39 k parameters, so an eager step is ~25 tiny launches of pure launch latency.  Single-GPU only (the all-reduce
-        stays eager)."""
-        import copy
-
+        """(fused_update=False) Capture one torch minibatch step (gather, forward, loss, backward, grad clip, Adam) into a
+        CUDA graph.  Single-GPU only.  The optimiser state tensors the graph updates are the ones the warm-up created:
+        they are restored IN PLACE afterwards (Optimizer.load_state_dict would replace them and orphan the graph's)."""
         self._g_idx = torch.zeros(bs, dtype=torch.int64, device=self.device)
         self._g_acc = torch.zeros(5, device=self.device)
-        model_sd, opt_sd = copy.deepcopy(self.model.state_dict()), copy.deepcopy(self.opt.state_dict())
+        if not self.opt.state:  # create the state tensors with one eager step, so that there is something to snapshot
+            self._step_eager(self._g_idx, self._g_acc)
+            for st in self.opt.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        model_sd = {k: v.clone() for k, v in self.model.state_dict().items()}
+        opt_snap = [{k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for st in self.opt.state.values()]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -455,14 +552,75 @@ class PPOTrainer:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._step_eager(self._g_idx, self._g_acc)
-        self.model.load_state_dict(model_sd)  # the warm-up steps must not count as training
-        self.opt.load_state_dict(opt_sd)
+        with torch.no_grad():  # the warm-up / capture steps must not count as training
+            for k, v in self.model.state_dict().items():
+                v.copy_(model_sd[k])
+            for st, snap in zip(self.opt.state.values(), opt_snap):
+                for k, v in snap.items():
+                    st[k].copy_(v)
         self._update_graph = g
+
+    def _update_fused(self) -> dict:
+        """SB3 PPO.train on the hand-written kernels: per epoch a fresh random permutation of the rollout's 128-row tiles,
+        cut into minibatches of batch_size rows; the optimiser steps of one epoch are one CUDA-graph replay (kernels and,
+        with several ranks, the gradient all-reduce)."""
+        cfg, ro, fu = self.cfg, self.rollout, self.fused
+        N = ro.T * ro.n
+        n_tiles = (N + 127) // 128
+        tpm = max(1, min(cfg.batch_size, N) // 128)  # tiles per minibatch
+        starts = list(range(0, n_tiles - tpm + 1, tpm)) or [0]
+        if getattr(self, "_perm", None) is None or self._perm.numel() != n_tiles:
+            self._perm = torch.zeros(n_tiles, dtype=torch.int32, device=self.device)
+            self._epoch_graph = None
+
+        def epoch_body():
+            for s0 in starts:
+                fu.step(ro, self._perm[s0:s0 + min(tpm, n_tiles - s0)])
+
+        fu.loss_stats.zero_()
+        done_epochs = 0
+        for _ in range(cfg.n_epochs):
+            self._perm.copy_(torch.randperm(n_tiles, device=self.device, generator=self.gen).to(torch.int32))
+            kl_before = float(fu.loss_stats[4]) if cfg.target_kl > 0.0 else 0.0
+            n_before = float(fu.loss_stats[5]) if cfg.target_kl > 0.0 else 0.0
+            if cfg.graph_update:
+                if self._epoch_graph is None:
+                    keep = {k: v.clone() for k, v in fu.state_dict().items() if torch.is_tensor(v)}
+                    steps0, stats0 = fu.adam_steps, fu.loss_stats.clone()
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(side):
+                        fu.step(ro, self._perm[:tpm])  # warm-up outside capture (one-time kernel attributes, NCCL)
+                    torch.cuda.current_stream(self.device).wait_stream(side)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        epoch_body()
+                    # warm-up and capture must not count as training: restore parameters, moments, step count, statistics
+                    fu.load_state_dict({**keep, "adam_steps": steps0})
+                    fu.loss_stats.copy_(stats0)
+                    self._epoch_graph = g
+                self._epoch_graph.replay()
+            else:
+                epoch_body()
+            done_epochs += 1
+            if cfg.target_kl > 0.0:
+                akl = torch.tensor([(float(fu.loss_stats[4]) - kl_before) / max(float(fu.loss_stats[5]) - n_before, 1.0)], device=self.device)
+                if self.world > 1:
+                    dist.all_reduce(akl)
+                    akl /= self.world
+                if float(akl) > 1.5 * cfg.target_kl:
+                    break
+        st = fu.loss_stats.tolist()
+        n = max(st[5], 1.0)
+        return {"pg": st[0] / n, "vf": st[1] / n, "kl": st[2] / n, "clipfrac": st[3] / n, "optimizer_steps": done_epochs * len(starts)}
 
     def update(self) -> dict:
         """SB3 PPO.train: n_epochs passes over the rollout in shuffled minibatches; target_kl stops the remaining epochs
         once the mean approximate KL of an epoch exceeds 1.5 x target (SB3 checks per minibatch; per epoch here, so that
         the check costs one host sync per epoch)."""
+        if self.fused is not None:
+            return self._update_fused()
         cfg, ro = self.cfg, self.rollout
         N = ro.T * ro.n
         bs = min(cfg.batch_size, N)
@@ -499,6 +657,9 @@ class PPOTrainer:
         with torch.cuda.nvtx.range("ppo_collect_rollouts"):
             self.rollout.collect()
         self.num_timesteps += self.rollout.T * self.rollout.n * self.world
+        if self.world > 1:  # every rank normalises with the statistics of all shards (outside the captured rollout graph)
+            self.rollout.obs_stats.allreduce_()
+            self.rollout.ret_stats.allreduce_()
         with torch.cuda.nvtx.range("ppo_update"):
             out = self.update()
         s, l, c = self.sim.episode_stats(clear=True)
@@ -511,19 +672,44 @@ class PPOTrainer:
         return out
 
     def save(self, path: str) -> None:
-        """Counterpart of model.save + env.save (train_hover.py:26-27,62-63): policy, optimiser, VecNormalize statistics."""
-        torch.save({"model": self.model.state_dict(), "opt": self.opt.state_dict(), "obs_stats": self.rollout.obs_stats.state_dict(),
-                    "ret_stats": self.rollout.ret_stats.state_dict(), "num_timesteps": self.num_timesteps, "cfg": self.cfg.__dict__,
+        """Counterpart of model.save + env.save (train_hover.py:26-27,62-63): policy, optimiser, VecNormalize statistics, and
+        what a resumed run needs to continue the same random streams (sampling counter, return accumulator, minibatch RNG)."""
+        opt = self.fused.state_dict() if self.fused is not None else self.opt.state_dict()
+        torch.save({"model": self.model.state_dict(), "opt": opt, "fused": self.fused is not None,
+                    "obs_stats": self.rollout.obs_stats.state_dict(), "ret_stats": self.rollout.ret_stats.state_dict(),
+                    "num_timesteps": self.num_timesteps, "cfg": dict(self.cfg.__dict__),
+                    "step_base": self.rollout.step_base.clone(), "returns_acc": self.rollout.returns_acc.clone(), "gen_state": self.gen.get_state(),
                     "sb3_policy_state_dict": export_sb3_state_dict(self.model),
-                    "sb3_vecnormalize": export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg)}, path)
+                    "sb3_vecnormalize": {k: (torch.as_tensor(v) if not isinstance(v, dict) else {kk: torch.as_tensor(vv) for kk, vv in v.items()})
+                                         for k, v in export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg).items()}}, path)
 
     def save_sb3(self, path: str) -> None:
         """The policy as an SB3-style archive (policy.pth + version + VecNormalize statistics), see export_sb3_zip."""
-        export_sb3_zip(self.model, path, export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg))
+        c = self.cfg
+        hyper = dict(log_std_init=c.log_std_init, learning_rate=c.learning_rate, n_steps=c.n_steps, batch_size=c.batch_size, gamma=c.gamma,
+                     gae_lambda=c.gae_lambda, clip_range=c.clip_range, ent_coef=c.ent_coef, vf_coef=c.vf_coef, max_grad_norm=c.max_grad_norm,
+                     num_timesteps=int(self.num_timesteps))
+        export_sb3_zip(self.model, path, export_vecnormalize(self.rollout.obs_stats, self.rollout.ret_stats, self.cfg), hyper=hyper)
 
     def load(self, path: str) -> None:
-        sd = torch.load(path, map_location=self.device, weights_only=False)
-        self.model.load_state_dict(sd["model"]); self.opt.load_state_dict(sd["opt"])
+        sd = torch.load(path, map_location=self.device, weights_only=True)  # tensors and plain containers only: no pickle execution
+        if bool(sd.get("fused", False)) != (self.fused is not None):
+            raise ValueError("checkpoint was written with a different PPOConfig.fused_update")
+        with torch.no_grad():  # in place: the parameters are views of the flat buffer / captured by CUDA graphs
+            for k, v in self.model.state_dict().items():
+                v.copy_(sd["model"][k])
+        if self.fused is not None:
+            self.fused.load_state_dict(sd["opt"])
+        else:
+            if getattr(self, "_update_graph", None) is not None and self.opt.state:
+                for st, src in zip(self.opt.state.values(), sd["opt"]["state"].values()):  # in place: the graph updates these tensors
+                    for k, v in src.items():
+                        if torch.is_tensor(v):
+                            st[k].copy_(v)
+            else:
+                self.opt.load_state_dict(sd["opt"])
         self.rollout.obs_stats.load_state_dict(sd["obs_stats"]); self.rollout.ret_stats.load_state_dict(sd["ret_stats"])
-        self.num_timesteps = sd["num_timesteps"]
+        self.rollout.step_base.copy_(sd["step_base"]); self.rollout.returns_acc.copy_(sd["returns_acc"])
+        self.gen.set_state(sd["gen_state"].cpu())
+        self.num_timesteps = int(sd["num_timesteps"])
         self.packed.refresh()

@@ -78,6 +78,41 @@ int64_t ppo_running_stats_scratch_bytes(int32_t dim);
 int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
                          float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream);
 
+/* ---- the PPO update (SB3 PPO.train, reached by train_hover.py:60 `model.learn`) --------------------------------------
+ * Flat fp32 parameter vector, in the module order of SB3's ActorCriticPolicy(net_arch=[128,128]) with separate pi / vf
+ * MLPs:  pi1.W [128][obs_dim], pi1.b, pi2.W [128][128], pi2.b, action_net.W [act_dim][128], action_net.b,
+ *        vf1.W, vf1.b, vf2.W, vf2.b, value_net.W [1][128], value_net.b, log_std [act_dim]
+ * (39 049 floats for the hover task).  The gradient and the Adam moments use the same layout. */
+int32_t ppo_update_num_params(int32_t obs_dim, int32_t act_dim);
+/* device workspace one updater needs: ZERO-FILLED once before the first call; holds the minibatch statistics, the Adam
+ * step counter and one partial gradient per SM */
+int64_t ppo_update_workspace_bytes(int32_t obs_dim, int32_t act_dim);
+
+/* Gradient of SB3's PPO loss on one minibatch (forward + loss + backward of both networks on the tensor cores):
+ *   loss = mean(max(-A r, -A clip(r, 1 - clip_range, 1 + clip_range))) + vf_coef * mean((ret - V)^2) - ent_coef * mean(entropy)
+ * with r = exp(logp - old_logp) and, when normalize_adv != 0, A = (adv - mean) / (std + 1e-8) over the minibatch.
+ * The minibatch is the set of 128-row tiles tiles_dev[0 .. n_tiles) of the rollout buffers (rows 128 t .. 128 t + 127; rows
+ * >= n_rows do not count): obs [n_rows, obs_dim] (normalised, as stored by ppo_policy_forward), actions [n_rows, act_dim],
+ * old_logp / adv / ret [n_rows].  `p` holds the bf16 weights the forward runs with.  Writes grad_out [n_params] (mean over the
+ * minibatch rows) and adds to loss_stats[0..5] (nullable) the SUMS over rows of: policy loss, squared value error,
+ * old_logp - logp, clipped indicator, (r - 1) - log r, 1.  Four launches on `stream`, no host synchronisation. */
+int ppo_update_minibatch(const PpoPolicy* p, const float* obs, const float* actions, const float* old_logp, const float* adv,
+                         const float* ret, const int32_t* tiles_dev, int32_t n_tiles, int64_t n_rows, float clip_range, float vf_coef,
+                         float ent_coef, int32_t normalize_adv, float* grad_out, float* loss_stats, void* workspace, void* stream);
+/* after an all-reduce of grad over the ranks: recompute the squared norm (of grad * grad_scale) the clip in ppo_update_adam uses */
+int ppo_update_grad_norm(const float* grad, int32_t n_params, float grad_scale, void* workspace, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_grad_norm) + torch.optim.Adam step (bias-corrected, eps outside the square root) on the
+ * flat fp32 master parameters, with g = grad * grad_scale; then the updated values are re-packed (bf16 weights, fp32 biases /
+ * log_std) into the buffers of `packed_out`, which the forward kernels read.  The Adam step counter lives in the workspace. */
+int ppo_update_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params, float lr, float beta1,
+                    float beta2, float eps, float max_grad_norm, float grad_scale, const PpoPolicy* packed_out, void* workspace, void* stream);
+/* read (out != NULL) and / or set (set_to >= 0) the Adam step counter: checkpoint / resume */
+int ppo_update_step_count(void* workspace, int64_t set_to, int64_t* out, void* stream);
+
+/* test hook: D[128, n] (fp32) = A x B^T through K-major (x_mn = 0: given as [rows][k]) or MN-major (x_mn = 1: given as
+ * [k][rows]) shared-memory descriptors -- the transposed operand forms the backward GEMMs rely on */
+int ppo_test_gemm_mn(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, int32_t a_mn, int32_t b_mn, void* stream);
+
 /* test hook: D[128, n] (fp32) = A[128, k] x B[n, k]^T with one tcgen05.mma chain (bf16 inputs) */
 int ppo_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int32_t n, int32_t k, void* stream);
 

@@ -171,6 +171,9 @@ int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float*
  * for parity tests and checkpoint/resume. */
 int qx_get_state(QxHandle* h, void* planes_host);
 int qx_set_state(QxHandle* h, const void* planes_host);
+/* The flags word of envs [first, first + count) (bit 0 contact, 1 terminated, 2 truncated, 3 out_of_bounds, 4 on_floor,
+ * 5 low-z): what the `info` dict of hover.py:53-57,280,289 is made of.  Synchronous, one word per env. */
+int qx_get_flags(QxHandle* h, int64_t first, int64_t count, uint32_t* flags_host);
 int32_t qx_state_words(const QxHandle* h);
 
 /* Replaces: SB3 Monitor's info["episode"] (train_hover.py:42 make_vec_env):

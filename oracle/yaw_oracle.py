@@ -25,7 +25,7 @@ class YawConfig:
     flight_dome_size: float = 3.0
     agent_dt: float = 1.0 / 120.0  # one Aviary.step (yaw.py:126-127) at control_hz 120
     sphere_pos: tuple = (2.0, 0.0, 1.0)  # main.py:16-23
-    cam_tilt_up_deg: float = 20.0  # PyFlyt default, yaw.py passes no camera options
+    cam_tilt_up_deg: float = -20.0  # PyFlyt default camera_angle_degrees = +20; positive = down under the convention hover.py's -25 = 25 deg up implies
     spawn_yaw_noise: float = np.pi  # yaw.py:79
     start_pos: tuple = (0.0, 0.0, 0.0)
     rate_scale: float = 30.0

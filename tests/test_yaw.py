@@ -49,9 +49,16 @@ def test_yaw_cuda_matches_oracle():
     import fpv_drone_rl_agent_b200 as pkg
     from oracle.yaw_oracle import YawVecOracle
 
+    from oracle.yaw_oracle import YawConfig
+
     n = 512
-    env = pkg.QuadXYawVecEnv(n, seed=4)
-    orc = YawVecOracle(n, seed=4, noise=True)
+    # default camera: PyFlyt's +20 deg = 20 deg DOWN (the convention hover.py's -25 = up implies); from the ground the sphere at
+    # 26.6 deg elevation is then above the image (top edge 25 deg), so the parity run uses a camera that does see it
+    env0 = pkg.QuadXYawVecEnv(64, seed=4)
+    assert float(env0.reset()[:, 3:5].abs().max()) == 0.0 and env0.sim.cfg.cam_tilt_up_deg == -20.0 == YawConfig().cam_tilt_up_deg
+    env0.close()
+    env = pkg.QuadXYawVecEnv(n, seed=4, cam_tilt_up_deg=20.0)
+    orc = YawVecOracle(n, cfg=YawConfig(cam_tilt_up_deg=20.0), seed=4, noise=True)
     o = env.reset().cpu().numpy()
     o2 = orc.reset()
     assert np.abs(o - o2).max() < 2e-3

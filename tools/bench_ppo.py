@@ -53,6 +53,8 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, w
     out = {"task": "yaw" if task else "hover", "envs": envs, "n_steps": steps,
            "rollout": {"samples_per_s": envs * steps / (ms * 1e-3), "ms_per_rollout": ms, "launches_per_rollout": ro.launches_per_rollout,
                        "what": "env step + reset + obs/reward normalisation + policy forward + sampling + time-limit bootstrap, x n_steps, + GAE; one CUDA graph replay"}}
+    if task == 0:
+        out["update"] = measure_update(tr, world)
     if rollout_only or task != 0:
         tr.sim.close()
         return out
@@ -79,6 +81,59 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, w
     gb = T * n * GAE_BYTES / (ms * 1e-3) / 1e9
     out["gae"] = {"ms": ms, "roofline": {"bound": "hbm", "achieved": gb, "peak": hbm_peak, "unit": "GB/s", "frac": gb / hbm_peak}}
     tr.sim.close()
+    return out
+
+
+def measure_update(tr, world: int = 1, batch_size: int = 262144, epochs: int = 2) -> dict:
+    """K5: the PPO update on the rollout just collected -- optimiser steps of `batch_size` rows (forward + loss + backward on
+    the tensor cores, gradient reduction, all-reduce when world > 1, clip + Adam + re-pack), one CUDA-graph replay per epoch.
+    Reports ms per optimiser step, trained sample-passes/s, and -- with several ranks -- the all-reduce of the flat gradient
+    timed alone (the only collective of the path)."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    cfg, ro = tr.cfg, tr.rollout
+    old = (cfg.batch_size, cfg.n_epochs)
+    cfg.batch_size, cfg.n_epochs = min(batch_size, ro.T * ro.n), epochs
+    tr._epoch_graph = None
+    tr.update()  # builds the graph
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s.record()
+    st = tr.update()
+    e.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = s.elapsed_time(e)
+    steps = st["optimizer_steps"]
+    rows = steps * (cfg.batch_size // 128) * 128
+    out = {"batch_size_per_rank": cfg.batch_size, "epochs": epochs, "optimizer_steps": steps, "update_ms_per_step": ms / max(steps, 1),
+           "update_ms_total": ms, "wall_ms_total": 1e3 * wall, "sample_passes_per_s_per_gpu": rows / (ms * 1e-3),
+           "flop_per_sample_pass": 3 * FLOP_PER_SAMPLE, "tflops_algorithmic": rows * 3 * FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12,
+           "kernels": "ppo_upd::update_prepare / update_fwdbwd (tcgen05) / update_reduce / update_adam", "n_params": tr.fused.n_params}
+    if world > 1:
+        g = tr.fused.grad
+        for _ in range(5):
+            dist.all_reduce(g)
+        torch.cuda.synchronize()
+        dist.barrier()
+        s.record()
+        for _ in range(50):
+            dist.all_reduce(g)
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / 50 * 1e3], device=g.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["allreduce_us"] = float(t.item())
+        out["allreduce_bytes"] = g.numel() * 4
+        g.zero_()
+    cfg.batch_size, cfg.n_epochs = old
+    tr._epoch_graph = None
     return out
 
 

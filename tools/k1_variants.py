@@ -26,12 +26,15 @@ obs = torch.zeros(E, 20, device=dev)
 rew = torch.zeros(E, device=dev)
 te = torch.zeros(E, dtype=torch.uint8, device=dev)
 tr = torch.zeros(E, dtype=torch.uint8, device=dev)
-variants = [("one_env", {"QX_PAIR": "0"})]
-variants += [(f"pair_packed_shape{k}", {"QX_PAIR": "1", "QX_PAIR_SHAPE": str(k), "QX_PAIR_PACKED": "1"}) for k in range(4)]
-variants += [(f"pair_scalar_shape{k}", {"QX_PAIR": "1", "QX_PAIR_SHAPE": str(k), "QX_PAIR_PACKED": "0"}) for k in range(4)]
+variants = [("legacy_one_env", {"QX_HOT": "0"})]
+variants += [(f"hot_1env_shape4_cs{cs}", {"QX_HOT": "1", "QX_LANES": "1", "QX_SHAPE": "4", "QX_PREFETCH": "0", "QX_STREAM_STORES": str(cs)}) for cs in (0, 1, 2)]
+variants += [(f"hot_2env_packed_shape0_cs{cs}", {"QX_HOT": "1", "QX_LANES": "2", "QX_SHAPE": "0", "QX_PREFETCH": "0", "QX_STREAM_STORES": str(cs)}) for cs in (0, 1)]
 only = os.environ.get("K1_ONLY")
 if only:
     variants = [v for v in variants if v[0] in only.split(",")]
+import ctypes as C  # noqa: E402
+L = pkg._lib.lib()
+probe = torch.zeros(4, dtype=torch.int64, device=dev)
 res = {}
 for name, env in variants:
     os.environ.update(env)
@@ -43,13 +46,17 @@ for name, env in variants:
         sim.step(acts[k % 8], obs, rew, te, tr)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(STEPS + 1)]
+    L.qx_debug_clock_probe(C.c_void_p(probe.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     ev[0].record()
     for k in range(STEPS):
         sim.step(acts[k % 8], obs, rew, te, tr)
         ev[k + 1].record()
+    L.qx_debug_clock_probe(C.c_void_p(probe.data_ptr() + 16), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
+    pr = probe.tolist()
+    sm_mhz = (pr[2] - pr[0]) / max(pr[3] - pr[1], 1) * 1e3
     per = sorted(ev[k].elapsed_time(ev[k + 1]) * 1e3 for k in range(STEPS))
     res[name] = {"mean_us": sum(per) / len(per), "min_us": per[0], "median_us": per[len(per) // 2], "p90_us": per[int(0.9 * len(per))],
-                 "frac_of_hbm_roofline_mean": 358.0 * E / (sum(per) / len(per) * 1e-6) / 6538.6e9, "checksum": float(rew.double().sum())}
+                 "frac_of_hbm_roofline_mean": 358.0 * E / (sum(per) / len(per) * 1e-6) / 6538.6e9, "checksum": float(rew.double().sum()), "sm_mhz_avg_over_loop": sm_mhz}
     sim.close()
     print(name, json.dumps(res[name]), flush=True)
