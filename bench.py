@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-small", action="store_true", help="skip the configs[1] (4096 envs) side measurements")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO rollout side measurements (metric M2)")
+    ap.add_argument("--no-train", action="store_true", help="skip the bounded PPO training-to-target leg (SURVEY C5)")
     return ap.parse_args()
 
 
@@ -179,17 +180,109 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = args.steps
-    r = cpu_run(args.cpu_envs, steps, min(args.warmup, 2), budget_s=120.0)
+    r = cpu_run(args.cpu_envs, args.steps, args.warmup, budget_s=150.0)
+    cfg = workload_config(args.cpu_envs, 1)
+    cfg["workload"] = ("hover (hover.py QuadXHoverEnv), CPU sample of the same workload: %d envs x %d steps on %d host threads "
+                       "(the GPU arm runs %d envs/GPU x %d GPU)" % (args.cpu_envs, r["steps_done"], r["cores"], args.envs, args.gpus))
+    cfg["gpu_arm_envs_per_gpu"] = args.envs
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_done"],
-        "warmup": min(args.warmup, 2), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args.envs, args.gpus),
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "PyFlyt/pybullet are not installable here (no network); the reference arm is the CPU oracle port of the same path",
+        "note": "PyFlyt/pybullet are not installable here (no network); the reference arm is the CPU oracle port of the same path "
+                "(oracle/quadx_oracle.c, float64, all host threads); env-steps/s does not depend on the batch size on the CPU",
     }
     print(json.dumps(line))
+
+
+def hover_leg(pkg, dev, envs: int, rank: int, world: int, steps: int, warmup: int, workload: str) -> dict:
+    """One more timing of the hover step on a fresh handle: `workload` = "tumble" (the headline's action distribution) or
+    "airborne" (zero rate commands, hover thrust, motor noise on: the drones stay in the air for the whole window, the regime a
+    trained policy keeps the fleet in -- no env touches the floor, nothing finishes, the reset queue stays empty)."""
+    import torch
+    import torch.distributed as dist
+
+    cfg = pkg.default_config()
+    cfg.update(start_pos=[0, 0, 1.0], spawn_throttle=HOVER_THR, auto_reset=1, noise=1)
+    sim = pkg.QuadXSim(envs, cfg, seed=1234, env_id0=rank * envs, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    acts = torch.rand(8, envs, 4, generator=g) * 2 - 1
+    if workload == "airborne":
+        acts[..., :3] = 0.0
+        acts[..., 3] = 2 * HOVER_THR - 1
+    else:
+        acts[..., :3] *= 0.3
+        acts[..., 3] = (2 * HOVER_THR - 1) + 0.3 * acts[..., 3]
+    acts = acts.to(dev)
+    obs = torch.zeros(envs, 20, device=dev); rew = torch.zeros(envs, device=dev)
+    te = torch.zeros(envs, dtype=torch.uint8, device=dev); tr = torch.zeros(envs, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if envs * 454 < (160 << 20) else None  # state + outputs fit in L2: flush between steps
+    sim.reset(obs)
+    for k in range(max(warmup, 3)):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        if flush is not None:
+            flush.zero_()
+        ev[k][0].record()
+        sim.step(acts[k % 8], obs, rew, te, tr)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sim.close()
+    return {"workload": workload, "envs_per_gpu": envs, "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+            "env_steps_per_s": envs * world * steps / (ms * 1e-3), "l2": "flushed between steps (256 MB memset, outside the timed events)" if flush is not None else "working set exceeds L2"}
+
+
+def train_leg(dev, rank: int, world: int, envs: int = 16384, budget_s: float = 40.0, target_len: float = 400.0, target_rew: float = 181.0) -> dict:
+    """SURVEY C5 as a bounded bench leg: PPO hover training from scratch on the reference's reset protocol until
+    rollout/ep_len_mean >= 402-ish (the cap the reference's runs saturate at) and rollout/ep_rew_mean >= 0.5 * 402 * 0.9 = 181,
+    or until the time budget is spent.  Rollout, update (hand-written kernels) and, with several ranks, the gradient all-reduce."""
+    import torch
+    import torch.distributed as dist
+
+    from fpv_drone_rl_agent_b200 import ppo
+
+    cfg = ppo.PPOConfig(n_envs=envs, n_steps=64, n_epochs=4, batch_size=32768, learning_rate=3e-4, seed=0, target_kl=0.02, log_std_init=-1.0)
+    tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world)
+    tr.learn_iteration()  # graph capture / one-time setup outside the clock (its samples still count as training)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    t_len = t_rew = None
+    best_rew, it, out = -1e9, 0, {}
+    while True:
+        out = tr.learn_iteration()
+        it += 1
+        now = time.perf_counter() - t0
+        if out["ep_len_mean"] == out["ep_len_mean"]:
+            best_rew = max(best_rew, out["ep_rew_mean"])
+            if t_len is None and out["ep_len_mean"] >= target_len:
+                t_len = now
+            if t_rew is None and out["ep_len_mean"] >= target_len and out["ep_rew_mean"] >= target_rew:
+                t_rew = now
+        stop = torch.tensor([1.0 if (t_rew is not None or now > budget_s) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(stop, op=dist.ReduceOp.MAX)
+        if float(stop) > 0:
+            break
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    res = {"envs_per_gpu": envs, "n_gpus": world, "n_steps": 64, "n_epochs": 4, "batch_size_per_rank": 32768, "iterations": it,
+           "env_steps": int(out["timesteps"]), "wall_s": wall, "env_steps_per_s_incl_update": (out["timesteps"] - envs * 64 * world) / wall,
+           "target_ep_len": target_len, "target_ep_rew": target_rew, "time_to_ep_len_s": t_len, "time_to_ep_len_and_rew_s": t_rew,
+           "final_ep_len_mean": out["ep_len_mean"], "final_ep_rew_mean": out["ep_rew_mean"], "best_ep_rew_mean": best_rew, "budget_s": budget_s,
+           "reference": "train_hover.py logs: ep_len_mean reaches the 402 cap after ~230-250 k steps = 275-300 s on 16 CPU processes (SURVEY 6)"}
+    tr.sim.close()
+    return res
 
 
 # ---------------------------------------------------------------------------- ours
@@ -327,6 +420,7 @@ def main_ours(args):
                          "kernel": "qx::quadx_step_kernel<MODE_STEP_DEFER, HOVER> (+ the reset-queue launch, both inside the step time)", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
         }
+        line["roofline"]["step_ms_first8_min"] = min(per[:8]) if len(per) >= 8 else None
         if world == 1 and not args.no_small:
             line["hover_4096"] = small_config(pkg, dev)
         if world == 1 and not args.no_small:
@@ -344,6 +438,20 @@ def main_ours(args):
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cpus")}
             line["cpu_baseline"]["others_env_steps_per_s"] = cpu_extras()
     sim.close()
+    if not args.no_small:
+        # the same step in the regime a trained policy keeps the fleet in (nobody on the floor, nothing to reset), and BASELINE
+        # configs[3] as written: 1 Mi envs in total, split over the GPUs (strong scaling; the per-GPU shard fits in L2 from N = 2)
+        air = hover_leg(pkg, dev, E, rank, world, 32, args.warmup, "airborne")
+        strong = hover_leg(pkg, dev, max((1 << 20) // world, 4096), rank, world, 32, args.warmup, "tumble")
+        if rank == 0:
+            air["frac_of_hbm_roofline"] = air["env_steps_per_s"] / world * ALG_BYTES_PER_ENV_STEP / (peak * 1e9)
+            line["hover_airborne"] = air
+            strong["frac_of_hbm_roofline_per_gpu"] = strong["env_steps_per_s"] / world * ALG_BYTES_PER_ENV_STEP / (peak * 1e9)
+            line["strong_1Mi"] = strong
+    if not args.no_train:
+        tl = train_leg(dev, rank, world)
+        if rank == 0:
+            line["train"] = tl
     if world > 1 and not args.no_ppo:
         # metric M2 at N GPUs: every rank collects its own rollouts (env shard + policy replica, no collective in the
         # rollout); aggregate samples/s = total samples / slowest rank

@@ -121,6 +121,7 @@ def lib() -> C.CDLL:
         "ppo_update_grad_norm": (C.c_int, [vp, i32, f32, vp, vp]),
         "ppo_update_adam": (C.c_int, [vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, C.POINTER(PpoPolicy), vp, vp]),
         "ppo_update_step_count": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
+        "ppo_update_set_lr_scale": (C.c_int, [vp, C.c_float, vp]),
         "qx_debug_clock_probe": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in protos.items():
@@ -139,7 +140,7 @@ EXPORTED = [
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
                 "ppo_reward_normalize", "ppo_test_gemm", "ppo_test_gemm_mn", "ppo_update_num_params", "ppo_update_workspace_bytes",
-                "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count"]
+                "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count", "ppo_update_set_lr_scale"]
 
 
 class QxError(RuntimeError):

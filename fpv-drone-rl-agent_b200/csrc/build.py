@@ -18,8 +18,11 @@ HEADERS = ["qx_model.cuh", "qx_lanes.cuh", "qx_ref_constants.cuh", "qx_internal.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",  # FTZ + approximate div/sqrt in the once-per-step epilogue; parity tests hold
+    "-fmad=false",  # no implicit contraction: every fused multiply-add is written as one (fmaf / __ffma2_rn), so that the same source gives the
+                    # same roundings in every kernel instantiation (generic / specialised / paired kernels are compared bit for bit)
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
+    "--threads", "0",  # the translation units compile in parallel
 ]
 
 

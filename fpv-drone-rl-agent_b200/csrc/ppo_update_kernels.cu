@@ -89,6 +89,7 @@ struct Header {
   unsigned int ticket, pad;
   double part[3];     // prepare: sum 1, sum adv, sum adv^2 (fp64)
   unsigned long long step;  // Adam step count
+  float lr_scale_m1;  // learning-rate schedule: the Adam kernel steps with lr * (1 + lr_scale_m1), so a zero-filled workspace means lr
 };
 constexpr size_t kHeaderBytes = 256;
 static_assert(sizeof(Header) <= kHeaderBytes, "header");
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(256) update_adam_kernel(const AdamArgs a) {
     a.m[p] = m; a.v[p] = v;
     const double bc1 = 1.0 - pow((double)a.beta1, (double)t), bc2 = 1.0 - pow((double)a.beta2, (double)t);
     const float denom = sqrtf(v) / (float)sqrt(bc2) + a.eps;
-    const float w = a.params[p] - (float)(a.lr / bc1) * (m / denom);
+    const float w = a.params[p] - (float)((double)a.lr * (1.0 + (double)a.hdr->lr_scale_m1) / bc1) * (m / denom);
     a.params[p] = w;
     // ---- re-pack into the bf16 / fp32 buffers of the forward kernels
     const Layout L = make_layout(a.pk.obs_dim, a.pk.act_dim);
@@ -763,6 +764,16 @@ extern "C" int ppo_update_adam(float* params, const float* grad, float* exp_avg,
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.max_grad_norm = max_grad_norm; a.grad_scale = grad_scale; a.pk = *packed_out;
   ppo_upd::update_adam_kernel<<<(n_params + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? QX_OK : ufail(QX_ECUDA, "ppo_update_adam: launch failed");
+}
+
+extern "C" int ppo_update_set_lr_scale(void* workspace, float scale, void* stream) {
+  if (!workspace || !(scale >= 0.f)) return ufail(QX_EINVAL, "ppo_update_set_lr_scale: bad arguments");
+  ppo_upd::Header* hdr = (ppo_upd::Header*)workspace;
+  const float v = scale - 1.0f;
+  if (cudaMemcpyAsync(&hdr->lr_scale_m1, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess)
+    return ufail(QX_ECUDA, "ppo_update_set_lr_scale: copy failed");
+  cudaStreamSynchronize((cudaStream_t)stream);  // v is on this frame
+  return QX_OK;
 }
 
 extern "C" int ppo_update_step_count(void* workspace, int64_t set_to, int64_t* out, void* stream) {

@@ -53,6 +53,9 @@ struct Stats {
 struct ResetQueue {
   unsigned int count;
   unsigned int ticket;
+  // merged step kernel (quadx_step_hot_kernel<..., MERGED>): block tickets of one launch, re-armed by the last block to
+  // leave, and the number of envs the launch queued (count itself is zero again when the launch ends)
+  unsigned int tasks_done, next_reset, exit_ticket, published;
   unsigned int pad[2];
   unsigned int idx[1];  // [n_envs]
 };
@@ -74,7 +77,9 @@ struct StepArgs {
   int32_t k;
   int32_t obs_bf16;
   int32_t stream_stores;    // hot kernel: 1 = observations / reward / flags with evict-first stores (write-once data), 2 = the state planes too
-  int32_t prefetch_blocks;  // hot kernel: each block asks L2 for the planes of the block this many positions ahead (0 = off)
+  int32_t merged;           // hot kernel: the last resident wave of blocks drains the reset queue in the same launch
+  uint32_t drainers;        // ... and this is how many blocks that wave has (resident blocks per SM x SMs)
+  int32_t paired_reset;     // queued envs are re-created by the paired code (hot_reset_env): even idle sub-step count, throttles >= 0
 };
 
 template <int DIM>
@@ -119,7 +124,7 @@ enum { MODE_STEP_INLINE = 0, MODE_STEP_DEFER = 1, MODE_RESET_MASK = 2, MODE_RESE
 
 // CASC: the instantiation for PyFlyt flight modes != 0 (outer PID loops; 6 more state planes).  hover.py itself only
 // ever reaches mode 0 (set_mode(0), hover.py:92), which is the CASC = false path.
-template <int MODE, int TASK, bool CASC>
+template <int MODE, int TASK, bool CASC, bool NC = true>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, int64_t i);
 
 constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
@@ -314,12 +319,12 @@ __device__ __forceinline__ void episode_end(const Env& e, const StepArgs& a, con
   }
 }
 
-template <int MODE, int TASK, bool CASC>
+template <int MODE, int TASK, bool CASC, bool NC>
 __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
   constexpr int OBS_DIM = ObsDim<TASK>::value;
   constexpr bool RESET_ONLY = MODE == MODE_RESET_MASK || MODE == MODE_RESET_QUEUE;
   Env e;
-  load_env(e, a.state, a.n, i);
+  load_env<NC>(e, a.state, a.n, i);
   if (CASC) load_cascade(e, a.state, a.n, i);
   float seul[3];  // cascade: Euler row of the Aviary.state snapshot
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
@@ -425,6 +430,7 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
   }
   store_env(e, a.state, a.n, i);
   if (CASC) store_cascade(e, a.state, a.n, i);
+  if (MODE == MODE_STEP_DEFER && a.merged) __threadfence();  // cold path of the merged launch (see hot_epilogue_loaded)
 }
 
 // ===========================================================================
@@ -439,8 +445,6 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, c
 // QX_SHAPE at qx_create picks one (tuning / profiling); the defaults are the fastest measured on B200.
 template <int SHAPE> struct HotShape;
 template <> struct HotShape<0> { static constexpr int kBlock = 128, kMinBlocks = 3; };  // 168 registers
-template <> struct HotShape<1> { static constexpr int kBlock = 128, kMinBlocks = 2; };  // 255
-template <> struct HotShape<2> { static constexpr int kBlock = 64, kMinBlocks = 6; };   // 168
 template <> struct HotShape<3> { static constexpr int kBlock = 128, kMinBlocks = 4; };  // 128
 template <> struct HotShape<4> { static constexpr int kBlock = 128, kMinBlocks = 5; };  // 96
 template <> struct HotShape<5> { static constexpr int kBlock = 128, kMinBlocks = 6; };  // 80
@@ -472,9 +476,15 @@ template <int HALF, bool PK> QX_DI void unpack_lane(Core<float>& a, const Core<P
 
 // once-per-step epilogue of one env of the hot kernel: observation, reward, flags, episode end, state store
 template <bool REF>
+QX_DI void hot_epilogue_loaded(Env& e, const DevConfig& c, const StepArgs& a, const int64_t i, const float4 av);
+template <bool REF>
 QX_DI void hot_epilogue(Env& e, const DevConfig& c, const StepArgs& a, const int64_t i, const float4 av) {
-  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
   load_env_tail(e, a.state, a.n, i);  // the epilogue planes are loaded only now: they do not occupy registers across the sub-step loop
+  hot_epilogue_loaded<REF>(e, c, a, i, av);
+}
+template <bool REF>
+QX_DI void hot_epilogue_loaded(Env& e, const DevConfig& c, const StepArgs& a, const int64_t i, const float4 av) {
+  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
   const float act[4] = {av.x, av.y, av.z, av.w};
   float obs[OBS_DIM];
   ObsAux x;
@@ -484,33 +494,124 @@ QX_DI void hot_epilogue(Env& e, const DevConfig& c, const StepArgs& a, const int
   else if (a.obs) write_obs(obs, a.obs, i, a.obs_stride, a.obs_bf16 != 0, a.stream_stores != 0);
   if (a.stream_stores >= 2) store_env<true>(e, a.state, a.n, i);
   else store_env(e, a.state, a.n, i);
+  if (done && a.merged) __threadfence();  // merged launch: the queue entry and these planes are read by a draining block
 }
 
-// V = float: one env per thread;  V = P2<true> / P2<false>: two envs per thread, packed / scalar arithmetic
-template <bool REF, int SHAPE, class V>
-__global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMinBlocks) quadx_step_hot_kernel(const __grid_constant__ DevConfig cparam,
-                                                                                                                 const __grid_constant__ StepArgs a) {
-  constexpr int kB = HotShape<SHAPE>::kBlock, kLanes = Lane<V>::N;
+// reset of a queued env inside the merged launch: its planes were stored by this launch, so no read-only loads
+template <bool REF>
+__device__ __noinline__ void run_env_requeue(const DevConfig& cparam, const StepArgs& a, const int64_t i) {
   DevConfig cref = cparam;
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
-  const int64_t end = a.env_begin + a.env_count;
-  const int64_t i0 = a.env_begin + (int64_t)blockIdx.x * (kLanes * kB) + threadIdx.x;
-  // L2 prefetch (TMA, no shared memory, no barrier) of the state planes and actions of the block that will take this
-  // block's place on the SM: in steady state DRAM is busy writing back the previous step's results and the first loads
-  // of a block are its longest stall -- they become L2 hits
-  if (a.prefetch_blocks > 0 && threadIdx.x < kBasePlanes + 1) {
-    const int64_t j0 = a.env_begin + ((int64_t)blockIdx.x + a.prefetch_blocks) * (kLanes * kB);
-    if (j0 < end) {
-      const int64_t cnt = (end - j0 < (int64_t)kLanes * kB) ? end - j0 : (int64_t)kLanes * kB;
-      const void* src = threadIdx.x < kBasePlanes ? (const void*)(a.state + (int64_t)threadIdx.x * a.n + j0)
-                                                   : (const void*)(reinterpret_cast<const float4*>(a.actions) + j0);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(cnt * 16)) : "memory");
+  run_env<MODE_RESET_QUEUE, QX_TASK_HOVER, false, false>(c, a, i);
+}
+
+// one agent step of envs i0 (and i1 when V has two lanes) in the calling thread
+// V = float: one env per thread;  V = P2<true> / P2<false>: two envs per thread, packed / scalar arithmetic
+// the 12 sub-steps of one agent step for the env(s) of the calling thread: setpoint scaling (hover.py:337-341), then per
+// Aviary.step() the rate PID, one Philox call per env and two physics sub-steps.  V = float: one env per thread;
+// V = P2<true> / P2<false>: two envs per thread, packed / scalar arithmetic.
+template <class V>
+QX_DI void hot_substeps(const DevConfig& c, Env& e0, Env& e1, const float4 av0, const float4 av1, const int64_t i0, const int64_t i1) {
+  constexpr int kLanes = Lane<V>::N;
+  typedef LaneOps<V> L;
+  Core<V> p;
+  L::pack(p, e0, e1);
+  V sp[4];  // hover.py:337-341
+  sp[0] = vmul(L::make(av0.x, av1.x), c.act_scale[0]);
+  sp[1] = vmul(L::make(av0.y, av1.y), c.act_scale[1]);
+  sp[2] = vmul(L::make(av0.z, av1.z), c.act_scale[2]);
+  sp[3] = vfma(L::make(av0.w, av1.w), c.thrust_scale, c.thrust_bias);
+  sp[3] = L::make(__saturatef(half_of<0>(sp[3])), __saturatef(half_of<1>(sp[3])));  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
+  const uint32_t k0a = c.seed_lo ^ (c.env_lo + (uint32_t)i0), k0b = c.seed_lo ^ (c.env_lo + (uint32_t)i1);
+  const uint32_t k1a = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
+  const uint32_t k1b = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i1) >> 32));
+  const int nsub = c.n_sub_step;
+#pragma unroll 1
+  for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call per env, two physics sub-steps
+    V apwm[4];
+    control_update<V>(p, c, sp, apwm);
+    V nz[4] = {splat<V>(0.f), splat<V>(0.f), splat<V>(0.f), splat<V>(0.f)};
+    uint4 ba = make_uint4(0u, 0u, 0u, 0u), bb = ba;
+    if (c.noise) {
+      ba = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e0.rng_ctr, 0u), k0a, k1a);
+      if (kLanes == 2) bb = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e1.rng_ctr, 0u), k0b, k1b);
+      if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.x, bb.x), make_uint2(ba.y, bb.y), c.noise_k, nz);
+      else normal4_scaled<V>(ba.x, ba.y, c.noise_k, nz);
     }
+    physics_substep<V>(p, c, apwm, nz, false);
+    if (c.noise) {
+      if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.z, bb.z), make_uint2(ba.w, bb.w), c.noise_k, nz);
+      else normal4_scaled<V>(ba.z, ba.w, c.noise_k, nz);
+    }
+    physics_substep<V>(p, c, apwm, nz, j + 2 == nsub);
   }
-  if (i0 >= end) return;
-  const bool has1 = kLanes == 2 && i0 + kB < end;
-  const int64_t i1 = has1 ? i0 + kB : i0;  // a thread without a second env computes its first one twice, stores it once
+  unpack_lane<0>(e0, p);
+  if (kLanes == 2) unpack_lane<1>(e1, p);
+}
+
+// the paired sub-step loop: nsub sub-steps (even) towards a fixed setpoint, noise stream `stream`
+QX_DI void substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float spz, const float thrust, const int nsub, const uint32_t stream, const int64_t i0) {
+  CoreS p;
+  pack_core_s(p, e0);
+  const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i0);
+  const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
+#pragma unroll 1
+  for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call, two physics sub-steps
+    f2 apwm[2];
+    control_update_s(p, c, spxy, spz, thrust, apwm);
+    f2 nz[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    if (c.noise) {
+      b = env_philox(make_uint4((uint32_t)j >> 1, stream, e0.rng_ctr, 0u), k0, k1);
+      normal4_scaled_s(b.x, b.y, c.noise_k, nz);
+    }
+    physics_substep_s(p, c, apwm, nz, false);
+    if (c.noise) normal4_scaled_s(b.z, b.w, c.noise_k, nz);
+    physics_substep_s(p, c, apwm, nz, j + 2 == nsub);
+  }
+  unpack_core_s(e0, p);
+}
+// hot_substeps for V = S1: one env per thread with its own components paired (qx_model.cuh, CoreS)
+template <>
+QX_DI void hot_substeps<S1>(const DevConfig& c, Env& e0, Env&, const float4 av0, const float4, const int64_t i0, const int64_t) {
+  const f2 spxy = vmul(f2{av0.x, av0.y}, cpair(c.act_scale[0], c.act_scale[1]));  // hover.py:337-341
+  const float spz = __fmul_rn(av0.z, c.act_scale[2]);
+  const float thrust = __saturatef(fmaf(av0.w, c.thrust_scale, c.thrust_bias));  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
+  substeps_s(c, e0, spxy, spz, thrust, c.n_sub_step, STREAM_STEP, i0);
+}
+
+// reset() of one queued env on the paired code (hover.py:72-113: respawn, the idle Aviary.step()s with a zero setpoint, first
+// observation): what run_env<MODE_RESET_QUEUE> does, in the register budget of the hot kernels.  NC = false inside the merged
+// launch, whose own step phase stored the planes this reads.
+template <bool NC>
+QX_DI void hot_reset_env(const DevConfig& c, const StepArgs& a, const int64_t i) {
+  constexpr int OBS_DIM = QX_OBS_DIM_HOVER;
+  Env e;
+  load_env<NC>(e, a.state, a.n, i);
+  const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
+  const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i) >> 32));
+  respawn(e, c, k0, k1);
+  substeps_s(c, e, f2{0.f, 0.f}, 0.f, 0.f, c.n_sub_reset, STREAM_RESET, i);  // set_mode(0): zero setpoint
+  const float act[4] = {0.f, 0.f, 0.f, 0.f};  // hover.py:101
+  float obs[OBS_DIM];
+  ObsAux x;
+  build_obs<QX_TASK_HOVER>(e, c, act, 1, true, obs, x);
+  if (a.obs) write_obs(obs, a.obs, i, a.obs_stride, a.obs_bf16 != 0);
+  store_env(e, a.state, a.n, i);
+}
+template <bool REF>
+__device__ __noinline__ void hot_reset_requeue(const DevConfig& cparam, const StepArgs& a, const int64_t i) {
+  DevConfig cref = cparam;
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
+  hot_reset_env<false>(c, a, i);
+}
+
+// one agent step of envs i0 (and i1 when V has two lanes) in the calling thread, state and actions from global memory
+template <bool REF, class V>
+QX_DI void hot_task(const DevConfig& c, const DevConfig& cparam, const StepArgs& a, const int64_t i0, const int64_t i1, const bool has1) {
+  constexpr int kLanes = Lane<V>::N;
   Env e0, e1;
   load_env_loop(e0, a.state, a.n, i0);
   if (kLanes == 2) load_env_loop(e1, a.state, a.n, i1);
@@ -521,44 +622,95 @@ __global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMin
   }
   const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0);
   const float4 av1 = kLanes == 2 ? __ldg(reinterpret_cast<const float4*>(a.actions) + i1) : av0;
-  {
-    typedef LaneOps<V> L;
-    Core<V> p;
-    L::pack(p, e0, e1);
-    V sp[4];  // hover.py:337-341
-    sp[0] = vmul(L::make(av0.x, av1.x), c.act_scale[0]);
-    sp[1] = vmul(L::make(av0.y, av1.y), c.act_scale[1]);
-    sp[2] = vmul(L::make(av0.z, av1.z), c.act_scale[2]);
-    sp[3] = vfma(L::make(av0.w, av1.w), c.thrust_scale, c.thrust_bias);
-    sp[3] = L::make(__saturatef(half_of<0>(sp[3])), __saturatef(half_of<1>(sp[3])));  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
-    const uint32_t k0a = c.seed_lo ^ (c.env_lo + (uint32_t)i0), k0b = c.seed_lo ^ (c.env_lo + (uint32_t)i1);
-    const uint32_t k1a = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
-    const uint32_t k1b = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i1) >> 32));
-    const int nsub = c.n_sub_step;
-#pragma unroll 1
-    for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call per env, two physics sub-steps
-      V apwm[4];
-      control_update<V>(p, c, sp, apwm);
-      V nz[4] = {splat<V>(0.f), splat<V>(0.f), splat<V>(0.f), splat<V>(0.f)};
-      uint4 ba = make_uint4(0u, 0u, 0u, 0u), bb = ba;
-      if (c.noise) {
-        ba = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e0.rng_ctr, 0u), k0a, k1a);
-        if (kLanes == 2) bb = env_philox(make_uint4((uint32_t)j >> 1, STREAM_STEP, e1.rng_ctr, 0u), k0b, k1b);
-        if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.x, bb.x), make_uint2(ba.y, bb.y), c.noise_k, nz);
-        else normal4_scaled<V>(ba.x, ba.y, c.noise_k, nz);
-      }
-      physics_substep<V>(p, c, apwm, nz, false);
-      if (c.noise) {
-        if constexpr (kLanes == 2) normal4_scaled<V>(make_uint2(ba.z, bb.z), make_uint2(ba.w, bb.w), c.noise_k, nz);
-        else normal4_scaled<V>(ba.z, ba.w, c.noise_k, nz);
-      }
-      physics_substep<V>(p, c, apwm, nz, j + 2 == nsub);
-    }
-    unpack_lane<0>(e0, p);
-    if (kLanes == 2) unpack_lane<1>(e1, p);
-  }
+  hot_substeps<V>(c, e0, e1, av0, av1, i0, i1);
   hot_epilogue<REF>(e0, c, a, i0, av0);
   if (has1) hot_epilogue<REF>(e1, c, a, i1, av1);
+}
+
+QX_DI unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// The unit of work is a warp task: 32 x lanes consecutive envs (lane l of the warp owns env base + l, and base + 32 + l
+// with two lanes); warp w of block b runs task b * warps + w.
+//
+// MERGED = false: the reset queue is drained by a second launch (MODE_RESET_QUEUE).
+//
+// MERGED = true (auto-reset): ONE launch per agent step.  Every block takes a ticket when it is done; the blocks holding
+// the last `a.drainers` tickets (the last resident wave -- at most that many blocks can still be running or waiting
+// when they arrive, so they all fit on the SMs and the wait below cannot deadlock) stay, wait until every block has
+// retired, and drain the reset queue the step phase filled -- in full warps, like the separate launch, but without the
+// second launch and the idle gap before it.  Only a thread that queued an env issues a fence (after its stores, before
+// its block's ticket): the queue entry and that env's planes are all a drainer reads.  The last block to leave re-arms
+// the counters for the next launch and publishes the queue length for qx_done_queue.
+//
+// Measured and rejected (B200, 1 Mi envs; profiles/k1_r2_merged.md): a persistent grid whose warps draw tasks from a
+// counter -- 166 us against 139 + 8 us for two plain launches, long-scoreboard stalls doubled -- and the same with the
+// next task's planes staged into shared memory by cp.async.bulk behind an mbarrier (174 us).
+template <bool REF, int SHAPE, class V, bool MERGED>
+__global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMinBlocks) quadx_step_hot_kernel(const __grid_constant__ DevConfig cparam,
+                                                                                                                 const __grid_constant__ StepArgs a) {
+  constexpr int kB = HotShape<SHAPE>::kBlock, kLanes = Lane<V>::N, kWarps = kB / 32, kTask = 32 * kLanes;
+  DevConfig cref = cparam;
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
+  const int64_t end = a.env_begin + a.env_count;
+  const int64_t i0 = a.env_begin + ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * kTask + (threadIdx.x & 31u);
+  if (i0 < end) {
+    const bool has1 = kLanes == 2 && i0 + 32 < end;
+    hot_task<REF, V>(c, cparam, a, i0, has1 ? i0 + 32 : i0, has1);  // a thread without a second env computes its first one twice, stores it once
+  }
+  if constexpr (MERGED) {
+    ResetQueue* const q = a.queue;
+    __shared__ unsigned int s_ticket;
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&q->tasks_done, 1u);
+    __syncthreads();
+    if (s_ticket + a.drainers < gridDim.x) return;
+    if (threadIdx.x == 0) {
+      unsigned int ns = 64u;
+      while (ld_acquire_u32(&q->tasks_done) < gridDim.x) { __nanosleep(ns); if (ns < 512u) ns += ns; }
+    }
+    __syncthreads();
+    const unsigned int cnt = ld_acquire_u32(&q->count);
+#pragma unroll 1
+    while (cnt != 0u) {
+      unsigned int r = 0u;
+      if ((threadIdx.x & 31u) == 0u) r = atomicAdd(&q->next_reset, 32u);
+      r = __shfl_sync(0xffffffffu, r, 0);
+      if (r >= cnt) break;
+      if (r + (threadIdx.x & 31u) < cnt) {
+        const int64_t ie = (int64_t)__ldcg(&q->idx[r + (threadIdx.x & 31u)]);
+        if (a.paired_reset) hot_reset_requeue<REF>(cparam, a, ie);
+        else run_env_requeue<REF>(cparam, a, ie);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int n_drain = a.drainers < gridDim.x ? a.drainers : gridDim.x;
+      if (atomicAdd(&q->exit_ticket, 1u) == n_drain - 1u) {
+        q->published = cnt; q->count = 0u; q->tasks_done = 0u; q->next_reset = 0u; q->exit_ticket = 0u;
+      }
+    }
+  }
+}
+
+// MODE_RESET_QUEUE on the paired code: the second launch of the two-launch step
+template <bool REF>
+__global__ void __launch_bounds__(128, 4) quadx_reset_hot_kernel(const __grid_constant__ DevConfig cparam, const __grid_constant__ StepArgs a) {
+  DevConfig cref = cparam;
+  if (REF) apply_ref_constants(cref);
+  const DevConfig& c = REF ? cref : cparam;
+  const unsigned int cnt = *reinterpret_cast<volatile unsigned int*>(&a.queue->count);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&a.queue->ticket, 1u) == gridDim.x - 1) { a.queue->count = 0u; a.queue->ticket = 0u; }
+  }
+  for (unsigned int t = blockIdx.x * 128 + threadIdx.x; t < cnt; t += gridDim.x * 128) hot_reset_env<true>(c, a, (int64_t)a.queue->idx[t]);
 }
 
 // debug / measurement hook: SM clock and wall clock of one thread, so that two samples give the average SM frequency
@@ -584,10 +736,13 @@ struct QxHandle {
   bool ref_constants;  // the model constants equal the reference's literals bit for bit: run the specialised kernels
   bool hot_ok;         // hover, flight mode 0, control every 2nd sub-step: the lean one-step kernel applies
   int hot_mode;        // QX_HOT env var at qx_create: -1 default (large batches), 0 never, 1 always
-  int hot_lanes;       // QX_LANES: 1 one env per thread, 2 two envs per thread on packed f32x2, 3 two envs on scalar FP instructions
+  int paired_reset;    // QX_PAIRED_RESET (default 1 where it applies): queued envs are re-created by the paired code in the hot kernels' register budget
+  int hot_lanes;       // QX_LANES: 1 one env per thread (scalar), 2 two envs per thread on packed f32x2, 4 one env per thread with its own components paired (f32x2)
   int hot_shape;       // QX_SHAPE: launch shape (HotShape)
   int stream_stores;   // QX_STREAM_STORES: 0 plain stores, 1 evict-first for obs / reward / flags, 2 also for the state planes
-  int prefetch_blocks; // QX_PREFETCH: L2 prefetch distance of the hot kernel in blocks (-1: one wave of resident blocks, 0: off)
+  int merged;          // QX_MERGED: 1 (default) the hot kernel also drains the reset queue (one launch per step), 0 separate reset launch
+  int sm_count;
+  int hot_grid;        // blocks of one resident wave of the merged launch (SMs x blocks per SM from the occupancy calculator), 0 = not computed yet
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
@@ -740,7 +895,7 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
 }
 
 static bool matches_ref_constants(const qx::DevConfig& d);
-constexpr int kDefaultHotLanes = 1, kDefaultShape1 = 4, kDefaultShape2 = 0, kDefaultPrefetch = 0;
+constexpr int kDefaultHotLanes = 4, kDefaultShape1 = 4, kDefaultShape2 = 0;  // measured on B200, profiles/k1_r2_variants.md
 
 extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uint64_t env_id0, int device, QxHandle** out) {
   if (!cfg || !out || n_envs <= 0) return fail(QX_EINVAL, "qx_create: bad arguments");
@@ -765,10 +920,13 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
   h->hot_mode = env_int("QX_HOT", -1);
   h->hot_lanes = env_int("QX_LANES", kDefaultHotLanes);
-  if (h->hot_lanes < 1 || h->hot_lanes > 3) h->hot_lanes = kDefaultHotLanes;
-  h->hot_shape = env_int("QX_SHAPE", h->hot_lanes == 1 ? kDefaultShape1 : kDefaultShape2);
-  if (h->hot_shape < 0 || h->hot_shape >= qx::kHotShapes) h->hot_shape = h->hot_lanes == 1 ? kDefaultShape1 : kDefaultShape2;
-  h->prefetch_blocks = env_int("QX_PREFETCH", kDefaultPrefetch);
+  if (h->hot_lanes != 1 && h->hot_lanes != 2 && h->hot_lanes != 4) h->hot_lanes = kDefaultHotLanes;
+  if (h->hot_lanes == 4 && !(cfg->spawn_throttle >= 0.f && cfg->pwm_idle >= 0.f)) h->hot_lanes = 1;  // the paired code assumes throttles >= 0
+  h->hot_shape = env_int("QX_SHAPE", h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2);
+  if (h->hot_shape < 0 || h->hot_shape >= qx::kHotShapes || h->hot_shape == 1 || h->hot_shape == 2) h->hot_shape = h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2;
+  h->paired_reset = (h->hot_ok && (h->dev.n_sub_reset & 1) == 0 && cfg->spawn_throttle >= 0.f && cfg->pwm_idle >= 0.f && env_int("QX_PAIRED_RESET", 1)) ? 1 : 0;
+  h->merged = env_int("QX_MERGED", 0);  // measured: saves the second launch (~5 us) when nothing finishes, loses ~13 us when the queue is not empty
+  h->sm_count = prop.multiProcessorCount;
   h->stream_stores = env_int("QX_STREAM_STORES", 0);
   cudaError_t e = cudaMalloc(&h->state, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(qx::Stats));
@@ -868,32 +1026,53 @@ static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream
   }
 }
 
+template <bool REF, int SHAPE, class V>
+static cudaError_t launch_hot_kernel(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  constexpr int B = qx::HotShape<SHAPE>::kBlock, per = 32 * qx::Lane<V>::N, warps = B / 32;
+  const int64_t n_tasks = (a.env_count + per - 1) / per;
+  unsigned grid = (unsigned)((n_tasks + warps - 1) / warps);
+  if (a.merged) {
+    if (h->hot_grid == 0) {
+      int per_sm = 0;
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qx::quadx_step_hot_kernel<REF, SHAPE, V, true>, B, 0);
+      if (e != cudaSuccess) return e;
+      h->hot_grid = h->sm_count * (per_sm > 0 ? per_sm : 1);
+    }
+    qx::StepArgs am = a;
+    am.drainers = (uint32_t)h->hot_grid;
+    qx::quadx_step_hot_kernel<REF, SHAPE, V, true><<<grid, B, 0, s>>>(h->dev, am);
+    return cudaSuccess;
+  }
+  qx::quadx_step_hot_kernel<REF, SHAPE, V, false><<<grid, B, 0, s>>>(h->dev, a);
+  return cudaSuccess;
+}
 template <int SHAPE, class V>
-static void launch_hot_one(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
-  constexpr int B = qx::HotShape<SHAPE>::kBlock, per = B * qx::Lane<V>::N;
-  const unsigned grid = (unsigned)((a.env_count + per - 1) / per);
-  if (h->ref_constants) qx::quadx_step_hot_kernel<true, SHAPE, V><<<grid, B, 0, s>>>(h->dev, a);
-  else qx::quadx_step_hot_kernel<false, SHAPE, V><<<grid, B, 0, s>>>(h->dev, a);
+static cudaError_t launch_hot_one(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+  return h->ref_constants ? launch_hot_kernel<true, SHAPE, V>(h, a, s) : launch_hot_kernel<false, SHAPE, V>(h, a, s);
 }
 template <class V>
-static void launch_hot_shape(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
+static cudaError_t launch_hot_shape(QxHandle* h, const qx::StepArgs& a, cudaStream_t s) {
   switch (h->hot_shape) {
-    case 1: launch_hot_one<1, V>(h, a, s); break;
-    case 2: launch_hot_one<2, V>(h, a, s); break;
-    case 3: launch_hot_one<3, V>(h, a, s); break;
-    case 4: launch_hot_one<4, V>(h, a, s); break;
-    case 5: launch_hot_one<5, V>(h, a, s); break;
-    default: launch_hot_one<0, V>(h, a, s); break;
+    case 3: return launch_hot_one<3, V>(h, a, s);
+    case 4: return launch_hot_one<4, V>(h, a, s);
+    case 5: return launch_hot_one<5, V>(h, a, s);
+    default: return launch_hot_one<0, V>(h, a, s);
   }
 }
+// the merged launch applies to a handle as a whole (qx_step_end and qx_done_queue depend on it)
+static bool use_merged(const QxHandle* h);
 // one agent step of the lean kernel (replaces MODE_STEP_DEFER, or MODE_STEP_INLINE with k = 1 and no auto-reset)
-static int launch_hot(QxHandle* h, qx::StepArgs a, cudaStream_t s) {
+static int launch_hot(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
-  a.prefetch_blocks = h->prefetch_blocks;
   a.stream_stores = h->stream_stores;
-  if (h->hot_lanes == 2) launch_hot_shape<qx::P2<true>>(h, a, s);
-  else if (h->hot_lanes == 3) launch_hot_shape<qx::P2<false>>(h, a, s);
-  else launch_hot_shape<float>(h, a, s);
+  a.merged = (mode == qx::MODE_STEP_DEFER && use_merged(h)) ? h->merged : 0;
+  a.paired_reset = h->paired_reset;
+  if (a.merged) a.queue = h->queue;
+  cudaError_t e;
+  if (h->hot_lanes == 2) e = launch_hot_shape<qx::P2<true>>(h, a, s);
+  else if (h->hot_lanes == 4) e = launch_hot_shape<qx::S1>(h, a, s);
+  else e = launch_hot_shape<float>(h, a, s);
+  QX_CUDA(e);
   ++g_launches;
   QX_CUDA(cudaGetLastError());
   return QX_OK;
@@ -904,11 +1083,21 @@ static bool use_hot(const QxHandle* h) {  // decided per handle, not per launch:
   if (!h->hot_ok || h->hot_mode == 0) return false;
   return h->hot_mode == 1 || h->n >= kHotMinEnvs;
 }
+static bool use_merged(const QxHandle* h) { return use_hot(h) && h->cfg.auto_reset && h->merged; }
 
 static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (a.env_count == 0) { a.env_begin = 0; a.env_count = h->n; }
   if (use_hot(h) && (mode == qx::MODE_STEP_DEFER || (mode == qx::MODE_STEP_INLINE && a.k == 1 && !h->cfg.auto_reset)))
-    return launch_hot(h, a, s);
+    return launch_hot(h, mode, a, s);
+  if (mode == qx::MODE_RESET_QUEUE && use_hot(h) && h->paired_reset) {
+    const unsigned blocks = (unsigned)((a.env_count + 127) / 128);
+    const unsigned g = blocks < (unsigned)qx::kResetQueueBlocks ? blocks : (unsigned)qx::kResetQueueBlocks;
+    if (h->ref_constants) qx::quadx_reset_hot_kernel<true><<<g, 128, 0, s>>>(h->dev, a);
+    else qx::quadx_reset_hot_kernel<false><<<g, 128, 0, s>>>(h->dev, a);
+    ++g_launches;
+    QX_CUDA(cudaGetLastError());
+    return QX_OK;
+  }
   if (h->dev.task == QX_TASK_YAW) launch_task<QX_TASK_YAW, false, false>(h, mode, a, s);
   else if (h->dev.flight_mode != 0) launch_task<QX_TASK_HOVER, true, false>(h, mode, a, s);
   else if (h->ref_constants) launch_task<QX_TASK_HOVER, false, true>(h, mode, a, s);
@@ -954,6 +1143,7 @@ extern "C" int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_
   if (!h) return fail(QX_EINVAL, "qx_step_end: null handle");
   if (!h->cfg.auto_reset) return QX_OK;
   if (obs_dev && obs_stride < h->dev.obs_dim) return fail(QX_EINVAL, "qx_step_end: obs_stride < obs_dim");
+  if (use_merged(h)) return QX_OK;  // the step launch already re-created the finished envs
   qx::StepArgs a{};
   a.state = h->state; a.obs = obs_dev; a.obs_stride = obs_stride; a.obs_bf16 = obs_dtype == QX_OBS_BF16;
   a.stats = h->stats; a.queue = h->queue; a.n = h->n; a.k = 1;
@@ -990,7 +1180,7 @@ extern "C" int qx_debug_clock_probe(unsigned long long* out_dev, void* stream) {
 
 extern "C" int qx_done_queue(QxHandle* h, const uint32_t** count_dev, const uint32_t** idx_dev) {
   if (!h || !count_dev || !idx_dev) return fail(QX_EINVAL, "qx_done_queue: bad arguments");
-  *count_dev = &h->queue->count;
+  *count_dev = use_merged(h) ? &h->queue->published : &h->queue->count;  // the merged launch zeroes count itself when it ends
   *idx_dev = h->queue->idx;
   return QX_OK;
 }
@@ -1075,7 +1265,7 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     if (h->cfg.auto_reset && (n > kInlineResetMaxEnvs || (h->hot_mode == 1 && h->hot_ok))) {
       rc = launch(h, qx::MODE_STEP_DEFER, a, h->stream);
       if (rc) return rc;
-      rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);
+      if (!use_merged(h)) rc = launch(h, qx::MODE_RESET_QUEUE, a, h->stream);
     } else {  // no auto-reset, or a small batch: one launch (see qx_step)
       rc = launch(h, qx::MODE_STEP_INLINE, a, h->stream);
     }

@@ -95,7 +95,9 @@ struct Env : Core<float> {
   float cp[18];
 };
 
-QX_DI float4 ldg4(const float4* p) { return __ldg(p); }
+// NC: the read-only path (ld.global.nc) -- only where no thread of the same launch wrote the word before; the reset phase
+// of the merged step kernel re-reads planes its own launch stored and takes the L2-coherent path instead.
+template <bool NC = true> QX_DI float4 ldg4(const float4* p) { return NC ? __ldg(p) : __ldcg(p); }
 
 constexpr int kLoopPlanes = 8;  // planes 0..7: sub-step loop state
 QX_DI void unpack_loop_planes(Env& e, const float4 (&v)[kLoopPlanes]) {
@@ -110,21 +112,26 @@ QX_DI void unpack_loop_planes(Env& e, const float4 (&v)[kLoopPlanes]) {
   e.contact = (e.flags & F_CONTACT) != 0u;
   e.sqx = e.qx; e.sqy = e.qy; e.sqz = e.qz; e.sqw = e.qw; e.spx = e.px; e.spy = e.py; e.spz = e.pz;
 }
+template <bool NC = true>
 QX_DI void load_env_loop(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
   float4 v[kLoopPlanes];
 #pragma unroll
-  for (int p = 0; p < kLoopPlanes; ++p) v[p] = ldg4(st + (int64_t)p * n + i);
+  for (int p = 0; p < kLoopPlanes; ++p) v[p] = ldg4<NC>(st + (int64_t)p * n + i);
   unpack_loop_planes(e, v);
 }
-QX_DI void load_env_tail(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
-  const float4 k = ldg4(st + 8 * n + i), l = ldg4(st + 9 * n + i), m = ldg4(st + 10 * n + i);
+QX_DI void unpack_tail_planes(Env& e, const float4 k, const float4 l, const float4 m) {
   e.peul[0] = k.x; e.peul[1] = k.y; e.peul[2] = k.z; e.ep_ret = k.w;
   e.pa[0] = l.x; e.pa[1] = l.y; e.pa[2] = l.z; e.pa[3] = l.w;
   e.pcx = m.x; e.pcy = m.y; e.parea = m.z; e.pratio = m.w;
 }
+template <bool NC = true>
+QX_DI void load_env_tail(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
+  unpack_tail_planes(e, ldg4<NC>(st + 8 * n + i), ldg4<NC>(st + 9 * n + i), ldg4<NC>(st + 10 * n + i));
+}
+template <bool NC = true>
 QX_DI void load_env(Env& e, const float4* __restrict__ st, int64_t n, int64_t i) {
-  load_env_loop(e, st, n, i);
-  load_env_tail(e, st, n, i);
+  load_env_loop<NC>(e, st, n, i);
+  load_env_tail<NC>(e, st, n, i);
 }
 
 template <bool CS = false>
@@ -382,11 +389,10 @@ QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], cons
     rr[m] = vabsmul(t, t);                // rpm |rpm| / max_rpm^2
   }
   T fz, tx, ty, tz;                       // r x F = (y F, -x F, 0)
-  if (c.x_layout) {
-    const T a = vadd(rr[0], rr[3]), b = vadd(rr[1], rr[2]), ee = vadd(rr[0], rr[2]), f = vadd(rr[1], rr[3]);
-    const T cc = vadd(rr[0], rr[1]), d = vadd(rr[2], rr[3]);
-    fz = vadd(a, b);
-    tx = vmul(vsub(b, a), c.arm_k); ty = vmul(vsub(f, ee), c.arm_k); tz = vmul(vsub(d, cc), c.tq_k);
+  if (c.x_layout) {  // sums and differences of the motor pairs (0,2) and (1,3): the order the pair-packed kernel uses
+    const T s0 = vadd(rr[0], rr[2]), s1 = vadd(rr[1], rr[3]), d0 = vsub(rr[0], rr[2]), d1 = vsub(rr[1], rr[3]);
+    fz = vadd(s0, s1);
+    tx = vmul(vsub(d1, d0), c.arm_k); ty = vmul(vsub(s1, s0), c.arm_k); tz = vmul(vadd(d0, d1), -c.tq_k);
   } else {
     fz = vadd(vadd(rr[0], rr[1]), vadd(rr[2], rr[3]));
     tx = vmul(rr[0], c.arm_y[0]); ty = vmul(rr[0], c.arm_x[0]); tz = vmul(rr[0], c.torque_k[0]);
@@ -453,11 +459,12 @@ QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], cons
   const T dwm1 = vmul(s, vfma(s, vfma(s, -1.f / 720.f, 1.f / 24.f), -0.5f));  // cos(|w| h / 2) - 1
   const T dx = vmul(e.wx, kq), dy = vmul(e.wy, kq), dz = vmul(e.wz, kq);
   const Neg<T> ndx = mkneg(dx), ndy = mkneg(dy), ndz = mkneg(dz);
+  // (term order chosen so that (nx, ny) and (nz, nw) are each one chain of pair operations in the pair-packed kernel)
   const T nx = vadd(x, vfnma(z, ndy, vfma(y, dz, vfma(x, dwm1, vmul(w, dx)))));
-  const T ny = vadd(y, vfnma(x, ndz, vfma(z, dx, vfma(y, dwm1, vmul(w, dy)))));
+  const T ny = vadd(y, vfma(z, dx, vfnma(x, ndz, vfma(y, dwm1, vmul(w, dy)))));
   const T nzq = vadd(z, vfnma(y, ndx, vfma(x, dy, vfma(z, dwm1, vmul(w, dz)))));
-  const T nw = vadd(w, vfnma(z, ndz, vfnma(y, ndy, vfnma(x, ndx, vmul(w, dwm1)))));
-  const T inv = vrsqrt(vfma(nw, nw, vfma(nzq, nzq, vfma(ny, ny, vmul(nx, nx)))));
+  const T nw = vadd(w, vfnma(y, ndy, vfnma(x, ndx, vfnma(z, ndz, vmul(w, dwm1)))));
+  const T inv = vrsqrt(vadd(vfma(nzq, nzq, vmul(nx, nx)), vfma(nw, nw, vmul(ny, ny))));
   e.qx = vmul(nx, inv); e.qy = vmul(ny, inv); e.qz = vmul(nzq, inv); e.qw = vmul(nw, inv);
   // floor stand-in
   const auto below = vlt(e.pz, c.floor_z);
@@ -474,6 +481,209 @@ QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], cons
     e.svb[1] = vfma(a21, e.vz, vfma(a11, e.vy, vmul(a01, e.vx)));
     e.svb[2] = vfma(a22, e.vz, vfma(a12, e.vy, vmul(a02, e.vx)));
     if (last) { e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.px; e.spy = e.py; e.spz = e.pz; }
+  }
+}
+
+// ===========================================================================
+// The same sub-step for ONE env with its own components paired: (x, y) of every vector, motors (0, 1) and (2, 3) and
+// (z, w) of the quaternion sit in aligned register pairs, so that the component-wise arithmetic issues as packed
+// FFMA2 / FMUL2 / FADD2 (one issue slot for two components; the FMA pipe is busy for two cycles either way, but issue
+// slots are what bound this kernel).  Every component goes through the same IEEE operations in the same order as in
+// physics_substep<float> / control_update<float> above, so the two are bitwise identical -- with one precondition:
+// motor throttles are never negative (|t| t == t t), which holds for flight mode 0 with spawn_throttle >= 0 and
+// pwm_idle >= 0 (qx_create checks it before it selects this code).
+// ===========================================================================
+struct S1 {};  // lane tag: one env per thread, its own components paired
+template <> struct Lane<S1> { typedef bool mask; typedef uint32_t u32; static constexpr int N = 1; };
+struct CoreS {
+  f2 pxy, qxy, qzw, vxy, wxy, thr01, thr23, pixy, pexy, swbxy;
+  float pz, vz, wz, piz, pez, swbz, svb[3];
+  bool contact;
+  float sqx, sqy, sqz, sqw, spx, spy, spz;  // transient: pose part of the Aviary.state snapshot
+};
+QX_DI void pack_core_s(CoreS& p, const Core<float>& a) {
+  p.pxy = f2{a.px, a.py}; p.pz = a.pz; p.qxy = f2{a.qx, a.qy}; p.qzw = f2{a.qz, a.qw};
+  p.vxy = f2{a.vx, a.vy}; p.vz = a.vz; p.wxy = f2{a.wx, a.wy}; p.wz = a.wz;
+  p.thr01 = f2{a.thr[0], a.thr[1]}; p.thr23 = f2{a.thr[2], a.thr[3]};
+  p.pixy = f2{a.pi[0], a.pi[1]}; p.piz = a.pi[2]; p.pexy = f2{a.pe[0], a.pe[1]}; p.pez = a.pe[2];
+  p.swbxy = f2{a.swb[0], a.swb[1]}; p.swbz = a.swb[2];
+  p.svb[0] = a.svb[0]; p.svb[1] = a.svb[1]; p.svb[2] = a.svb[2];
+  p.contact = a.contact;
+  p.sqx = a.sqx; p.sqy = a.sqy; p.sqz = a.sqz; p.sqw = a.sqw; p.spx = a.spx; p.spy = a.spy; p.spz = a.spz;
+}
+QX_DI void unpack_core_s(Core<float>& a, const CoreS& p) {
+  a.px = p.pxy.x; a.py = p.pxy.y; a.pz = p.pz; a.qx = p.qxy.x; a.qy = p.qxy.y; a.qz = p.qzw.x; a.qw = p.qzw.y;
+  a.vx = p.vxy.x; a.vy = p.vxy.y; a.vz = p.vz; a.wx = p.wxy.x; a.wy = p.wxy.y; a.wz = p.wz;
+  a.thr[0] = p.thr01.x; a.thr[1] = p.thr01.y; a.thr[2] = p.thr23.x; a.thr[3] = p.thr23.y;
+  a.pi[0] = p.pixy.x; a.pi[1] = p.pixy.y; a.pi[2] = p.piz; a.pe[0] = p.pexy.x; a.pe[1] = p.pexy.y; a.pe[2] = p.pez;
+  a.swb[0] = p.swbxy.x; a.swb[1] = p.swbxy.y; a.swb[2] = p.swbz;
+  a.svb[0] = p.svb[0]; a.svb[1] = p.svb[1]; a.svb[2] = p.svb[2];
+  a.contact = p.contact;
+  a.sqx = p.sqx; a.sqy = p.sqy; a.sqz = p.sqz; a.sqw = p.sqw; a.spx = p.spx; a.spy = p.spy; a.spz = p.spz;
+}
+// a pair of config constants: when both halves are the same value ptxas uses the broadcast / immediate operand form
+QX_DI f2 cpair(float a, float b) { return f2{a, b}; }
+
+// 4 x noise_ratio N(0,1) of one env as two pairs (n0, n1), (n2, n3): normal4_scaled<float> with the two Box-Muller words paired
+QX_DI void normal4_scaled_s(uint32_t w0, uint32_t w1, float noise_k, f2 n[2]) {
+  const f2 u = vadd(f2{m12_lo16(w0), m12_lo16(w1)}, -0.99999237060546875f);
+  const f2 r2 = vmul(f2{__log2f(u.x), __log2f(u.y)}, noise_k);
+  const float ra = fsqrt(r2.x), rb = fsqrt(r2.y);
+  const f2 t = vfma(f2{m12_hi16(w0), m12_hi16(w1)}, 6.28318530718f, -9.42473002f);
+  n[0] = vmul(f2{__cosf(t.x), __sinf(t.x)}, ra);
+  n[1] = vmul(f2{__cosf(t.y), __sinf(t.y)}, rb);
+}
+
+// control_update<float>, roll / pitch as one pair; spxy = rate setpoints (roll, pitch), spz = yaw rate, thrust = sp[3]
+QX_DI void control_update_s(CoreS& e, const DevConfig& c, const f2 spxy, const float spz, const float thrust, f2 apwm[2]) {
+  const f2 err = vsub(spxy, e.swbxy);
+  f2 pi = vfma(err, cpair(c.kiT[0], c.kiT[1]), e.pixy);
+  pi = f2{clampf(pi.x, -c.lim[0], c.lim[0]), clampf(pi.y, -c.lim[1], c.lim[1])};
+  e.pixy = pi;
+  f2 u = vfma(err, cpair(c.kp[0], c.kp[1]), pi);
+  if (c.kd_T[0] != 0.f || c.kd_T[1] != 0.f) {
+    const f2 ud = vfma(vsub(err, e.pexy), cpair(c.kd_T[0], c.kd_T[1]), u);
+    u = f2{c.kd_T[0] != 0.f ? ud.x : u.x, c.kd_T[1] != 0.f ? ud.y : u.y};
+  }
+  e.pexy = err;
+  const float cmd0 = clampf(u.x, -c.lim[0], c.lim[0]), cmd1 = clampf(u.y, -c.lim[1], c.lim[1]);
+  const float errz = spz - e.swbz;
+  e.piz = clampf(fmaf(errz, c.kiT[2], e.piz), -c.lim[2], c.lim[2]);
+  float uz = fmaf(errz, c.kp[2], e.piz);
+  if (c.kd_T[2] != 0.f) uz = fmaf(errz - e.pez, c.kd_T[2], uz);
+  const float cmd2 = clampf(uz, -c.lim[2], c.lim[2]);
+  e.pez = errz;
+  float pwm[4];
+  if (c.x_mixer) {  // rows (-,-,-,+) (+,+,-,+) (+,-,+,+) (-,+,+,+): shared sums and differences
+    const float s = __fadd_rn(cmd0, cmd1), d = __fsub_rn(cmd0, cmd1), a = __fsub_rn(thrust, cmd2), b = __fadd_rn(thrust, cmd2);
+    pwm[0] = __fsub_rn(a, s); pwm[1] = __fadd_rn(a, s); pwm[2] = __fadd_rn(b, d); pwm[3] = __fsub_rn(b, d);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      pwm[m] = fmaf(thrust, c.map[4 * m + 3], fmaf(cmd2, c.map[4 * m + 2], fmaf(cmd1, c.map[4 * m + 1], __fmul_rn(cmd0, c.map[4 * m + 0]))));
+  }
+  const float high = fmaxf(fmaxf(pwm[0], pwm[1]), fmaxf(pwm[2], pwm[3]));
+  if (high > 1.0f) {
+    const float inv = frcp(high);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pwm[m] = __fmul_rn(pwm[m], inv);
+  }
+  const float low = fminf(fminf(pwm[0], pwm[1]), fminf(pwm[2], pwm[3]));
+  if (low < c.pwm_idle) {
+    const float k = __fmul_rn(__fsub_rn(c.pwm_idle, low), frcp(__fsub_rn(1.0f, low)));
+#pragma unroll
+    for (int m = 0; m < 4; ++m) pwm[m] = fmaf(__fsub_rn(1.0f, pwm[m]), k, pwm[m]);
+  }
+  apwm[0] = vmul(f2{pwm[0], pwm[1]}, c.lag_alpha);
+  apwm[1] = vmul(f2{pwm[2], pwm[3]}, c.lag_alpha);
+}
+
+QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], const f2 nz[2], const bool last) {
+  // motors: first-order lag, multiplicative noise, thrust and torques
+  f2 t01 = vfma(e.thr01, c.one_m_alpha, apwm[0]), t23 = vfma(e.thr23, c.one_m_alpha, apwm[1]);
+  t01 = vfma(nz[0], t01, t01); t23 = vfma(nz[1], t23, t23);
+  e.thr01 = t01; e.thr23 = t23;
+  const f2 rr01 = vmul(t01, t01), rr23 = vmul(t23, t23);  // throttle >= 0 (see above): |t| t == t t
+  float fz, tx, ty, tz;
+  if (c.x_layout) {
+    const f2 s = vadd(rr01, rr23), d = vsub(rr01, rr23);
+    fz = __fadd_rn(s.x, s.y);
+    const f2 txy = vmul(f2{__fsub_rn(d.y, d.x), __fsub_rn(s.y, s.x)}, c.arm_k);
+    tx = txy.x; ty = txy.y; tz = __fmul_rn(__fadd_rn(d.x, d.y), -c.tq_k);
+  } else {
+    const float rr[4] = {rr01.x, rr01.y, rr23.x, rr23.y};
+    fz = __fadd_rn(__fadd_rn(rr[0], rr[1]), __fadd_rn(rr[2], rr[3]));
+    tx = __fmul_rn(rr[0], c.arm_y[0]); ty = __fmul_rn(rr[0], c.arm_x[0]); tz = __fmul_rn(rr[0], c.torque_k[0]);
+#pragma unroll
+    for (int m = 1; m < 4; ++m) { tx = fmaf(rr[m], c.arm_y[m], tx); ty = fmaf(rr[m], c.arm_x[m], ty); tz = fmaf(rr[m], c.torque_k[m], tz); }
+  }
+  if (c.thrust_k != 1.0f) fz = __fmul_rn(fz, c.thrust_k);
+  // drag from the (stale) snapshot, body frame (|v| does not pack: scalar)
+  const float fbx = __fmul_rn(vabsmul(e.svb[0], c.ndrag_c), e.svb[0]);
+  const float fby = __fmul_rn(vabsmul(e.svb[1], c.ndrag_c), e.svb[1]);
+  const float fbz = fmaf(vabsmul(e.svb[2], c.ndrag_c), e.svb[2], fz);
+  {
+    const float dq = e.contact ? 0.f : c.ndrag_pqr;  // no angular drag while resting on the floor
+    tx = fmaf(vabsmul(e.swbxy.x, dq), e.swbxy.x, tx);
+    ty = fmaf(vabsmul(e.swbxy.y, dq), e.swbxy.y, ty);
+    tz = fmaf(vabsmul(e.swbz, dq), e.swbz, tz);
+  }
+  // rotation matrix of the current attitude
+  const float x = e.qxy.x, y = e.qxy.y, z = e.qzw.x, w = e.qzw.y;
+  const f2 xy2 = vadd(e.qxy, e.qxy);
+  const float x2 = xy2.x, y2 = xy2.y, z2 = __fadd_rn(z, z);
+  const f2 wxy2 = vmul(xy2, w);
+  const float wx = wxy2.x, wy = wxy2.y, wz = __fmul_rn(w, z2);
+  const float r00 = fmaf(-y, y2, fmaf(-z, z2, 1.f)), r11 = fmaf(-x, x2, fmaf(-z, z2, 1.f)), r22 = fmaf(-x, x2, fmaf(-y, y2, 1.f));
+  const float r01 = fmaf(x, y2, -wz), r10 = fmaf(x, y2, wz);
+  const float r02 = fmaf(x, z2, wy), r20 = fmaf(x, z2, -wy);
+  const float r12 = fmaf(y, z2, -wx), r21 = fmaf(y, z2, wx);
+  if (c.state_stale) {  // QuadX.update_state runs before stepSimulation
+    e.swbxy = e.wxy; e.swbz = e.wz;
+    const float vx = e.vxy.x, vy = e.vxy.y;
+    e.svb[0] = fmaf(r20, e.vz, fmaf(r10, vy, __fmul_rn(r00, vx)));
+    e.svb[1] = fmaf(r21, e.vz, fmaf(r11, vy, __fmul_rn(r01, vx)));
+    e.svb[2] = fmaf(r22, e.vz, fmaf(r12, vy, __fmul_rn(r02, vx)));
+    if (last) { e.sqx = x; e.sqy = y; e.sqz = z; e.sqw = w; e.spx = e.pxy.x; e.spy = e.pxy.y; e.spz = e.pz; }
+  }
+  // angular half, body frame: (wx, wy) as a pair
+  {
+    const float owx = e.wxy.x, owy = e.wxy.y, owz = e.wz;
+    const f2 g = f2{__fmul_rn(owy, owz), __fmul_rn(owz, owx)};
+    e.wxy = vfma(g, cpair(c.gk[0], c.gk[1]), vfma(f2{tx, ty}, cpair(c.hI[0], c.hI[1]), e.wxy));
+    e.wz = c.gk[2] != 0.f ? fmaf(__fmul_rn(owx, owy), c.gk[2], fmaf(tz, c.hI[2], owz)) : fmaf(tz, c.hI[2], owz);
+  }
+  // linear half, world frame: (vx, vy) as a pair over the column pairs of R
+  {
+    const f2 acc = vfma(f2{r02, r12}, fbz, vfma(f2{r01, r11}, fby, vmul(f2{r00, r10}, fbx)));
+    e.vxy = vfma(acc, c.hm, e.vxy);
+    e.vz = __fadd_rn(fmaf(fmaf(r22, fbz, fmaf(r21, fby, __fmul_rn(r20, fbx))), c.hm, e.vz), -c.hg);
+  }
+  if (fmaxf(fmaxf(vabsmax(e.vxy.x, e.vxy.y), vabsmax(e.vz, e.wxy.x)), vabsmax(e.wxy.y, e.wz)) > c.vmax) {  // cold
+    e.vxy = f2{clampf(e.vxy.x, -c.vmax, c.vmax), clampf(e.vxy.y, -c.vmax, c.vmax)}; e.vz = clampf(e.vz, -c.vmax, c.vmax);
+    e.wxy = f2{clampf(e.wxy.x, -c.vmax, c.vmax), clampf(e.wxy.y, -c.vmax, c.vmax)}; e.wz = clampf(e.wz, -c.vmax, c.vmax);
+  }
+  e.pxy = vfma(e.vxy, c.h, e.pxy);
+  e.pz = fmaf(e.vz, c.h, e.pz);
+  // q <- q exp(h w_b / 2), then renormalise (same series as physics_substep)
+  {
+    const float nwx = e.wxy.x, nwy = e.wxy.y, nwz = e.wz;
+    const float s = __fmul_rn(fmaf(nwz, nwz, fmaf(nwy, nwy, __fmul_rn(nwx, nwx))), c.hh2);
+    const float kq = fmaf(s, fmaf(s, c.kq2, c.kq1), c.hh);
+    const float dwm1 = __fmul_rn(s, fmaf(s, fmaf(s, -1.f / 720.f, 1.f / 24.f), -0.5f));
+    const f2 dxy = vmul(e.wxy, kq);
+    const float dz = __fmul_rn(nwz, kq);
+    const f2 jq = f2{y, -x}, jd = f2{-dxy.y, dxy.x};
+    // (nx, ny) = (x, y) + w (dx, dy) + dwm1 (x, y) + dz (y, -x) + z (-dy, dx)
+    const f2 nxy = vadd(e.qxy, vfma(jd, z, vfma(jq, dz, vfma(e.qxy, dwm1, vmul(dxy, w)))));
+    // (nz, nw) = (z, w) + w (dz, dwm1) + z (dwm1, -dz) + (-x) (-dy, dx) + (-y) (dx, dy)
+    const f2 nzw = vadd(e.qzw, vfma(dxy, -y, vfma(jd, jq.y, vfma(f2{dwm1, -dz}, z, vmul(f2{dz, dwm1}, w)))));
+    const f2 m = vfma(nzw, nzw, vmul(nxy, nxy));
+    const float inv = frsqrt(__fadd_rn(m.x, m.y));
+    e.qxy = vmul(nxy, inv); e.qzw = vmul(nzw, inv);
+  }
+  // floor stand-in (cold)
+  const bool below = e.pz < c.floor_z;
+  if (below) {
+    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vxy = f2{0.f, 0.f};
+    const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
+    const float a20 = __fmul_rn(__fsub_rn(__fmul_rn(X, Z), __fmul_rn(W, Y)), 2.f), a21 = __fmul_rn(fmaf(Y, Z, __fmul_rn(W, X)), 2.f);
+    const float a22 = __fsub_rn(1.f, __fmul_rn(fmaf(X, X, __fmul_rn(Y, Y)), 2.f));
+    const float wzw = fmaf(a22, e.wz, fmaf(a21, e.wxy.y, __fmul_rn(a20, e.wxy.x)));  // world yaw rate survives
+    e.wxy = f2{__fmul_rn(a20, wzw), __fmul_rn(a21, wzw)}; e.wz = __fmul_rn(a22, wzw);
+  }
+  e.contact = below;
+  if (!c.state_stale) {
+    const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
+    const float X2 = X + X, Y2 = Y + Y, Z2 = Z + Z;
+    const float a00 = __fsub_rn(1.f, fmaf(Y2, Y, __fmul_rn(Z2, Z))), a01 = __fsub_rn(__fmul_rn(X, Y2), __fmul_rn(W, Z2)), a02 = fmaf(X, Z2, __fmul_rn(W, Y2));
+    const float a10 = fmaf(X, Y2, __fmul_rn(W, Z2)), a11 = __fsub_rn(1.f, fmaf(X2, X, __fmul_rn(Z2, Z))), a12 = __fsub_rn(__fmul_rn(Y, Z2), __fmul_rn(W, X2));
+    const float a20 = __fsub_rn(__fmul_rn(X, Z2), __fmul_rn(W, Y2)), a21 = fmaf(Y, Z2, __fmul_rn(W, X2)), a22 = __fsub_rn(1.f, fmaf(X2, X, __fmul_rn(Y2, Y)));
+    e.swbxy = e.wxy; e.swbz = e.wz;
+    e.svb[0] = fmaf(a20, e.vz, fmaf(a10, e.vxy.y, __fmul_rn(a00, e.vxy.x)));
+    e.svb[1] = fmaf(a21, e.vz, fmaf(a11, e.vxy.y, __fmul_rn(a01, e.vxy.x)));
+    e.svb[2] = fmaf(a22, e.vz, fmaf(a12, e.vxy.y, __fmul_rn(a02, e.vxy.x)));
+    if (last) { e.sqx = X; e.sqy = Y; e.sqz = Z; e.sqw = W; e.spx = e.pxy.x; e.spy = e.pxy.y; e.spz = e.pz; }
   }
 }
 

@@ -294,6 +294,8 @@ class PPOConfig:
     log_std_init: float = 0.0  # SB3 policy_kwargs log_std_init
     graph_update: bool = True  # replay captured optimiser steps instead of eager launches
     tf32_update: bool = True  # (fused_update=False only) library GEMMs of the torch update in TF32
+    lr_final_frac: float = 1.0  # linear learning-rate schedule (SB3 lr callable): lr * (1 - (1 - lr_final_frac) * progress), progress from
+    lr_anneal_iters: int = 0    # iteration / lr_anneal_iters clipped to 1 (0 = constant learning rate); fused update only
     fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
 
 
@@ -412,6 +414,8 @@ class FusedUpdater:
 
     def __init__(self, model: ActorCritic, packed: PackedPolicy, cfg: "PPOConfig", device, world: int = 1):
         self.model, self.packed, self.cfg, self.device, self.world = model, packed, cfg, torch.device(device), world
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.lib()
         od, ad = model.obs_dim, model.act_dim
         self.n_params = int(self.lib.ppo_update_num_params(od, ad))
@@ -455,6 +459,10 @@ class FusedUpdater:
         self.gradient(ro, tiles)
         self.apply()
 
+    def set_lr_scale(self, scale: float) -> None:
+        """Learning-rate schedule: later optimiser steps (graph replays included) use learning_rate * scale."""
+        check(self.lib.ppo_update_set_lr_scale(_p(self.workspace), float(scale), _stream(self.device)))
+
     @property
     def adam_steps(self) -> int:
         out = C.c_int64()
@@ -477,6 +485,8 @@ class PPOTrainer:
         """task: QX_TASK_HOVER (0, hover.py) or QX_TASK_YAW (1, yaw.py: 12-D obs, 1-D action)."""
         self.cfg, self.rank, self.world = cfg, rank, world
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type == "cuda" and dev.index is None:  # "cuda" -> "cuda:<current>": tensors report an indexed device
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         if cfg.tf32_update:
             torch.backends.cuda.matmul.allow_tf32 = True
@@ -494,6 +504,7 @@ class PPOTrainer:
                                                                    capturable=bool(cfg.graph_update and world == 1))
         self._epoch_graph = None
         self.num_timesteps = 0
+        self._iteration = 0
         self._flat_grad = None
         self.gen = torch.Generator(device=dev).manual_seed(cfg.seed + 1000 + rank)
 
@@ -654,6 +665,10 @@ class PPOTrainer:
         return {"pg": out[0], "vf": out[1], "kl": out[2], "clipfrac": out[3]}
 
     def learn_iteration(self) -> dict:
+        if self.fused is not None and self.cfg.lr_anneal_iters > 0:
+            prog = min(1.0, self._iteration / self.cfg.lr_anneal_iters)
+            self.fused.set_lr_scale(1.0 - (1.0 - self.cfg.lr_final_frac) * prog)
+        self._iteration += 1
         with torch.cuda.nvtx.range("ppo_collect_rollouts"):
             self.rollout.collect()
         self.num_timesteps += self.rollout.T * self.rollout.n * self.world

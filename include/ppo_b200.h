@@ -106,6 +106,9 @@ int ppo_update_grad_norm(const float* grad, int32_t n_params, float grad_scale, 
  * log_std) into the buffers of `packed_out`, which the forward kernels read.  The Adam step counter lives in the workspace. */
 int ppo_update_adam(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params, float lr, float beta1,
                     float beta2, float eps, float max_grad_norm, float grad_scale, const PpoPolicy* packed_out, void* workspace, void* stream);
+/* learning-rate schedule (SB3 `learning_rate` as a callable of the remaining progress): subsequent ppo_update_adam calls --
+ * captured in a CUDA graph or not -- step with lr * scale.  The factor lives in the workspace; a fresh workspace means 1. */
+int ppo_update_set_lr_scale(void* workspace, float scale, void* stream);
 /* read (out != NULL) and / or set (set_to >= 0) the Adam step counter: checkpoint / resume */
 int ppo_update_step_count(void* workspace, int64_t set_to, int64_t* out, void* stream);
 

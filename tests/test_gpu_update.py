@@ -187,13 +187,14 @@ def test_graph_replay_equals_eager_and_training_learns(pkg):
     assert n1 == n2 == 2 * 4 * (4096 * 32 // 16384)
     assert float((f1 - f2).abs().max()) <= 5e-4, float((f1 - f2).abs().max())
     assert all(np.isfinite(list(s.values())).all() for s in s1 + s2)
-    cfg = ppo.PPOConfig(n_envs=8192, n_steps=32, seed=1, batch_size=32768, n_epochs=6)
+    # (64-step rollouts: a window shorter than the floor-rule horizon of hover.py:283 never sees past the 32-step plateau)
+    cfg = ppo.PPOConfig(n_envs=8192, n_steps=64, seed=1, batch_size=32768, n_epochs=4, target_kl=0.02, log_std_init=-1.0)
     tr = ppo.PPOTrainer(cfg, device="cuda:0")
     first = tr.learn_iteration()
-    for _ in range(30):
+    for _ in range(60):
         last = tr.learn_iteration()
     print("ep_len_mean", first["ep_len_mean"], "->", last["ep_len_mean"], "ep_rew_mean", first["ep_rew_mean"], "->", last["ep_rew_mean"])
-    assert last["ep_len_mean"] > first["ep_len_mean"] + 5 and last["ep_rew_mean"] > first["ep_rew_mean"]
+    assert last["ep_rew_mean"] > first["ep_rew_mean"] + 30 and last["ep_len_mean"] > first["ep_len_mean"] + 1
     tr.sim.close()
 
 

@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r1}
 ENVS=${2:-1048576}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 6 --warmup 3 --envs $ENVS --no-small --no-cpu-baseline --no-ppo"
+CMD="python bench.py --steps 6 --warmup 3 --envs $ENVS --no-small --no-cpu-baseline --no-ppo --no-train"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&

@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""PPO hover training sweep towards SURVEY C5 (rollout/ep_len_mean >= 400 and rollout/ep_rew_mean >= 181), GPU box.
+
+    python tools/train_sweep.py [budget_s_per_config] [config-name ...]
+
+Each config trains from scratch for the wall-clock budget and reports time-to-targets, best / final reward and throughput;
+the curve of every run is kept (one point per ~1 s) so that the winner can be committed under profiles/."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build()
+from fpv_drone_rl_agent_b200 import ppo  # noqa: E402
+
+BASE = dict(n_envs=16384, n_steps=64, n_epochs=4, batch_size=32768, learning_rate=3e-4, seed=0, target_kl=0.02, log_std_init=-1.0)
+CONFIGS = {
+    "base": {},
+    "lr_decay": dict(lr_final_frac=0.05, lr_anneal_iters=3000),
+    "std_lo": dict(log_std_init=-1.6),
+    "std_lo_decay": dict(log_std_init=-1.6, lr_final_frac=0.05, lr_anneal_iters=3000),
+    "big_batch": dict(n_envs=65536, batch_size=131072, learning_rate=6e-4),
+    "big_decay": dict(n_envs=65536, batch_size=131072, learning_rate=6e-4, lr_final_frac=0.05, lr_anneal_iters=800, log_std_init=-1.6),
+    "gamma995": dict(gamma=0.995, gae_lambda=0.97, lr_final_frac=0.05, lr_anneal_iters=3000, log_std_init=-1.6),
+    "epochs8": dict(n_epochs=8, lr_final_frac=0.05, lr_anneal_iters=2000, log_std_init=-1.6),
+    "long_rollout": dict(n_steps=128, batch_size=65536, lr_final_frac=0.05, lr_anneal_iters=1500, log_std_init=-1.6),
+}
+
+
+def run(name: str, over: dict, budget: float) -> dict:
+    cfg = ppo.PPOConfig(**{**BASE, **over})
+    tr = ppo.PPOTrainer(cfg, device="cuda:0")
+    tr.learn_iteration()
+    torch.cuda.synchronize()
+    t0, t_len, t_rew, best, curve, nxt = time.perf_counter(), None, None, -1e9, [], 0.0
+    it, out = 0, {}
+    while True:
+        out = tr.learn_iteration()
+        it += 1
+        now = time.perf_counter() - t0
+        if out["ep_len_mean"] == out["ep_len_mean"]:
+            best = max(best, out["ep_rew_mean"])
+            if t_len is None and out["ep_len_mean"] >= 400:
+                t_len = now
+            if t_rew is None and out["ep_len_mean"] >= 400 and out["ep_rew_mean"] >= 181:
+                t_rew = now
+        if now >= nxt:
+            curve.append([round(now, 2), int(out["timesteps"]), round(out["ep_len_mean"], 1), round(out["ep_rew_mean"], 2), round(out["kl"], 4),
+                          round(float(tr.model.log_std.mean()), 3)])
+            nxt += 1.0
+        if now > budget:
+            break
+    res = {"name": name, "config": {**BASE, **over}, "iterations": it, "env_steps": int(out["timesteps"]), "wall_s": round(now, 1),
+           "env_steps_per_s": out["timesteps"] / now, "time_to_len400_s": t_len, "time_to_len400_rew181_s": t_rew, "best_ep_rew": best,
+           "final_ep_rew": out["ep_rew_mean"], "final_ep_len": out["ep_len_mean"], "final_log_std": float(tr.model.log_std.mean()), "curve": curve}
+    tr.sim.close()
+    del tr
+    torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == "__main__":
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 40.0
+    names = sys.argv[2:] or list(CONFIGS)
+    for n in names:
+        r = run(n, CONFIGS[n], budget)
+        print(json.dumps(r), flush=True)
+        print("#", n, "len400 at", r["time_to_len400_s"], "s; rew181 at", r["time_to_len400_rew181_s"], "s; best", round(r["best_ep_rew"], 1), "final",
+              round(r["final_ep_rew"], 1), "log_std", round(r["final_log_std"], 2), "steps/s %.3g" % r["env_steps_per_s"], file=sys.stderr, flush=True)
