@@ -252,7 +252,10 @@ def train_leg(dev, rank: int, world: int, envs: int = 16384, budget_s: float = 4
 
     from fpv_drone_rl_agent_b200 import ppo
 
-    cfg = ppo.PPOConfig(n_envs=envs, n_steps=64, n_epochs=4, batch_size=32768, learning_rate=3e-4, seed=0, target_kl=0.02, log_std_init=-1.0)
+    # hyper-parameters: tools/train_sweep.py "long_rollout" (profiles/train_hover_r2.md): SB3 PPO defaults (gamma 0.99, lambda 0.95,
+    # clip 0.2, lr 3e-4 of train_hover.py:56) with 128-step rollouts, a linear learning-rate decay and a small initial action noise
+    cfg = ppo.PPOConfig(n_envs=envs, n_steps=128, n_epochs=4, batch_size=65536, learning_rate=3e-4, seed=0, target_kl=0.02, log_std_init=-1.6,
+                        lr_final_frac=0.05, lr_anneal_iters=1500)
     tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world)
     tr.learn_iteration()  # graph capture / one-time setup outside the clock (its samples still count as training)
     torch.cuda.synchronize()
@@ -276,8 +279,8 @@ def train_leg(dev, rank: int, world: int, envs: int = 16384, budget_s: float = 4
             break
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    res = {"envs_per_gpu": envs, "n_gpus": world, "n_steps": 64, "n_epochs": 4, "batch_size_per_rank": 32768, "iterations": it,
-           "env_steps": int(out["timesteps"]), "wall_s": wall, "env_steps_per_s_incl_update": (out["timesteps"] - envs * 64 * world) / wall,
+    res = {"envs_per_gpu": envs, "n_gpus": world, "n_steps": cfg.n_steps, "n_epochs": cfg.n_epochs, "batch_size_per_rank": cfg.batch_size, "iterations": it,
+           "env_steps": int(out["timesteps"]), "wall_s": wall, "env_steps_per_s_incl_update": (out["timesteps"] - envs * cfg.n_steps * world) / wall,
            "target_ep_len": target_len, "target_ep_rew": target_rew, "time_to_ep_len_s": t_len, "time_to_ep_len_and_rew_s": t_rew,
            "final_ep_len_mean": out["ep_len_mean"], "final_ep_rew_mean": out["ep_rew_mean"], "best_ep_rew_mean": best_rew, "budget_s": budget_s,
            "reference": "train_hover.py logs: ep_len_mean reaches the 402 cap after ~230-250 k steps = 275-300 s on 16 CPU processes (SURVEY 6)"}

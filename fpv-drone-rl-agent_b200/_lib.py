@@ -38,6 +38,7 @@ class QxConfig(C.Structure):
         ("spawn_pos_noise", f32), ("spawn_yaw_noise", f32), ("render", i32), ("auto_reset", i32), ("noise", i32),
         ("flight_mode", i32), ("thrust_scale", f32), ("thrust_bias", f32), ("att_pid", f32 * 12), ("vel_pid", f32 * 8),
         ("pos_pid", f32 * 8), ("zpos_pid", f32 * 4), ("zvel_pid", f32 * 4),
+        ("vision_mode", i32), ("panel_back", f32 * 12),
     ]
 
     def update(self, **kw) -> "QxConfig":

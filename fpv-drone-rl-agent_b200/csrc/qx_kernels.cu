@@ -129,6 +129,20 @@ __device__ __forceinline__ void run_env(const DevConfig& c, const StepArgs& a, i
 
 constexpr int kResetQueueBlocks = 148 * 4;  // persistent grid of the queue-draining launch
 
+// Deferred-reset step launches: the last block to finish copies the queue length to ResetQueue.published, which is what
+// qx_done_queue hands out -- it stays valid while the reset launch (which zeroes count) runs, so a consumer of the queue
+// (the rollout's time-limit bootstrap) may run concurrently with the reset.  No fence: every count atomic of a block has
+// returned (its result was used) before the block's __syncthreads, and atomics are performed at L2.
+__device__ __forceinline__ void publish_queue_length(ResetQueue* q) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&q->tasks_done, 1u) == gridDim.x - 1) {
+      q->published = atomicAdd(&q->count, 0u);
+      q->tasks_done = 0u;
+    }
+  }
+}
+
 // REF: the model constants are the reference's literals (qx_ref_constants.cuh) instead of kernel parameters
 template <int MODE, int TASK, bool CASC = false, bool REF = false>
 __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig cparam, const __grid_constant__ StepArgs a) {
@@ -146,6 +160,10 @@ __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const
     }
     for (unsigned int t = blockIdx.x * kBlock + threadIdx.x; t < cnt; t += gridDim.x * kBlock)
       run_env<MODE, TASK, CASC>(c, a, (int64_t)a.queue->idx[t]);
+  } else if (MODE == MODE_STEP_DEFER) {
+    const int64_t i = a.env_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < a.env_begin + a.env_count) run_env<MODE, TASK, CASC>(c, a, i);
+    publish_queue_length(a.queue);
   } else {
     const int64_t i = a.env_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.env_begin + a.env_count) return;
@@ -169,7 +187,9 @@ template <int TASK> struct ObsDim { static constexpr int value = TASK == QX_TASK
 struct ObsAux { float er, ep, ey, cx, cy, area, ratio; bool vis; };
 
 // ---- compute_attitude / compute_state, hover.py:224-272 (phase 0: after an agent step, 1: first observation of an episode)
-template <int TASK>
+// RASTER_OK: the instantiation may take the vision_mode = 1 branch (a non-inlined call; the lean hot kernels leave it out --
+// a handle in that mode runs the generic kernels -- so that the call's ABI does not cost their sub-step loop registers)
+template <int TASK, bool RASTER_OK = true>
 __device__ __forceinline__ void build_obs(Env& e, const DevConfig& c, const float act[4], const int phase, const bool live,
                                           float (&obs)[ObsDim<TASK>::value], ObsAux& x) {
   float er, ep, ey;
@@ -187,7 +207,8 @@ __device__ __forceinline__ void build_obs(Env& e, const DevConfig& c, const floa
   bool vis;
   float cx, cy, area = 0.f, ratio = 0.f;
   if (TASK == QX_TASK_HOVER) {
-    vision(e, c, vis, cx, cy, area, ratio);
+    if (RASTER_OK && c.vision_mode == 1) vision_raster(e.px, e.py, e.pz, e.qx, e.qy, e.qz, e.qw, c.raster, vis, cx, cy, area, ratio);
+    else vision(e, c, vis, cx, cy, area, ratio);
     obs[0] = d0 * c.inv_agent_dt; obs[1] = d1 * c.inv_agent_dt; obs[2] = d2 * c.inv_agent_dt;
     euler_to_quat(er, ep, ey, obs[3], obs[4], obs[5], obs[6]);  // hover.py:233
     obs[7] = cx; obs[8] = cy; obs[9] = e.pcx; obs[10] = e.pcy;
@@ -488,7 +509,7 @@ QX_DI void hot_epilogue_loaded(Env& e, const DevConfig& c, const StepArgs& a, co
   const float act[4] = {av.x, av.y, av.z, av.w};
   float obs[OBS_DIM];
   ObsAux x;
-  build_obs<QX_TASK_HOVER>(e, c, act, 0, true, obs, x);
+  build_obs<QX_TASK_HOVER, false>(e, c, act, 0, true, obs, x);
   const bool done = reward_and_flags<QX_TASK_HOVER, false>(e, c, a, i, act, true, obs, x);
   if (done) episode_end<true>(e, a, i, obs);
   else if (a.obs) write_obs(obs, a.obs, i, a.obs_stride, a.obs_bf16 != 0, a.stream_stores != 0);
@@ -596,7 +617,7 @@ QX_DI void hot_reset_env(const DevConfig& c, const StepArgs& a, const int64_t i)
   const float act[4] = {0.f, 0.f, 0.f, 0.f};  // hover.py:101
   float obs[OBS_DIM];
   ObsAux x;
-  build_obs<QX_TASK_HOVER>(e, c, act, 1, true, obs, x);
+  build_obs<QX_TASK_HOVER, false>(e, c, act, 1, true, obs, x);
   if (a.obs) write_obs(obs, a.obs, i, a.obs_stride, a.obs_bf16 != 0);
   store_env(e, a.state, a.n, i);
 }
@@ -661,6 +682,9 @@ __global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMin
   if (i0 < end) {
     const bool has1 = kLanes == 2 && i0 + 32 < end;
     hot_task<REF, V>(c, cparam, a, i0, has1 ? i0 + 32 : i0, has1);  // a thread without a second env computes its first one twice, stores it once
+  }
+  if constexpr (!MERGED) {
+    if (a.queue) publish_queue_length(a.queue);  // two-launch step: the reset-queue launch follows
   }
   if constexpr (MERGED) {
     ResetQueue* const q = a.queue;
@@ -746,6 +770,7 @@ struct QxHandle {
   float4* state;
   qx::Stats* stats;
   qx::ResetQueue* queue;
+  float* raster;       // vision_mode 1: qx::RasterConsts
   // staging for the *_host calls
   cudaStream_t stream, h2d_stream, d2h_stream;
   cudaEvent_t ev_h2d[16], ev_k[16], ev_d2h;
@@ -797,6 +822,8 @@ extern "C" int qx_default_config(int32_t task, QxConfig* c) {
   c->cam_tilt_up_deg = 25.f; c->cam_fov_deg = 90.f; c->cam_res = 128.f; c->cam_near = 0.1f; c->vis_margin_px = 0.5f;
   const float panel[12] = {4.98f, -1, 5, 4.98f, 1, 5, 4.98f, 1, 7, 4.98f, -1, 7};
   memcpy(c->panel, panel, sizeof(panel));
+  for (int k = 0; k < 4; ++k) { c->panel_back[3 * k] = panel[3 * k] + 0.04f; c->panel_back[3 * k + 1] = panel[3 * k + 1]; c->panel_back[3 * k + 2] = panel[3 * k + 2]; }  /* hover.py:118-147: box half extent 0.02 in depth */
+  c->vision_mode = 0;
   c->aviary_steps_per_step = task == QX_TASK_HOVER ? 6 : 1;
   c->max_steps = 400; c->floor_grace_steps = 30; c->reset_idle_steps = task == QX_TASK_HOVER ? 10 : 0;
   c->agent_dt = 0.025f; c->flight_dome_size = 3.0f; c->floor_threshold = 0.1f;
@@ -829,6 +856,7 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   if (!(s.physics_hz > 0) || !(s.control_hz > 0) || s.control_hz > s.physics_hz) return fail(QX_EINVAL, "qx_create: bad rates");
   if (s.flight_mode < -1 || s.flight_mode > 7) return fail(QX_EINVAL, "qx_create: flight_mode outside PyFlyt's -1..7");
   if (s.flight_mode != 0 && s.task != QX_TASK_HOVER) return fail(QX_EINVAL, "qx_create: flight modes other than 0 apply to the hover task");
+  if (s.vision_mode != 0 && s.vision_mode != 1) return fail(QX_EINVAL, "qx_create: vision_mode is 0 (analytic) or 1 (raster)");
   const int per = (int)(s.physics_hz / s.control_hz);
   d->task = s.task;
   d->ctrl_every = per;
@@ -870,6 +898,7 @@ static int derive(const QxConfig& s, uint64_t seed, uint64_t env_id0, qx::DevCon
   d->res = s.cam_res; d->half_res = 0.5f * s.cam_res; d->inv_half_res = 2.0f / s.cam_res; d->inv_res2 = 1.0f / (s.cam_res * s.cam_res);
   d->cam_near = s.cam_near; d->margin = s.vis_margin_px;
   memcpy(d->panel, s.panel, sizeof(d->panel));
+  d->vision_mode = s.vision_mode;
   d->inv_agent_dt = 1.0f / s.agent_dt; d->dome2 = s.flight_dome_size * s.flight_dome_size; d->floor_thr = s.floor_threshold;
   d->target_area = s.target_area; d->target_ratio = s.target_ratio;
   d->spawn_thr = s.spawn_throttle; d->spawn_pos_noise = s.spawn_pos_noise; d->spawn_yaw_noise = s.spawn_yaw_noise;
@@ -916,7 +945,7 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   cudaSetDevice(device);
   h->planes = cfg->flight_mode != 0 ? qx::kCascadePlanes : qx::kBasePlanes;
   h->ref_constants = !getenv("QX_FORCE_GENERIC") && matches_ref_constants(h->dev);
-  h->hot_ok = cfg->task == QX_TASK_HOVER && cfg->flight_mode == 0 && h->dev.ctrl_every == 2 && (h->dev.n_sub_step & 1) == 0 && h->dev.n_sub_step > 0;
+  h->hot_ok = cfg->task == QX_TASK_HOVER && cfg->flight_mode == 0 && cfg->vision_mode == 0 && h->dev.ctrl_every == 2 && (h->dev.n_sub_step & 1) == 0 && h->dev.n_sub_step > 0;
   auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
   h->hot_mode = env_int("QX_HOT", -1);
   h->hot_lanes = env_int("QX_LANES", kDefaultHotLanes);
@@ -934,6 +963,14 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   if (e == cudaSuccess) e = cudaMemset(h->queue, 0, sizeof(qx::ResetQueue));
   if (e == cudaSuccess) e = cudaMemset(h->state, 0, sizeof(float4) * h->planes * n_envs);
   if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(qx::Stats));
+  if (e == cudaSuccess) e = cudaMalloc(&h->raster, sizeof(qx::RasterConsts));
+  if (e == cudaSuccess) {
+    const qx::DevConfig& d = h->dev;
+    qx::RasterConsts rc = {d.cam_sd, d.cam_cd, d.inv_tan, d.res, d.half_res, d.inv_half_res, d.inv_res2, d.cam_near, {d.cam_off[0], d.cam_off[1], d.cam_off[2]}, 0.f, {}, {}};
+    memcpy(rc.panel, cfg->panel, sizeof(rc.panel)); memcpy(rc.panel_back, cfg->panel_back, sizeof(rc.panel_back));
+    e = cudaMemcpy(h->raster, &rc, sizeof(rc), cudaMemcpyHostToDevice);
+    h->dev.raster = h->raster;
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
@@ -944,7 +981,7 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming);
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
-    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue); delete h;
+    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue); cudaFree(h->raster); delete h;
     return fail(QX_ECUDA, "qx_create: %s", cudaGetErrorString(e));
   }
   *out = h;
@@ -956,7 +993,7 @@ extern "C" int qx_destroy(QxHandle* h) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(h->device);
-  cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue);
+  cudaFree(h->state); cudaFree(h->stats); cudaFree(h->queue); cudaFree(h->raster);
   if (h->staging) {
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_flags); cudaFreeHost(h->h_tobs);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_flags); cudaFree(h->d_tobs);
@@ -1180,7 +1217,7 @@ extern "C" int qx_debug_clock_probe(unsigned long long* out_dev, void* stream) {
 
 extern "C" int qx_done_queue(QxHandle* h, const uint32_t** count_dev, const uint32_t** idx_dev) {
   if (!h || !count_dev || !idx_dev) return fail(QX_EINVAL, "qx_done_queue: bad arguments");
-  *count_dev = use_merged(h) ? &h->queue->published : &h->queue->count;  // the merged launch zeroes count itself when it ends
+  *count_dev = &h->queue->published;  // written by the step launch; count itself is zeroed by the reset launch
   *idx_dev = h->queue->idx;
   return QX_OK;
 }

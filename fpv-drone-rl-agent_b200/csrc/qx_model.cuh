@@ -44,6 +44,10 @@ struct DevConfig {
   // motor map is the +-1 matrix of that layout, so the mixer is eight adds.
   int32_t x_layout, x_mixer;
   float arm_x[4], arm_y[4], arm_k, tq_k;
+  // camera features: 0 = analytic projection of the front face (vision()), 1 = scan conversion of the box silhouette
+  // on the pixel lattice (vision_raster()); panel_back = the four corners of the face behind panel[]
+  int32_t vision_mode;
+  const float* raster;  // vision_mode 1: 36 floats in device memory (RasterConsts), written by qx_create
 };
 
 }  // namespace qx
@@ -774,6 +778,106 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
   cy = ok ? fmaf(0.25f * (pys[0] + pys[1] + pys[2] + pys[3]) - 0.5f, c.inv_half_res, -1.f) : 0.f;
   area = ok ? fmaxf(0.5f * fabsf(a2) - 0.5f * per + 1.f, 0.f) * c.inv_res2 : 0.f;
   ratio = ok ? wpx * frcp(hpx) : 0.f;
+}
+
+// vision_mode = 1: the camera features as detect_rectangle (hover.py:157-222) reports them for the rendered frame, without
+// rendering it.  The red box (front face panel[], back face panel_back[]) projects to a convex silhouette; for every pixel
+// row the silhouette's x interval at the row's centre line is the min / max over the 12 box edges crossing it, which gives
+// the covered columns [l, r].  From the row spans:
+//   red_at_edges (hover.py:180-189)  a covered pixel in row / column 0 or res-1 rejects the frame
+//   contourArea  (hover.py:206)      the contour runs through the centres of the border pixels (blob pixels with a
+//                                    background 4-neighbour), so by Pick's theorem its area is N - B/2 - 1
+//   boundingRect (hover.py:209-213)  covered columns x covered rows
+//   centre       (hover.py:197-203)  mean of the projected front-face corners - 0.5 px (stand-in for the mean of the
+//                                    approxPolyDP corners: within 0.8 px, tests/test_oracle_golden.py)
+// oracle/vision.py:raster_features is the float64 statement of this function and equals the reference's detector on 1000
+// rasterised frames (visibility, area, ratio exactly).  Not inlined: it runs once per agent step and only in this mode.
+// (its constants live in a small device buffer: passing the DevConfig by reference would force the specialised kernels to
+// materialise their literal-folded copy of it in local memory, and 35 by-value arguments would cost the callers registers)
+struct RasterConsts { float cam_sd, cam_cd, inv_tan, res, half_res, inv_half_res, inv_res2, cam_near, cam_off[3], pad, panel[12], panel_back[12]; };
+static __device__ __noinline__ void vision_raster(const float px_w, const float py_w, const float pz_w, const float x, const float y, const float z,
+                                                  const float w, const float* __restrict__ consts, bool& vis, float& cx, float& cy, float& area, float& ratio) {
+  const RasterConsts c = *reinterpret_cast<const RasterConsts*>(consts);
+  const float* panel_front = c.panel;
+  const float* panel_back = c.panel_back;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
+  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
+  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
+  float sph = 0.f, cph = 1.f;
+  if (fabsf(r20) < 0.99999f) {
+    const float inv = frsqrt(r21 * r21 + r22 * r22);
+    sph = r21 * inv; cph = r22 * inv;
+  }
+  const float sd = c.cam_sd, cd = c.cam_cd;
+  const float fx = cd, fy = sd * sph, fzz = sd * cph;
+  const float ux = -sd * cph, uy = sph * cph * (cd - 1.f), uz = fmaf(sph, sph, cd * cph * cph);
+  const float rx = fy * uz - fzz * uy, ry = fzz * ux - fx * uz, rz = fx * uy - fy * ux;
+  float pxs[8], pys[8];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* P = k < 4 ? &panel_front[3 * k] : &panel_back[3 * (k - 4)];
+    const float dx = P[0] - px_w, dy = P[1] - py_w, dz = P[2] - pz_w;
+    const float bx = r00 * dx + r10 * dy + r20 * dz - c.cam_off[0];
+    const float by = r01 * dx + r11 * dy + r21 * dz - c.cam_off[1];
+    const float bz = r02 * dx + r12 * dy + r22 * dz - c.cam_off[2];
+    const float depth = fx * bx + fy * by + fzz * bz;
+    ok = ok && (depth > c.cam_near);
+    const float k1 = c.inv_tan / fmaxf(depth, 1e-9f);
+    pxs[k] = fmaf((rx * bx + ry * by + rz * bz) * k1, c.half_res, c.half_res);
+    pys[k] = fmaf(-(ux * bx + uy * by + uz * bz) * k1, c.half_res, c.half_res);
+  }
+  vis = false; cx = cy = area = ratio = 0.f;
+  if (!ok) return;
+  float ymin = pys[0], ymax = pys[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) { ymin = fminf(ymin, pys[k]); ymax = fmaxf(ymax, pys[k]); }
+  const int res = (int)c.res;
+  int r0 = (int)ceilf(ymin - 0.5f), r1 = (int)floorf(ymax - 0.5f);
+  r0 = max(r0, -1); r1 = min(r1, res);  // rows outside the image only matter as "touches the border"
+  // edges: front ring, back ring, connectors
+  constexpr int ea[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3}, eb[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+  float ex0[12], ey0[12], ey1[12], esl[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    ex0[k] = pxs[ea[k]]; ey0[k] = pys[ea[k]]; ey1[k] = pys[eb[k]];
+    const float dy = ey1[k] - ey0[k];
+    esl[k] = dy != 0.f ? (pxs[eb[k]] - pxs[ea[k]]) / dy : 0.f;
+  }
+  int n_pix = 0, interior = 0, lmin = 1 << 20, rmax = -(1 << 20), first = 1 << 20, last = -(1 << 20);
+  int lp = 1, rp = 0, lc = 1, rc = 0;  // spans of the previous and the current row (empty: l > r)
+  bool edge = false;
+  for (int r = r0; r <= r1 + 1; ++r) {  // one row ahead: the interior count of a row needs its lower neighbour
+    int ln = 1, rn = 0;
+    if (r <= r1) {
+      const float yl = (float)r + 0.5f;
+      float xl = 3.0e38f, xr = -3.0e38f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        if ((ey0[k] - yl) * (ey1[k] - yl) <= 0.f && ey0[k] != ey1[k]) {
+          const float xi = fmaf(yl - ey0[k], esl[k], ex0[k]);
+          xl = fminf(xl, xi); xr = fmaxf(xr, xi);
+        }
+      }
+      if (xl <= xr) { ln = (int)ceilf(xl - 0.5f); rn = (int)floorf(xr - 0.5f); }
+      if (ln <= rn) {
+        n_pix += rn - ln + 1;
+        lmin = min(lmin, ln); rmax = max(rmax, rn); first = min(first, r); last = max(last, r);
+        edge = edge || r <= 0 || r >= res - 1 || ln <= 0 || rn >= res - 1;
+      }
+    }
+    if (lc <= rc && lp <= rp && ln <= rn) interior += max(0, min(min(rc - 1, rp), rn) - max(max(lc + 1, lp), ln) + 1);
+    lp = lc; rp = rc; lc = ln; rc = rn;
+  }
+  if (n_pix == 0 || edge) return;
+  const int wpx = rmax - lmin + 1, hpx = last - first + 1;
+  if (wpx < 2 || hpx < 2) return;
+  vis = true;
+  area = ((float)n_pix - 0.5f * (float)(n_pix - interior) - 1.f) * c.inv_res2;
+  ratio = (float)wpx / (float)hpx;
+  cx = fmaf(0.25f * (pxs[0] + pxs[1] + pxs[2] + pxs[3]) - 0.5f, c.inv_half_res, -1.f);
+  cy = fmaf(0.25f * (pys[0] + pys[1] + pys[2] + pys[3]) - 0.5f, c.inv_half_res, -1.f);
 }
 
 // yaw task: centre of the red sphere (main.py:16-23, radius 0.1 at (2,0,1); yaw.py:63 detect_red_sphere_center is

@@ -338,6 +338,7 @@ class RolloutEngine:
         check(self.lib.qx_done_queue(sim._h, C.byref(cnt), C.byref(idx)))
         self._q_count, self._q_idx = cnt, idx
         self._graph = None
+        self._side = torch.cuda.Stream(device=d)
         self.sim.reset(self.cur_obs)
         # one-time kernel attribute setup must not happen inside a graph capture
         policy_forward(self.pol, self.cur_obs, deterministic=True, values=self.last_values)
@@ -353,6 +354,12 @@ class RolloutEngine:
                        log_probs=self.log_probs[t], obs_norm=self.obs[t])
         check(L.qx_step_begin(sim._h, _p(self.env_actions), _p(self.cur_obs), 0, self.cur_obs.stride(0), _p(self.raw_reward), _p(self.te),
                               _p(self.tr), _p(self.terminal_obs), s))
+        # fork: the reset of the finished envs (a latency chain of 20 idle sub-steps for a handful of warps) runs on a side
+        # stream next to the reward path and the time-limit bootstrap, which only read what the step launch wrote
+        main = torch.cuda.current_stream(self.device)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), _stream(self.device)))
         if cfg.norm_reward:
             check(L.ppo_reward_normalize(_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
                                          self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]),
@@ -364,7 +371,7 @@ class RolloutEngine:
         check(L.ppo_bootstrap_truncated(C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
                                         _p(stats.mean) if stats else None, _p(stats.inv_std) if stats else None, cfg.clip_obs,
                                         self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), s))
-        check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), s))
+        main.wait_stream(self._side)  # join
 
     def _rollout_body(self) -> None:
         for t in range(self.T):

@@ -113,6 +113,12 @@ typedef struct QxConfig {
   float pos_pid[8];           /* lin_pos kp[2] ki[2] kd[2] lim[2], cf2x.yaml:35-40 */
   float zpos_pid[4];          /* z_pos kp ki kd lim,               cf2x.yaml:42-47 */
   float zvel_pid[4];          /* z_vel kp ki kd lim,               cf2x.yaml:49-54 */
+  /* --- camera features (hover.py:157-222).  0: analytic projection of the four front-face corners with pixel-lattice
+   * corrections (default, cheapest).  1: scan conversion of the box silhouette on the 128 x 128 lattice and the contour
+   * features as cv2 reports them for the rendered frame -- visibility, contour area and bounding-box ratio equal the
+   * reference's detect_rectangle on rasterised frames; ~1.5x the step cost. ------------------------------------------- */
+  int32_t vision_mode;
+  float panel_back[12];       /* the 4 corners of the box face behind panel[] (hover.py:118-147: 0.04 deep) */
 } QxConfig;
 
 typedef struct QxHandle QxHandle;
@@ -148,7 +154,8 @@ int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dt
  * rollout bootstraps truncated episodes from terminal_obs there): qx_step_begin runs the step and queues the
  * finished envs, qx_step_end re-creates them and writes their first observation.  qx_step == begin + end in effect;
  * for batches of <= 16 384 envs (latency-bound) qx_step does both in one launch instead of two.
- * qx_done_queue gives the device addresses of the queue (count, env indices) valid between the two calls. */
+ * qx_done_queue gives the device addresses of the queue (count, env indices) of the step just taken: valid from qx_step_begin
+ * until the next step, also while qx_step_end runs -- a consumer of the queue may run concurrently with the reset on another stream. */
 int qx_step_begin(QxHandle* h, const float* actions_dev, void* obs_dev, int32_t obs_dtype, int64_t obs_stride,
                   float* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev, float* terminal_obs_dev, void* stream);
 int qx_step_end(QxHandle* h, void* obs_dev, int32_t obs_dtype, int64_t obs_stride, void* stream);

@@ -57,7 +57,9 @@ def test_policy_kernel_fits_three_slots(ptxas):
 
 def test_reference_constant_kernel_is_the_smaller_one(ptxas):
     """Static SASS size of the hover step kernel: the reference-constant instantiation must stay clearly below the generic
-    one (it was 2 432 vs 2 736 instructions when it was introduced) -- if it does not, the literals stopped folding."""
+    one (it was 2 432 vs 2 736 instructions when it was introduced; 3 328 vs 3 800 since -fmad=false spells every product-sum of
+    the once-per-step epilogue as two instructions and the raster-vision call was added) -- if it does not, the literals stopped
+    folding."""
     _, lib = ptxas
     try:
         sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, timeout=300).stdout
@@ -72,4 +74,4 @@ def test_reference_constant_kernel_is_the_smaller_one(ptxas):
             counts[cur] += 1
     gen = [v for k, v in counts.items() if "quadx_step_kernelILi1ELi0ELb0ELb0E" in k][0]
     ref = [v for k, v in counts.items() if "quadx_step_kernelILi1ELi0ELb0ELb1E" in k][0]
-    assert ref <= 2600 and gen <= 2900 and ref <= 0.92 * gen, (ref, gen)
+    assert ref <= 3500 and gen <= 4000 and ref <= 0.92 * gen, (ref, gen)

@@ -473,3 +473,58 @@ def test_batch_scale_parity_against_c_oracle(pkg, n):
     s1, s2 = sim.episode_stats(), orc.stats()
     assert abs(s1[2] - s2[2]) <= max(4, n // 500) and abs(s1[1] - s2[1]) <= 48 * max(4, n // 500)
     sim.close()
+
+
+def test_raster_vision_mode_equals_reference_detector(pkg):
+    """vision_mode = 1 (csrc/qx_model.cuh:vision_raster, H4): the camera columns of the observation against the reference's real
+    detect_rectangle (hover.py:157-222) run on rasterised frames of the same poses (random in-dome poses put in through
+    qx_set_state; the comparison is feature extraction only): visibility identical,
+    contour area and bounding-box ratio the detector's own numbers (a boundary pixel may differ in fp32: counted), centre
+    within 0.8 px, and the target term of the reward (hover.py:296-317) within 2e-2 -- against 0.45 for the analytic mode."""
+    from oracle import vision
+    from oracle.hover_oracle import detect_rectangle
+    from oracle.quadx_model import QuadXParams
+
+    n = 512
+    cfg = pkg.default_config()
+    # aviary_steps_per_step = 0: a step runs no physics, so the observation is built from exactly the pose that was set
+    cfg.update(start_pos=[0, 0, 1.2], reset_idle_steps=0, auto_reset=0, noise=0, vision_mode=1, aviary_steps_per_step=0, max_steps=10000)
+    rng = np.random.default_rng(3)
+    p = QuadXParams()
+    sim = pkg.QuadXSim(n, cfg, seed=78)
+    b = _Bufs(sim)
+    sim.reset(b.obs)
+    st = sim.get_state()
+    from oracle.quadx_model import euler_to_quat
+
+    pos = rng.uniform(-1.8, 1.8, (n, 3)); pos[:, 2] = rng.uniform(0.3, 2.4, n)
+    quat = euler_to_quat(rng.uniform(-0.4, 0.4, (n, 3)))
+    for j, key in enumerate(("px", "py", "pz")):
+        st[key] = pos[:, j].astype(np.float32)
+    for j, key in enumerate(("qx", "qy", "qz", "qw")):
+        st[key] = quat[:, j].astype(np.float32)
+    sim.set_state(st)
+    a = np.zeros((n, 4), np.float32)
+    o, r, te, tr = b.step(sim, a)
+    st2 = sim.get_state()
+    pos2 = np.stack([st2["px"], st2["py"], st2["pz"]], 1).astype(np.float64)
+    quat2 = np.stack([st2["qx"], st2["qy"], st2["qz"], st2["qw"]], 1).astype(np.float64)
+    assert np.array_equal(pos2.astype(np.float32), pos.astype(np.float32))
+    V, C, A, R = np.zeros(n, bool), np.zeros((n, 2)), np.zeros(n), np.zeros(n)
+    for i in range(n):
+        V[i], C[i], A[i], R[i] = detect_rectangle(vision.render_rgba(pos2[i], quat2[i], p))
+    vis = o[:, 13] > 0.5
+    vis_mis = int((vis != V).sum())
+    both = vis & V
+    assert both.sum() > 250 and vis_mis <= max(2, n // 100), (int(both.sum()), vis_mis)
+    area_flip = np.abs(o[:, 11] - A)[both] > 1e-7
+    ratio_flip = np.abs(o[:, 14] - R)[both] > 1e-6
+    print(f"raster mode vs the reference detector: {int(both.sum())} frames, visibility mismatches {vis_mis}, area differs in {int(area_flip.sum())}, "
+          f"ratio differs in {int(ratio_flip.sum())}, worst centre error {np.abs(o[:, 7:9] - C)[both].max() * 64:.2f} px")
+    assert area_flip.sum() <= max(3, n // 50) and ratio_flip.sum() <= max(3, n // 50)  # a border pixel decided differently by the moved pose / fp32
+    assert np.abs(o[:, 11] - A)[both].max() * 128 * 128 <= 3.0
+    assert np.abs(o[:, 7:9] - C)[both].max() * 64 <= 1.0
+    ok = both.copy(); ok[both] = ~(area_flip | ratio_flip)
+    rew = lambda cc, aa, rr: -(np.hypot(cc[:, 0], cc[:, 1]) + np.abs(aa - 0.013) + np.abs(rr - 1.53))  # noqa: E731
+    assert np.abs(rew(o[:, 7:9], o[:, 11], o[:, 14]) - rew(C, A, R))[ok].max() <= 2e-2
+    sim.close()

@@ -140,3 +140,33 @@ def test_drone_parameters_match_reference_files(golden_dir):
     # the motor map is derived from the prop positions: tau = r x F = (y F, -x F)
     for (x, y), row in zip(p.motor_xy, p.motor_map):
         assert row[0] == np.sign(y) and row[1] == -np.sign(x) and row[3] == 1.0
+
+
+def test_raster_vision_equals_reference_detector():
+    """vision_mode = 1 (oracle/vision.raster_features: row spans of the box silhouette, contour features by Pick's theorem)
+    against the reference's real detect_rectangle on rasterised frames, 1000 random in-dome poses: visibility, contour area
+    and bounding-box ratio (hover.py:180-213) must be the detector's own numbers; the centre (mean of the approxPolyDP corners,
+    hover.py:197-203) within 0.8 px.  These are the tolerances the GPU test of the raster mode uses."""
+    from oracle import vision
+    from oracle.hover_oracle import detect_rectangle
+    from oracle.quadx_model import euler_to_quat
+
+    p = QuadXParams()
+    rng = np.random.default_rng(1)
+    n = 1000
+    pos = rng.uniform(-2, 2, (n, 3))
+    pos[:, 2] = rng.uniform(0.01, 2.5, n)
+    q = euler_to_quat(rng.uniform(-0.5, 0.5, (n, 3)))
+    v, c, a, r = vision.raster_features(pos, q, p)
+    V, C, A, R = np.zeros(n, bool), np.zeros((n, 2)), np.zeros(n), np.zeros(n)
+    for i in range(n):
+        V[i], C[i], A[i], R[i] = detect_rectangle(vision.render_rgba(pos[i], q[i], p))
+    assert (V != v).sum() == 0
+    both = V & v
+    assert both.sum() > 600
+    assert np.abs(C - c)[both].max() * 64 <= 0.8  # pixels
+    assert (np.abs(A - a)[both] > 1e-12).sum() <= 3 and np.abs(A - a)[both].max() * 128 * 128 <= 2.0  # a boundary pixel in a handful of frames
+    assert (np.abs(R - r)[both] > 1e-12).sum() <= 1
+    # the reward term built from them (hover.py:296-317)
+    rew = lambda cc, aa, rr: -(np.hypot(cc[:, 0], cc[:, 1]) + np.abs(aa - 0.013) + np.abs(rr - 1.53))  # noqa: E731
+    assert np.abs(rew(C, A, R) - rew(c, a, r))[both].max() <= 2e-2

@@ -31,6 +31,9 @@ CONFIGS = {
     "epochs8": dict(n_epochs=8, lr_final_frac=0.05, lr_anneal_iters=2000, log_std_init=-1.6),
     "long_rollout": dict(n_steps=128, batch_size=65536, lr_final_frac=0.05, lr_anneal_iters=1500, log_std_init=-1.6),
 }
+for _s in range(1, 6):  # run-to-run spread of the configuration bench.py's train leg uses
+    CONFIGS[f"long_rollout_seed{_s}"] = dict(CONFIGS["long_rollout"], seed=_s)
+    CONFIGS[f"gamma995_seed{_s}"] = dict(CONFIGS["gamma995"], seed=_s)
 
 
 def run(name: str, over: dict, budget: float) -> dict:

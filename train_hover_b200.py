@@ -43,6 +43,10 @@ def main():
     ap.add_argument("--min-steps-between-checkpoints", type=int, default=20000)  # train_hover.py:9
     ap.add_argument("--tensorboard", default="")
     ap.add_argument("--target-len", type=float, default=0.0, help="stop when rollout/ep_len_mean reaches this")
+    ap.add_argument("--target-rew", type=float, default=0.0, help="... and rollout/ep_rew_mean reaches this (SURVEY C5: 181)")
+    ap.add_argument("--gae-lambda", type=float, default=0.95)
+    ap.add_argument("--lr-final-frac", type=float, default=1.0, help="linear learning-rate decay to this fraction ...")
+    ap.add_argument("--lr-anneal-iters", type=int, default=0, help="... over this many iterations (0 = constant)")
     ap.add_argument("--json", default="", help="write the per-iteration log here")
     args = ap.parse_args()
 
@@ -62,7 +66,8 @@ def main():
     from fpv_drone_rl_agent_b200 import ppo
 
     cfg = ppo.PPOConfig(n_envs=args.envs, n_steps=args.steps, n_epochs=args.epochs, batch_size=args.batch, learning_rate=args.lr, seed=args.seed,
-                        ent_coef=args.ent_coef, gamma=args.gamma, target_kl=args.target_kl, log_std_init=args.log_std_init)
+                        ent_coef=args.ent_coef, gamma=args.gamma, target_kl=args.target_kl, log_std_init=args.log_std_init, gae_lambda=args.gae_lambda,
+                        lr_final_frac=args.lr_final_frac, lr_anneal_iters=args.lr_anneal_iters)
     trainer = ppo.PPOTrainer(cfg, device=f"cuda:{local}", rank=rank, world=world)
     writer = None
     if args.tensorboard and rank == 0:
@@ -90,7 +95,7 @@ def main():
                 name = f"ppo_hover_{out['timesteps']}_steps_{round(out['vf'], 2)}_len{round(out['ep_len_mean'], 2)}_rew{round(out['ep_rew_mean'], 2)}.pt"
                 trainer.save(os.path.join(args.save_path, name))
                 last_ckpt = out["timesteps"]
-        if args.target_len and out["ep_len_mean"] >= args.target_len:
+        if args.target_len and out["ep_len_mean"] >= args.target_len and (not args.target_rew or out["ep_rew_mean"] >= args.target_rew):
             break
         if args.total_timesteps and out["timesteps"] >= args.total_timesteps:
             break
@@ -101,6 +106,11 @@ def main():
             json.dump(log, open(args.json, "w"))
         print("Training complete.")
     if world > 1:
+        # the captured graphs hold NCCL kernels: release them before the communicator goes away
+        trainer._epoch_graph = None
+        trainer.rollout._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
