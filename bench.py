@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_ENV_STEP = 358  # 128+128 state, 16 action, 80 obs, 4 reward, 2 flags
-ACT_BYTES, OUT_BYTES = 16, 80 + 4 + 1 + 1
+ACT_BYTES, OUT_BYTES, OUT_BYTES_BF16 = 16, 80 + 4 + 1 + 1, 40 + 4 + 1 + 1
 HOVER_THR = (0.1 * 9.81 / 4.0) ** 0.5
 METRIC = "env-steps/sec (physics+reward+obs), QuadX hover"
 UNIT = "env-steps/s"
@@ -358,33 +358,48 @@ def main_ours(args):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     value = E * world * args.steps / (max_ms * 1e-3)
 
-    # ---- e2e: the C-ABI host-buffer call, H2D + kernel + D2H inside the timed region
+    # ---- e2e: the C-ABI host-buffer call, H2D + kernel + D2H inside the timed region.  The call is bound by the device-to-host
+    # copy, so it is measured with both wire formats of the observation: bf16 (qx_step_host_ex, what a bf16 policy input needs;
+    # the headline `e2e`) and f32 (qx_step_host, `e2e_f32_obs`).  Physics, reward and flags are the same f32 arithmetic in both.
+    import ctypes as C
+
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)  # pinned buffers are allocated on the host NUMA node the GPU hangs off
+    acts_pinned = acts_pinned.clone().pin_memory() if numa is not None else acts_pinned
     h_obs = torch.zeros(E, 20).pin_memory()
+    h_obs16 = torch.zeros(E, 20, dtype=torch.bfloat16).pin_memory()
     h_rew = torch.zeros(E).pin_memory()
     h_te = torch.zeros(E, dtype=torch.uint8).pin_memory()
     h_tr = torch.zeros(E, dtype=torch.uint8).pin_memory()
-    import ctypes as C
 
     L = _lib.lib()
     vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
     e2e_steps = max(3, min(args.steps, 20))
 
-    def host_step(k):
-        _lib.check(L.qx_step_host(sim._h, vp(acts_pinned[k % 8]), vp(h_obs), vp(h_rew), vp(h_te), vp(h_tr), None))
+    def e2e_run(bf16: bool) -> float:
+        def host_step(k):
+            if bf16:
+                _lib.check(L.qx_step_host_ex(sim._h, vp(acts_pinned[k % 8]), vp(h_obs16), 1, vp(h_rew), vp(h_te), vp(h_tr), None))
+            else:
+                _lib.check(L.qx_step_host(sim._h, vp(acts_pinned[k % 8]), vp(h_obs), vp(h_rew), vp(h_te), vp(h_tr), None))
 
-    for k in range(3):
-        host_step(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0 = time.perf_counter()
-    for k in range(e2e_steps):
-        host_step(k)
-    e1 = time.perf_counter()
-    te2e = torch.tensor([e1 - e0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
-    e2e_value = E * world * e2e_steps / float(te2e.item())
+        for k in range(3):
+            host_step(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = time.perf_counter()
+        for k in range(e2e_steps):
+            host_step(k)
+        e1 = time.perf_counter()
+        te2e = torch.tensor([e1 - e0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te2e, op=dist.ReduceOp.MAX)
+        return E * world * e2e_steps / float(te2e.item())
+
+    e2e_f32 = e2e_run(False)
+    e2e_value = e2e_run(True)
+    os.sched_setaffinity(0, affinity0)  # the CPU legs below use every host thread again
 
     line = None
     if rank == 0:
@@ -413,8 +428,11 @@ def main_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(E, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * ACT_BYTES, "d2h_bytes_per_step": E * OUT_BYTES,
-                    "steps": e2e_steps, "api": "qx_step_host (C-ABI, pinned host buffers, synchronous)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * ACT_BYTES, "d2h_bytes_per_step": E * OUT_BYTES_BF16,
+                    "steps": e2e_steps, "api": "qx_step_host_ex (C-ABI, pinned host buffers, synchronous; f32 actions in, bf16 observations + f32 reward + u8 terminated / truncated out)",
+                    "host_numa_node": numa},
+            "e2e_f32_obs": {"value": e2e_f32, "unit": UNIT, "h2d_bytes_per_step": E * ACT_BYTES, "d2h_bytes_per_step": E * OUT_BYTES,
+                            "steps": e2e_steps, "api": "qx_step_host (same call with f32 observations)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernels": ("reference-constant instantiation (model constants of the reference's own parameter set as literals)"
@@ -474,6 +492,32 @@ def main_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+
+def bind_to_gpu_numa_node(local: int):
+    """Run this process on the CPUs of the NUMA node GPU `local` is attached to, so that the pinned host buffers it allocates
+    afterwards (first touch) are local to that GPU's PCIe root.  Returns the node, or None where sysfs does not say."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def yaw_side(pkg, dev, envs: int) -> dict:

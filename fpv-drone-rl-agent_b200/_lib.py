@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         "qx_step_k": (C.c_int, [vp, i32, f32p, f32p, f32p, u8p, u8p, vp]),
         "qx_reset_host": (C.c_int, [vp, u8p, f32p]),
         "qx_step_host": (C.c_int, [vp, f32p, f32p, f32p, u8p, u8p, f32p]),
+        "qx_step_host_ex": (C.c_int, [vp, f32p, vp, i32, f32p, u8p, u8p, f32p]),
         "qx_get_state": (C.c_int, [vp, vp]),
         "qx_set_state": (C.c_int, [vp, vp]),
         "qx_get_flags": (C.c_int, [vp, i64, i64, vp]),
@@ -123,6 +124,9 @@ def lib() -> C.CDLL:
         "ppo_update_adam": (C.c_int, [vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, C.POINTER(PpoPolicy), vp, vp]),
         "ppo_update_step_count": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
         "ppo_update_set_lr_scale": (C.c_int, [vp, C.c_float, vp]),
+        "ppo_update_recompute_logp": (C.c_int, [C.POINTER(PpoPolicy), vp, vp, vp, i32, i64, vp, vp, vp]),
+        "ppo_update_kl_stop": (C.c_int, [vp, C.c_float, C.POINTER(i32), C.POINTER(i32), vp]),
+        "ppo_update_set_log_std_floor": (C.c_int, [vp, i32, C.c_float, vp]),
         "qx_debug_clock_probe": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in protos.items():
@@ -135,13 +139,13 @@ def lib() -> C.CDLL:
 
 
 EXPORTED = [
-    "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host",
+    "qx_default_config", "qx_create", "qx_destroy", "qx_reset", "qx_step", "qx_step_begin", "qx_step_end", "qx_done_queue", "qx_step_k", "qx_reset_host", "qx_step_host", "qx_step_host_ex",
     "qx_get_state", "qx_set_state", "qx_get_flags", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words", "qx_uses_reference_constants", "qx_config_matches_reference_constants",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
 PPO_EXPORTED = ["ppo_policy_forward", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
                 "ppo_reward_normalize", "ppo_test_gemm", "ppo_test_gemm_mn", "ppo_update_num_params", "ppo_update_workspace_bytes",
-                "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count", "ppo_update_set_lr_scale"]
+                "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count", "ppo_update_set_lr_scale", "ppo_update_kl_stop", "ppo_update_set_log_std_floor", "ppo_update_recompute_logp"]
 
 
 class QxError(RuntimeError):

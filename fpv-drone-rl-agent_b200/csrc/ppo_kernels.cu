@@ -122,6 +122,7 @@ struct FwdArgs {
   const uint8_t* boot_te;
   const uint8_t* boot_tr;
   float boot_gamma;
+  int32_t grid;                   // CTAs of this launch (= gridDim.x), as a parameter so that the tile walk needs no register for it
 };
 
 __device__ __forceinline__ uint32_t tanh_pack_bf16x2(float lo, float hi) {
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
 #endif
   K2_TRACE(127);
   // gather mode (time-limit bootstrap): most steps have no truncated env at all -- leave before staging 88 KB of weights
-  if (a.gather_idx && (int64_t)blockIdx.x * kSlots * 128 >= (int64_t)*a.gather_count) return;
+  if (a.gather_idx && (int64_t)blockIdx.x * 128 >= (int64_t)*a.gather_count) return;  // (slot-major tile order: this CTA's first tile is blockIdx.x)
   // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barriers
   stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, kFwdThreads);
   stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, kFwdThreads);
@@ -249,13 +250,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   const uint32_t idesc_h = make_idesc_bf16(128, kHid), idesc_o = make_idesc_bf16(128, kHead);
   uint32_t phase = 0;
   const int64_t n_rows = a.gather_idx ? (int64_t)*a.gather_count : a.n;
-  const int64_t n_tiles = (n_rows + 127) / 128;
+  const int n_tiles = (int)((n_rows + 127) / 128);  // 32-bit tile indices (rows stay 64-bit): the kernel sits at its 80-register cap
   const float clipv = a.obs_clip > 0.f ? a.obs_clip : 3.0e38f;
   const uint64_t step = a.step + (a.step_base ? *a.step_base : 0ull);
 
   long long* dbg = (blockIdx.x == 0 && slot == 0) ? g_phase_clk : nullptr;
   int it = -1;
-  const int64_t tile_stride = (int64_t)gridDim.x * kSlots, tile0 = (int64_t)blockIdx.x * kSlots + slot;
+  // slot-major tile order: tile t belongs to CTA t % grid, so the tiles that do not fill a whole round of grid x kSlots slots are
+  // spread over the CTAs (1 024 tiles on 148 SMs: 6 or 7 per SM) instead of giving the first CTAs a third tile in every slot (9 vs 6)
+  const int tile_stride = a.grid * kSlots, tile0 = slot * a.grid + (int)blockIdx.x;
 
   // normalise (VecNormalize.normalize_obs) the raw row chunks in xbuf, write them as bf16 into the slot's X operand
   // (interleaved K-major; 2 threads per row, 2 chunks of 8 columns each) and, if asked, as fp32 into obs_norm_out
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
     slot_sync(slot);
     if (st == 0) { fence_after_sync(); issue_l1p(); mma_commit(bar); }
     int64_t prev = -1;
-    for (int64_t tile = tile0; tile < n_tiles; tile += tile_stride) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_stride) {
       ++it;
       PHASE_STAMP(0);
       // ---- G_a: action/value of the previous tile are complete, and this tile's actor layer 1
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
       fence_after_sync();
       PHASE_STAMP(5);
       // X is free: stage the next tile (its raw rows are in xbuf) and request the one after
-      const int64_t next = tile + tile_stride;
+      const int next = tile + tile_stride;
       if (next < n_tiles) {
         stage_x(next, xbuf);
         load_obs_chunks(a, next + tile_stride, n_rows, xrow, xh, obs_dim, xbuf);
@@ -701,8 +704,9 @@ static int launch_forward(ppo::FwdArgs& a, int64_t max_rows, void* stream) {
     sms_of[dev].store(n, std::memory_order_release);
     sms = n;
   }
-  const int64_t tiles = (max_rows + 127) / 128, ctas = (tiles + ppo::kSlots - 1) / ppo::kSlots;
-  const unsigned grid = (unsigned)(ctas < sms ? ctas : sms);
+  const int64_t tiles = (max_rows + 127) / 128;
+  const unsigned grid = (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);  // small batches: one tile per SM before a second slot is used
+  a.grid = (int32_t)grid;
   ppo::policy_forward_kernel<<<grid, ppo::kFwdThreads, ppo::kSmTotal, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_policy_forward: launch failed");
 }

@@ -90,6 +90,17 @@ struct Header {
   double part[3];     // prepare: sum 1, sum adv, sum adv^2 (fp64)
   unsigned long long step;  // Adam step count
   float lr_scale_m1;  // learning-rate schedule: the Adam kernel steps with lr * (1 + lr_scale_m1), so a zero-filled workspace means lr
+  // SB3's target_kl early stop (PPO.train: "if approx_kl_div > 1.5 * target_kl: continue_training = False; break"), on the device so
+  // that it works per minibatch inside a captured epoch: the forward/backward kernel sums (ratio - 1) - log ratio and the row count
+  // of THIS minibatch, the reduce kernel appends both to the flat gradient (slots [total], [total + 1], so a gradient all-reduce
+  // carries them and every rank takes the same decision), and the Adam kernel skips its update -- and every later one until the
+  // host re-arms -- once the mean exceeds 1.5 x target_kl.
+  float mb_k3, mb_n;
+  float target_kl;        // 0 = off (zero-filled workspace)
+  unsigned int stopped;   // latched by the Adam kernel
+  unsigned int skipped;   // optimiser steps skipped since the last re-arm
+  unsigned int ls_floor_on;
+  float ls_floor;         // lower bound of log_std after the Adam step (optional)
 };
 constexpr size_t kHeaderBytes = 256;
 static_assert(sizeof(Header) <= kHeaderBytes, "header");
@@ -109,6 +120,7 @@ struct UpdArgs {
   Header* hdr;
   float* scratch;         // [gridDim.x][total] per-CTA partial gradients
   float* loss_stats;      // [8] accumulated: pg, vf, -(logp - old), clipfrac, (ratio - 1) - log ratio, n_rows, 0, 0
+  float* logp_out;        // non-null: forward pass of the actor only, log pi(a | s) of every row written here, nothing else touched
 };
 
 // ---------------------------------------------------------------------------
@@ -143,6 +155,7 @@ __global__ void __launch_bounds__(256) update_prepare_kernel(const float* __rest
       hdr->adv_mean = normalize ? (float)mean : 0.f;
       hdr->adv_inv_std = normalize ? (float)(1.0 / (sqrt(var) + 1e-8)) : 1.f;
       hdr->norm2 = 0.f;
+      hdr->mb_k3 = 0.f; hdr->mb_n = 0.f;
       hdr->part[0] = hdr->part[1] = hdr->part[2] = 0.0;
       hdr->ticket = 0u;
     }
@@ -274,8 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
   // every entry of the CTA's scratch slot is written below (each CTA owns at least one tile of both passes)
 
   float st_pg = 0.f, st_vf = 0.f, st_kl = 0.f, st_cf = 0.f, st_k3 = 0.f, st_n = 0.f;  // per-thread loss statistics (rows of warps 0..3)
+  const bool fwd_only = a.logp_out != nullptr;
 
-  for (int net = 0; net < 2; ++net) {
+  for (int net = 0; net < (fwd_only ? 1 : 2); ++net) {
     const uint32_t sW1n = sW1 + (net ? kHid * 16 : 0), sW2n = net ? sW2v : sW2p, sW3n = sW3 + (net ? 16 * W3S : 0);
     const float* b1 = sB1 + (net ? kHid : 0);
     const float* b2 = sB2 + (net ? kHid : 0);
@@ -368,8 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
                 logp += -0.5f * z[j] * z[j] - ls - 0.91893853320467f;
               }
             }
-            const float advn = (__ldg(a.adv + row) - adv_mean) * adv_inv_std;
-            const float lr = logp - __ldg(a.old_logp + row), ratio = __expf(lr);
+            if (fwd_only) a.logp_out[row] = logp;
+            const float advn = fwd_only ? 0.f : (__ldg(a.adv + row) - adv_mean) * adv_inv_std;
+            const float lr = fwd_only ? 0.f : logp - __ldg(a.old_logp + row), ratio = __expf(lr);
             const float lo = 1.f - a.clip_range, hi = 1.f + a.clip_range;
             const bool clipped = (advn > 0.f && ratio > hi) || (advn < 0.f && ratio < lo);
             const float g = clipped ? 0.f : -advn * ratio * inv_b;  // d loss / d logp
@@ -404,6 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
+      if (fwd_only) { fence_after_sync(); continue; }
       // ---- B1: dH2 = dOut W3 (K = 16 heads);  dW3 += H2^T dOut (K = 128 samples)
       if (tid == 0) {
         fence_after_sync();
@@ -451,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
       fence_after_sync();
     }
     // ---- flush this pass's weight gradients (TMEM, fp32) to the CTA's scratch slot, in the flat parameter layout
-    if (iter > 0 && warp < 4) {
+    if (iter > 0 && warp < 4 && !fwd_only) {
       const int oW2 = net ? L.w2v : L.w2p, oB2 = net ? L.b2v : L.b2p, oW1 = net ? L.w1v : L.w1p, oB1 = net ? L.b1v : L.b1p;
       // dW2: TMEM row = input feature i, column = output feature o  ->  W2[o][i]
 #pragma unroll 1
@@ -505,6 +521,12 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
     fence_after_sync();
   }
   // ---- head biases, log_std, loss statistics
+  if (fwd_only) {
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, kTmCols);
+    return;
+  }
   if (warp < 4) {
     float v[6] = {st_pg, st_vf, st_kl, st_cf, st_k3, st_n};
 #pragma unroll
@@ -520,6 +542,8 @@ __global__ void __launch_bounds__(kThreads, 1) update_fwdbwd_kernel(const UpdArg
   }
   if (tid == 0) my_scratch[L.bv] = sAcc[ad];
   if (tid < 6 && a.loss_stats) atomicAdd(&a.loss_stats[tid], sAcc[24 + tid]);
+  if (tid == 6) atomicAdd(&a.hdr->mb_k3, sAcc[24 + 4]);
+  if (tid == 7) atomicAdd(&a.hdr->mb_n, sAcc[24 + 5]);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, kTmCols);
@@ -543,6 +567,7 @@ __global__ void __launch_bounds__(256) update_reduce_kernel(const float* __restr
     s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     grad[p] = s;
   }
+  if (p == 0 && hdr->target_kl > 0.f) { grad[total] = hdr->mb_k3; grad[total + 1] = hdr->mb_n; }  // see Header
   float q = s * s;
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   __shared__ float sh[8];
@@ -589,7 +614,9 @@ struct AdamArgs {
 __global__ void __launch_bounds__(256) update_adam_kernel(const AdamArgs a) {
   const int p = blockIdx.x * 256 + threadIdx.x;
   const unsigned long long t = a.hdr->step + 1ull;
-  if (p < a.total) {
+  const float tkl = a.hdr->target_kl;
+  const bool stop = a.hdr->stopped != 0u || (tkl > 0.f && a.grad[a.total] > 1.5f * tkl * fmaxf(a.grad[a.total + 1], 1.f));
+  if (p < a.total && !stop) {
     const float norm = sqrtf(a.hdr->norm2);
     const float clip = a.max_grad_norm > 0.f ? fminf(1.f, a.max_grad_norm / (norm + 1e-6f)) : 1.f;  // torch clip_grad_norm_
     const float g = a.grad[p] * a.grad_scale * clip;
@@ -598,7 +625,8 @@ __global__ void __launch_bounds__(256) update_adam_kernel(const AdamArgs a) {
     a.m[p] = m; a.v[p] = v;
     const double bc1 = 1.0 - pow((double)a.beta1, (double)t), bc2 = 1.0 - pow((double)a.beta2, (double)t);
     const float denom = sqrtf(v) / (float)sqrt(bc2) + a.eps;
-    const float w = a.params[p] - (float)((double)a.lr * (1.0 + (double)a.hdr->lr_scale_m1) / bc1) * (m / denom);
+    float w = a.params[p] - (float)((double)a.lr * (1.0 + (double)a.hdr->lr_scale_m1) / bc1) * (m / denom);
+    if (a.hdr->ls_floor_on && p >= make_layout(a.pk.obs_dim, a.pk.act_dim).ls) w = fmaxf(w, a.hdr->ls_floor);
     a.params[p] = w;
     // ---- re-pack into the bf16 / fp32 buffers of the forward kernels
     const Layout L = make_layout(a.pk.obs_dim, a.pk.act_dim);
@@ -629,7 +657,11 @@ __global__ void __launch_bounds__(256) update_adam_kernel(const AdamArgs a) {
     last = atomicAdd(&a.hdr->ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) { a.hdr->step = t; a.hdr->ticket = 0u; }
+  if (last && threadIdx.x == 0) {
+    if (stop) { a.hdr->stopped = 1u; a.hdr->skipped += 1u; }
+    else a.hdr->step = t;
+    a.hdr->ticket = 0u;
+  }
 }
 
 // test hook: D[128, n] = A^T-or-A times B^T-or-B through MN-major / K-major descriptors
@@ -706,6 +738,19 @@ static int upd_sms(int* out) {
   return QX_OK;
 }
 
+// per-device one-time opt-in to ~170 KB of dynamic shared memory
+static int upd_smem_optin() {
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ufail(QX_ECUDA, "ppo_update: cannot query the current device");
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(ppo_upd::update_fwdbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppo_upd::kSmTotal) != cudaSuccess)
+      return ufail(QX_ECUDA, "ppo_update: cannot reserve shared memory");
+    attr_set[dev].store(true, std::memory_order_release);
+  }
+  return QX_OK;
+}
+
 extern "C" int64_t ppo_update_workspace_bytes(int32_t obs_dim, int32_t act_dim) {
   const int32_t n = ppo_update_num_params(obs_dim, act_dim);
   if (n < 0) return -1;
@@ -728,15 +773,7 @@ extern "C" int ppo_update_minibatch(const PpoPolicy* p, const float* obs, const 
   float* scratch = (float*)((uint8_t*)workspace + ppo_upd::kHeaderBytes);
   const int grid = n_tiles < sms ? n_tiles : sms;
   ppo_upd::update_prepare_kernel<<<grid < 64 ? grid : 64, 256, 0, s>>>(adv, tiles_dev, n_tiles, n_rows, normalize_adv, hdr);
-  // per-device one-time opt-in to ~170 KB of dynamic shared memory
-  static std::atomic<bool> attr_set[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ufail(QX_ECUDA, "ppo_update_minibatch: cannot query the current device");
-  if (!attr_set[dev].load(std::memory_order_acquire)) {
-    if (cudaFuncSetAttribute(ppo_upd::update_fwdbwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ppo_upd::kSmTotal) != cudaSuccess)
-      return ufail(QX_ECUDA, "ppo_update_minibatch: cannot reserve shared memory");
-    attr_set[dev].store(true, std::memory_order_release);
-  }
+  if (int rc = upd_smem_optin()) return rc;
   ppo_upd::UpdArgs a{};
   a.p = *p; a.obs = obs; a.actions = actions; a.old_logp = old_logp; a.adv = adv; a.ret = ret; a.tiles = tiles_dev; a.n_tiles = n_tiles;
   a.n_rows = n_rows; a.clip_range = clip_range; a.vf_coef = vf_coef; a.ent_coef = ent_coef; a.normalize_adv = normalize_adv; a.hdr = hdr;
@@ -744,6 +781,22 @@ extern "C" int ppo_update_minibatch(const PpoPolicy* p, const float* obs, const 
   ppo_upd::update_fwdbwd_kernel<<<grid, ppo_upd::kThreads, ppo_upd::kSmTotal, s>>>(a);
   ppo_upd::update_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(scratch, grid, total, grad_out, hdr);
   return cudaGetLastError() == cudaSuccess ? QX_OK : ufail(QX_ECUDA, "ppo_update_minibatch: launch failed");
+}
+
+extern "C" int ppo_update_recompute_logp(const PpoPolicy* p, const float* obs, const float* actions, const int32_t* tiles_dev, int32_t n_tiles,
+                                         int64_t n_rows, float* logp_out, void* workspace, void* stream) {
+  if (!p || !obs || !actions || !tiles_dev || n_tiles <= 0 || n_rows <= 0 || !logp_out || !workspace)
+    return ufail(QX_EINVAL, "ppo_update_recompute_logp: bad arguments");
+  if (ppo_update_num_params(p->obs_dim, p->act_dim) < 0) return ufail(QX_EINVAL, "ppo_update_recompute_logp: unsupported observation / action width");
+  int sms = 0;
+  if (int rc = upd_sms(&sms)) return rc;
+  if (int rc = upd_smem_optin()) return rc;
+  ppo_upd::UpdArgs a{};
+  a.p = *p; a.obs = obs; a.actions = actions; a.tiles = tiles_dev; a.n_tiles = n_tiles; a.n_rows = n_rows; a.clip_range = 0.2f;
+  a.hdr = (ppo_upd::Header*)workspace; a.scratch = (float*)((uint8_t*)workspace + ppo_upd::kHeaderBytes); a.logp_out = logp_out;
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  ppo_upd::update_fwdbwd_kernel<<<grid, ppo_upd::kThreads, ppo_upd::kSmTotal, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? QX_OK : ufail(QX_ECUDA, "ppo_update_recompute_logp: launch failed");
 }
 
 extern "C" int ppo_update_grad_norm(const float* grad, int32_t n_params, float grad_scale, void* workspace, void* stream) {
@@ -773,6 +826,36 @@ extern "C" int ppo_update_set_lr_scale(void* workspace, float scale, void* strea
   if (cudaMemcpyAsync(&hdr->lr_scale_m1, &v, sizeof(v), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess)
     return ufail(QX_ECUDA, "ppo_update_set_lr_scale: copy failed");
   cudaStreamSynchronize((cudaStream_t)stream);  // v is on this frame
+  return QX_OK;
+}
+
+extern "C" int ppo_update_kl_stop(void* workspace, float target_kl, int32_t* stopped_out, int32_t* skipped_out, void* stream) {
+  if (!workspace) return ufail(QX_EINVAL, "ppo_update_kl_stop: null workspace");
+  ppo_upd::Header* hdr = (ppo_upd::Header*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (stopped_out || skipped_out) {
+    unsigned int v[2] = {0u, 0u};
+    if (cudaMemcpyAsync(v, &hdr->stopped, sizeof(v), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+      return ufail(QX_ECUDA, "ppo_update_kl_stop: copy failed");
+    if (stopped_out) *stopped_out = (int32_t)v[0];
+    if (skipped_out) *skipped_out = (int32_t)v[1];
+  }
+  if (target_kl >= 0.f) {  // (re-)arm: set the threshold, clear the latch and the counter
+    struct { float tkl; unsigned int stopped, skipped; } v = {target_kl, 0u, 0u};
+    static_assert(offsetof(ppo_upd::Header, stopped) == offsetof(ppo_upd::Header, target_kl) + 4 && offsetof(ppo_upd::Header, skipped) == offsetof(ppo_upd::Header, target_kl) + 8, "layout");
+    if (cudaMemcpyAsync(&hdr->target_kl, &v, sizeof(v), cudaMemcpyHostToDevice, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+      return ufail(QX_ECUDA, "ppo_update_kl_stop: copy failed");
+  }
+  return QX_OK;
+}
+
+extern "C" int ppo_update_set_log_std_floor(void* workspace, int32_t on, float floor, void* stream) {
+  if (!workspace) return ufail(QX_EINVAL, "ppo_update_set_log_std_floor: null workspace");
+  ppo_upd::Header* hdr = (ppo_upd::Header*)workspace;
+  struct { unsigned int on; float v; } x = {on ? 1u : 0u, floor};
+  static_assert(offsetof(ppo_upd::Header, ls_floor) == offsetof(ppo_upd::Header, ls_floor_on) + 4, "layout");
+  if (cudaMemcpyAsync(&hdr->ls_floor_on, &x, sizeof(x), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess || cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+    return ufail(QX_ECUDA, "ppo_update_set_log_std_floor: copy failed");
   return QX_OK;
 }
 

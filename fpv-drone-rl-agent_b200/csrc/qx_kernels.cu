@@ -772,7 +772,7 @@ struct QxHandle {
   qx::ResetQueue* queue;
   float* raster;       // vision_mode 1: qx::RasterConsts
   // staging for the *_host calls
-  cudaStream_t stream, h2d_stream, d2h_stream;
+  cudaStream_t stream, h2d_stream, d2h_stream, d2h2_stream;  // d2h2: the small result arrays, so that their per-copy latency hides behind the observation copy
   cudaEvent_t ev_h2d[16], ev_k[16], ev_d2h;
   float* h_act; float* d_act;
   float* h_obs; float* d_obs;
@@ -974,6 +974,7 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->d2h2_stream, cudaStreamNonBlocking);
   for (int k = 0; k < 16 && e == cudaSuccess; ++k) {
     e = cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_k[k], cudaEventDisableTiming);
@@ -1001,6 +1002,7 @@ extern "C" int qx_destroy(QxHandle* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  if (h->d2h2_stream) cudaStreamDestroy(h->d2h2_stream);
   for (int k = 0; k < 16; ++k) { if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]); if (h->ev_k[k]) cudaEventDestroy(h->ev_k[k]); }
   if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
   cudaSetDevice(prev);
@@ -1273,9 +1275,12 @@ static bool is_pinned(const void* p) {
 // batches are cut into chunks and pipelined over three streams -- actions H2D (chunk k+1) | step + reset kernels
 // (chunk k) | results D2H (chunk k-1) -- so the PCIe transfers, which dominate this call, overlap the kernels and
 // each other (H2D and D2H use different copy engines).
-extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
-                            uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
+static int step_host_impl(QxHandle* h, const float* actions_host, void* obs_host, const int32_t obs_dtype, float* reward_host,
+                          uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
   if (!h || !actions_host) return fail(QX_EINVAL, "qx_step_host: bad arguments");
+  if (obs_dtype != QX_OBS_F32 && obs_dtype != QX_OBS_BF16) return fail(QX_EINVAL, "qx_step_host: obs_dtype is QX_OBS_F32 or QX_OBS_BF16");
+  const bool bf16 = obs_dtype == QX_OBS_BF16;
+  const size_t osz = bf16 ? 2 : 4;  // bytes per observation element on the wire
   DeviceGuard g(h->device);
   int rc = ensure_staging(h);
   if (rc) return rc;
@@ -1285,8 +1290,10 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
   if (!is_pinned(actions_host)) { memcpy(h->h_act, actions_host, sizeof(float) * n * ad); src = h->h_act; }
   const bool p_obs = is_pinned(obs_host), p_rew = is_pinned(reward_host), p_te = is_pinned(terminated_host),
              p_tr = is_pinned(truncated_host);
-  float* dst_obs = obs_host ? (p_obs ? obs_host : h->h_obs) : nullptr;
+  char* dst_obs = obs_host ? (p_obs ? (char*)obs_host : (char*)h->h_obs) : nullptr;
   float* dst_rew = reward_host ? (p_rew ? reward_host : h->h_rew) : nullptr;
+  // the handle's own copy of the flags is only needed to unpack pageable buffers and to pick the terminal observations
+  const bool own_flags = terminal_obs_host || (terminated_host && !p_te) || (truncated_host && !p_tr);
   const int chunks = n >= (1 << 17) ? 8 : 1;
   const int64_t per = ((n + chunks - 1) / chunks + qx::kBlock - 1) / qx::kBlock * qx::kBlock;
   for (int k = 0; k < chunks; ++k) {
@@ -1296,7 +1303,7 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     QX_CUDA(cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
     QX_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[k], 0));
     qx::StepArgs a{};
-    a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.reward = h->d_rew;
+    a.state = h->state; a.actions = h->d_act; a.obs = h->d_obs; a.obs_stride = od; a.obs_bf16 = bf16; a.reward = h->d_rew;
     a.terminated = h->d_flags; a.truncated = h->d_flags + n; a.terminal_obs = terminal_obs_host ? h->d_tobs : nullptr;
     a.stats = h->stats; a.queue = h->queue; a.n = n; a.k = 1; a.env_begin = b; a.env_count = cnt;
     if (h->cfg.auto_reset && (n > kInlineResetMaxEnvs || (h->hot_mode == 1 && h->hot_ok))) {
@@ -1309,17 +1316,22 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
     if (rc) return rc;
     QX_CUDA(cudaEventRecord(h->ev_k[k], h->stream));
     QX_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->ev_k[k], 0));
-    if (dst_obs) QX_CUDA(cudaMemcpyAsync(dst_obs + b * od, h->d_obs + b * od, sizeof(float) * cnt * od, cudaMemcpyDeviceToHost, h->d2h_stream));
-    if (dst_rew) QX_CUDA(cudaMemcpyAsync(dst_rew + b, h->d_rew + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-    QX_CUDA(cudaMemcpyAsync(h->h_flags + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-    QX_CUDA(cudaMemcpyAsync(h->h_flags + n + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-    if (p_te) QX_CUDA(cudaMemcpyAsync(terminated_host + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
-    if (p_tr) QX_CUDA(cudaMemcpyAsync(truncated_host + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, h->d2h_stream));
+    QX_CUDA(cudaStreamWaitEvent(h->d2h2_stream, h->ev_k[k], 0));
+    if (dst_obs) QX_CUDA(cudaMemcpyAsync(dst_obs + b * od * osz, (const char*)h->d_obs + b * od * osz, osz * cnt * od, cudaMemcpyDeviceToHost, h->d2h_stream));
+    cudaStream_t s2 = h->d2h2_stream;
+    if (dst_rew) QX_CUDA(cudaMemcpyAsync(dst_rew + b, h->d_rew + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s2));
+    if (own_flags) {
+      QX_CUDA(cudaMemcpyAsync(h->h_flags + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, s2));
+      QX_CUDA(cudaMemcpyAsync(h->h_flags + n + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, s2));
+    }
+    if (p_te) QX_CUDA(cudaMemcpyAsync(terminated_host + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, s2));
+    if (p_tr) QX_CUDA(cudaMemcpyAsync(truncated_host + b, h->d_flags + n + b, cnt, cudaMemcpyDeviceToHost, s2));
   }
   if (terminal_obs_host) QX_CUDA(cudaMemcpyAsync(h->h_tobs, h->d_tobs, sizeof(float) * n * od, cudaMemcpyDeviceToHost, h->d2h_stream));
+  QX_CUDA(cudaStreamSynchronize(h->d2h2_stream));
   QX_CUDA(cudaStreamSynchronize(h->d2h_stream));
   QX_CUDA(cudaStreamSynchronize(h->stream));
-  if (obs_host && !p_obs) memcpy(obs_host, h->h_obs, sizeof(float) * n * od);
+  if (obs_host && !p_obs) memcpy(obs_host, h->h_obs, osz * n * od);
   if (reward_host && !p_rew) memcpy(reward_host, h->h_rew, sizeof(float) * n);
   if (terminated_host && !p_te) memcpy(terminated_host, h->h_flags, n);
   if (truncated_host && !p_tr) memcpy(truncated_host, h->h_flags + n, n);
@@ -1328,6 +1340,16 @@ extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_h
       if (h->h_flags[i] || h->h_flags[n + i]) memcpy(terminal_obs_host + i * od, h->h_tobs + i * od, sizeof(float) * od);
   }
   return QX_OK;
+}
+
+extern "C" int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
+                            uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
+  return step_host_impl(h, actions_host, obs_host, QX_OBS_F32, reward_host, terminated_host, truncated_host, terminal_obs_host);
+}
+
+extern "C" int qx_step_host_ex(QxHandle* h, const float* actions_host, void* obs_host, int32_t obs_dtype, float* reward_host,
+                               uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host) {
+  return step_host_impl(h, actions_host, obs_host, obs_dtype, reward_host, terminated_host, truncated_host, terminal_obs_host);
 }
 
 extern "C" int qx_get_state(QxHandle* h, void* planes_host) {

@@ -238,13 +238,20 @@ QX_DI uint4 env_philox(uint4 c, uint32_t k0, uint32_t k1) { return philox4x32<kE
 
 // ((x >> 9) + 0.5) * 2^-23 without an int->float conversion (reset pose noise)
 QX_DI float u01(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 0.99999994f; }
-// 16-bit field in the top of the mantissa of [1,2): m = 1 + k 2^-16
-QX_DI float m12_lo16(uint32_t w) { return __uint_as_float(((w << 7) & 0x007fff80u) | 0x3f800000u); }
-QX_DI float m12_hi16(uint32_t w) { return __uint_as_float(((w >> 9) & 0x007fff80u) | 0x3f800000u); }
-template <class T> QX_DI T m12_lo(uint32_t w) { return m12_lo16(w); }
-template <class T> QX_DI T m12_hi(uint32_t w) { return m12_hi16(w); }
-template <class T> QX_DI T m12_lo(uint2 w) { return T{m12_lo16(w.x), m12_lo16(w.y)}; }
-template <class T> QX_DI T m12_hi(uint2 w) { return T{m12_hi16(w.x), m12_hi16(w.y)}; }
+// the 16-bit halves of a word as floats k in [0, 65535] (one I2F.U16 each: the conversion takes the half-word operand directly,
+// where building 1 + k 2^-16 in the mantissa costs a shift, a mask and an or per field)
+QX_DI float f16_lo16(uint32_t w) { return __uint2float_rn(w & 0xffffu); }
+QX_DI float f16_hi16(uint32_t w) { return __uint2float_rn(w >> 16); }
+template <class T> QX_DI T f16_lo(uint32_t w) { return f16_lo16(w); }
+template <class T> QX_DI T f16_hi(uint32_t w) { return f16_hi16(w); }
+template <class T> QX_DI T f16_lo(uint2 w) { return T{f16_lo16(w.x), f16_lo16(w.y)}; }
+template <class T> QX_DI T f16_hi(uint2 w) { return T{f16_hi16(w.x), f16_hi16(w.y)}; }
+// Box-Muller inputs from a field k: u = (k + 0.5) 2^-16 in (0,1), angle = 2 pi u - pi.  Written on m = 1 + k 2^-16 these were
+// u = m - (1 - 2^-17) and angle = fma(m, c, -d) with c = 6.28318530718f, d = 9.42473002f; on k they are the same real numbers
+// rounded once -- u is exact either way, and c - d is exactly representable, so fma(k, c 2^-16, c - d) == fma(m, c, -d) bit for bit
+// (oracle/quadx_model.py:normal4 and oracle/quadx_oracle.c keep the m form; tests/test_gpu_parity.py compares the streams).
+constexpr float kBmU0 = 7.62939453125e-06f, kBmUk = 1.52587890625e-05f;             // 2^-17, 2^-16
+constexpr float kBmTk = 6.28318530718f * 1.52587890625e-05f, kBmT0 = 6.28318530718f - 9.42473002f;
 
 // 4 x noise_ratio * N(0,1) from two 32-bit words, like oracle normal4(): each word is one Box-Muller pair
 // (low half -> radius, high half -> angle).  u = m - (1 - 2^-17) = (k + 0.5) 2^-16 in (0,1);  the scale is folded into
@@ -252,10 +259,10 @@ template <class T> QX_DI T m12_hi(uint2 w) { return T{m12_hi16(w.x), m12_hi16(w.
 // sine / cosine are most accurate, = 2 pi m - (2 pi (1 - 2^-17) + pi).
 template <class T, class U>
 QX_DI void normal4_scaled(U w0, U w1, float noise_k, T n[4]) {
-  const T ra = vsqrt(vmul(vlg2(vadd(m12_lo<T>(w0), -0.99999237060546875f)), noise_k));
-  const T rb = vsqrt(vmul(vlg2(vadd(m12_lo<T>(w1), -0.99999237060546875f)), noise_k));
-  const T ta = vfma(m12_hi<T>(w0), 6.28318530718f, -9.42473002f);
-  const T tb = vfma(m12_hi<T>(w1), 6.28318530718f, -9.42473002f);
+  const T ra = vsqrt(vmul(vlg2(vfma(f16_lo<T>(w0), kBmUk, splat<T>(kBmU0))), noise_k));
+  const T rb = vsqrt(vmul(vlg2(vfma(f16_lo<T>(w1), kBmUk, splat<T>(kBmU0))), noise_k));
+  const T ta = vfma(f16_hi<T>(w0), kBmTk, splat<T>(kBmT0));
+  const T tb = vfma(f16_hi<T>(w1), kBmTk, splat<T>(kBmT0));
   n[0] = vmul(ra, vcos(ta)); n[1] = vmul(ra, vsin(ta)); n[2] = vmul(rb, vcos(tb)); n[3] = vmul(rb, vsin(tb));
 }
 
@@ -472,7 +479,9 @@ QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], cons
   e.qx = vmul(nx, inv); e.qy = vmul(ny, inv); e.qz = vmul(nzq, inv); e.qw = vmul(nw, inv);
   // floor stand-in
   const auto below = vlt(e.pz, c.floor_z);
-  if (vany(below)) floor_contact(e, c, below);
+  if (warp_any(below)) {
+    if (vany(below)) floor_contact(e, c, below);
+  }
   e.contact = below;
   if (!c.state_stale) {
     const T X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
@@ -530,10 +539,10 @@ QX_DI f2 cpair(float a, float b) { return f2{a, b}; }
 
 // 4 x noise_ratio N(0,1) of one env as two pairs (n0, n1), (n2, n3): normal4_scaled<float> with the two Box-Muller words paired
 QX_DI void normal4_scaled_s(uint32_t w0, uint32_t w1, float noise_k, f2 n[2]) {
-  const f2 u = vadd(f2{m12_lo16(w0), m12_lo16(w1)}, -0.99999237060546875f);
+  const f2 u = vfma(f2{f16_lo16(w0), f16_lo16(w1)}, kBmUk, f2{kBmU0, kBmU0});
   const f2 r2 = vmul(f2{__log2f(u.x), __log2f(u.y)}, noise_k);
   const float ra = fsqrt(r2.x), rb = fsqrt(r2.y);
-  const f2 t = vfma(f2{m12_hi16(w0), m12_hi16(w1)}, 6.28318530718f, -9.42473002f);
+  const f2 t = vfma(f2{f16_hi16(w0), f16_hi16(w1)}, kBmTk, f2{kBmT0, kBmT0});
   n[0] = vmul(f2{__cosf(t.x), __sinf(t.x)}, ra);
   n[1] = vmul(f2{__cosf(t.y), __sinf(t.y)}, rb);
 }
@@ -668,7 +677,7 @@ QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], con
   }
   // floor stand-in (cold)
   const bool below = e.pz < c.floor_z;
-  if (below) {
+  if (warp_any(below) && below) {
     e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vxy = f2{0.f, 0.f};
     const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
     const float a20 = __fmul_rn(__fsub_rn(__fmul_rn(X, Z), __fmul_rn(W, Y)), 2.f), a21 = __fmul_rn(fmaf(Y, Z, __fmul_rn(W, X)), 2.f);
@@ -691,6 +700,26 @@ QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], con
   }
 }
 
+// atan2 for finite arguments that are not both zero: octant reduction to t = min / max in [0, 1], t P(t^2) with the degree-7
+// minimax P (tools/fit_atan.py: max error 1.2e-7 in fp32 arithmetic, the size of one rounding at pi), ~22 instructions against
+// libm's ~50.  The Euler angles are differenced over agent_dt = 1/40 s in the observation: 2.4e-7 rad -> 1e-5 rad/s.
+QX_DI float fast_atan2f(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+  const float t = mn * frcp(mx), u = t * t;
+  float p = fmaf(u, -0.0040544066578149796f, 0.021862365305423737f);
+  p = fmaf(u, p, -0.05591144412755966f);
+  p = fmaf(u, p, 0.09642129391431808f);
+  p = fmaf(u, p, -0.13908600807189941f);
+  p = fmaf(u, p, 0.1994655877351761f);
+  p = fmaf(u, p, -0.33329859375953674f);
+  p = fmaf(u, p, 0.9999993443489075f);
+  float r = t * p;
+  r = ay > ax ? 1.57079632679f - r : r;
+  r = x < 0.f ? 3.14159265359f - r : r;
+  return copysignf(r, y);
+}
+
 // pybullet.getEulerFromQuaternion (ZYX, with its gimbal guard)
 __device__ __forceinline__ void quat_to_euler(float x, float y, float z, float w, float& roll, float& pitch, float& yaw) {
   const float sarg = -2.f * (x * z - w * y);
@@ -699,9 +728,9 @@ __device__ __forceinline__ void quat_to_euler(float x, float y, float z, float w
   } else if (sarg >= 0.99999f) {
     roll = 0.f; pitch = 1.57079632679f; yaw = 2.f * atan2f(-x, y);
   } else {
-    roll = atan2f(2.f * (y * z + w * x), w * w - x * x - y * y + z * z);
+    roll = fast_atan2f(2.f * (y * z + w * x), w * w - x * x - y * y + z * z);
     pitch = asinf(sarg);
-    yaw = atan2f(2.f * (x * y + w * z), w * w + x * x - y * y - z * z);
+    yaw = fast_atan2f(2.f * (x * y + w * z), w * w + x * x - y * y - z * z);
   }
 }
 

@@ -184,6 +184,18 @@ class QuadXSim:
                                     None if tobs is None else tobs.ctypes.data_as(C.c_void_p)))
         return obs, rew, te.astype(bool), tr.astype(bool), tobs
 
+    def step_host_tensors(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor,
+                          truncated: torch.Tensor) -> None:
+        """qx_step_host_ex on caller-owned CPU tensors (pinned ones are read / written in place by the copy engines):
+        `obs` is float32 or bfloat16 [n, obs_dim] -- bfloat16 halves the bytes of the device-to-host copy that bounds this call."""
+        for t, shape, dt, name in ((actions, (self.n, self.act_dim), (torch.float32,), "actions"), (obs, (self.n, self.obs_dim), (torch.float32, torch.bfloat16), "obs"),
+                                   (reward, (self.n,), (torch.float32,), "reward"), (terminated, (self.n,), (torch.uint8,), "terminated"),
+                                   (truncated, (self.n,), (torch.uint8,), "truncated")):
+            if t.device.type != "cpu" or tuple(t.shape) != shape or t.dtype not in dt or not t.is_contiguous():
+                raise ValueError(f"{name}: expected a contiguous CPU tensor {shape} of {dt}, got {tuple(t.shape)} {t.dtype} on {t.device}")
+        check(self.lib.qx_step_host_ex(self._h, _ptr(actions), _ptr(obs), 1 if obs.dtype == torch.bfloat16 else 0, _ptr(reward), _ptr(terminated),
+                                       _ptr(truncated), None))
+
     @property
     def state_fields(self) -> list[str]:
         """Names of the carried words, in plane order (qx_state_words of them)."""

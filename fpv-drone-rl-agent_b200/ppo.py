@@ -202,10 +202,12 @@ class RunningStats:
         self.inv_std = torch.ones(dim, device=device)
         self.scratch = torch.zeros(_lib.lib().ppo_running_stats_scratch_bytes(dim) // 8, dtype=torch.float64, device=device)
 
-    def update(self, x: torch.Tensor) -> None:
+    def update(self, x: torch.Tensor, out: tuple | None = None) -> None:
+        """Merge the rows of x; the refreshed fp32 (mean, inv_std) go to `out` instead of self.mean / self.inv_std when given."""
         assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] >= self.dim and x.stride(1) == 1
-        check(_lib.lib().ppo_running_stats_update(_p(x), x.stride(0), x.shape[0], self.dim, _p(self.stats), self.eps, _p(self.mean),
-                                                  _p(self.inv_std), _p(self.scratch), _stream(self.device)))
+        mean, inv_std = out if out is not None else (self.mean, self.inv_std)
+        check(_lib.lib().ppo_running_stats_update(_p(x), x.stride(0), x.shape[0], self.dim, _p(self.stats), self.eps, _p(mean),
+                                                  _p(inv_std), _p(self.scratch), _stream(self.device)))
 
     def state_dict(self):
         return {"stats": self.stats.clone(), "mean": self.mean.clone(), "inv_std": self.inv_std.clone()}
@@ -233,12 +235,13 @@ class RunningStats:
 
 def policy_forward(pol: PackedPolicy, obs: torch.Tensor, *, obs_stats: RunningStats | None = None, obs_clip: float = 10.0, seed: int = 0,
                    row0: int = 0, step: int = 0, step_base: torch.Tensor | None = None, deterministic: bool = False,
-                   actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None) -> None:
-    """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward)."""
+                   actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None, norm: tuple | None = None) -> None:
+    """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward).  norm = (mean, inv_std) overrides obs_stats' buffers."""
     n = obs.shape[0]
     assert obs.dtype == torch.float32 and obs.stride(1) == 1
-    check(_lib.lib().ppo_policy_forward(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(obs_stats.mean) if obs_stats else None,
-                                        _p(obs_stats.inv_std) if obs_stats else None, obs_clip, seed, row0, step, _p(step_base),
+    mean, inv_std = norm if norm is not None else ((obs_stats.mean, obs_stats.inv_std) if obs_stats else (None, None))
+    check(_lib.lib().ppo_policy_forward(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(mean),
+                                        _p(inv_std), obs_clip, seed, row0, step, _p(step_base),
                                         int(deterministic), _p(actions), _p(env_actions), _p(values), _p(log_probs), _p(obs_norm),
                                         _stream(pol.device)))
 
@@ -296,6 +299,9 @@ class PPOConfig:
     tf32_update: bool = True  # (fused_update=False only) library GEMMs of the torch update in TF32
     lr_final_frac: float = 1.0  # linear learning-rate schedule (SB3 lr callable): lr * (1 - (1 - lr_final_frac) * progress), progress from
     lr_anneal_iters: int = 0    # iteration / lr_anneal_iters clipped to 1 (0 = constant learning rate); fused update only
+    recompute_old_logp: bool = False  # (fused update) old log-probs from the update kernel's own forward pass, see ppo_update_recompute_logp
+    kl_stop_per_minibatch: bool = False  # target_kl checked per minibatch on the device (SB3) instead of on the epoch mean by the host
+    log_std_min: float | None = None  # optional floor of log_std (fused update only): the exploration noise cannot collapse below exp(this)
     fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
 
 
@@ -339,45 +345,56 @@ class RolloutEngine:
         self._q_count, self._q_idx = cnt, idx
         self._graph = None
         self._side = torch.cuda.Stream(device=d)
+        self._snap_mean = torch.zeros(2, od, **f)  # fp32 (mean, inv_std) of the observation statistics, one pair per step parity
+        self._snap_inv = torch.ones(2, od, **f)
         self.sim.reset(self.cur_obs)
         # one-time kernel attribute setup must not happen inside a graph capture
         policy_forward(self.pol, self.cur_obs, deterministic=True, values=self.last_values)
 
-    # one env step of the rollout, slot t
+    # one env step of the rollout, slot t.  Two streams (two branches of the captured graph):
+    #   main: obs statistics -> policy forward + sampling -> env step -> reset of the finished envs        (the critical path)
+    #   side: reward normalisation (return statistics) -> time-limit bootstrap                           (only GAE reads its results)
+    # The side branch of step t reads what the env step wrote (raw reward, flags, terminal observations, the done queue) and the
+    # observation statistics of step t, so (a) main joins it before the env step of t + 1 overwrites those, and (b) the fp32
+    # (mean, inv_std) of step t live in the buffer pair t & 1, which the statistics update of step t + 1 does not touch.
     def _step(self, t: int) -> None:
         cfg, sim, L, s = self.cfg, self.sim, self.lib, _stream(self.device)
         stats = self.obs_stats if cfg.norm_obs else None
+        norm = (self._snap_mean[t & 1], self._snap_inv[t & 1]) if cfg.norm_obs else None
         if cfg.norm_obs:
-            self.obs_stats.update(self.cur_obs)
-        policy_forward(self.pol, self.cur_obs, obs_stats=stats, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
+            self.obs_stats.update(self.cur_obs, out=norm)
+        policy_forward(self.pol, self.cur_obs, obs_stats=stats, norm=norm, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
                        step_base=self.step_base, actions=self.actions[t], env_actions=self.env_actions, values=self.values[t],
                        log_probs=self.log_probs[t], obs_norm=self.obs[t])
+        main = torch.cuda.current_stream(self.device)
+        if t > 0:
+            main.wait_stream(self._side)  # join the side branch of step t - 1 (the rollout ends with a join, so there is none at t = 0)
         check(L.qx_step_begin(sim._h, _p(self.env_actions), _p(self.cur_obs), 0, self.cur_obs.stride(0), _p(self.raw_reward), _p(self.te),
                               _p(self.tr), _p(self.terminal_obs), s))
-        # fork: the reset of the finished envs (a latency chain of 20 idle sub-steps for a handful of warps) runs on a side
-        # stream next to the reward path and the time-limit bootstrap, which only read what the step launch wrote
-        main = torch.cuda.current_stream(self.device)
-        self._side.wait_stream(main)
+        self._side.wait_stream(main)  # fork
         with torch.cuda.stream(self._side):
-            check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), _stream(self.device)))
-        if cfg.norm_reward:
-            check(L.ppo_reward_normalize(_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
-                                         self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]),
-                                         _p(self.ret_stats.scratch), s))
-        else:
-            self.rewards[t].copy_(self.raw_reward)
-            torch.bitwise_or(self.te, self.tr, out=self.dones[t])
-        # SB3: rewards[idx] += gamma * V(terminal_obs) when the time limit, not the task, ended the episode
-        check(L.ppo_bootstrap_truncated(C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
-                                        _p(stats.mean) if stats else None, _p(stats.inv_std) if stats else None, cfg.clip_obs,
-                                        self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), s))
-        main.wait_stream(self._side)  # join
+            ss = _stream(self.device)
+            if cfg.norm_reward:
+                check(L.ppo_reward_normalize(_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
+                                             self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]),
+                                             _p(self.ret_stats.scratch), ss))
+            else:
+                self.rewards[t].copy_(self.raw_reward)
+                torch.bitwise_or(self.te, self.tr, out=self.dones[t])
+            # SB3: rewards[idx] += gamma * V(terminal_obs) when the time limit, not the task, ended the episode
+            check(L.ppo_bootstrap_truncated(C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
+                                            _p(norm[0]) if norm else None, _p(norm[1]) if norm else None, cfg.clip_obs,
+                                            self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), ss))
+        check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), s))
 
     def _rollout_body(self) -> None:
         for t in range(self.T):
             with torch.cuda.nvtx.range(f"rollout_step_{t}"):  # shows up per step in nsys / ncu timelines
                 self._step(t)
+        torch.cuda.current_stream(self.device).wait_stream(self._side)  # join: rewards / dones of the last step
         stats = self.obs_stats if self.cfg.norm_obs else None
+        if stats is not None:  # the canonical fp32 copies (final forward, export, checkpoints) follow the last step's pair
+            stats.mean.copy_(self._snap_mean[(self.T - 1) & 1]); stats.inv_std.copy_(self._snap_inv[(self.T - 1) & 1])
         policy_forward(self.pol, self.cur_obs, obs_stats=stats, obs_clip=self.cfg.clip_obs, deterministic=True, values=self.last_values)
         gae(self.rewards, self.values, self.dones, self.last_values, self.cfg.gamma, self.cfg.gae_lambda, self.advantages, self.returns)
         self.step_base += self.T
@@ -435,7 +452,7 @@ class FusedUpdater:
                 p.data = self.flat[o:o + p.numel()].view_as(p)
                 o += p.numel()
         f = dict(device=self.device, dtype=torch.float32)
-        self.grad = torch.zeros(self.n_params, **f)
+        self.grad = torch.zeros(self.n_params + 4, **f)  # + the two early-stop slots (ppo_update_kl_stop), padded to 16 bytes
         self.exp_avg = torch.zeros(self.n_params, **f)
         self.exp_avg_sq = torch.zeros(self.n_params, **f)
         self.loss_stats = torch.zeros(8, **f)
@@ -449,7 +466,7 @@ class FusedUpdater:
         check(self.lib.ppo_update_minibatch(C.byref(self.packed.struct), _p(ro.obs), _p(ro.actions), _p(ro.log_probs), _p(ro.advantages),
                                             _p(ro.returns), _p(tiles), tiles.numel(), N, cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
                                             int(normalize_adv), _p(self.grad), _p(self.loss_stats), _p(self.workspace), _stream(self.device)))
-        return self.grad
+        return self.grad[:self.n_params]
 
     def apply(self) -> None:
         """All-reduce (world > 1), clip, Adam, re-pack."""
@@ -465,6 +482,28 @@ class FusedUpdater:
     def step(self, ro: "RolloutEngine", tiles: torch.Tensor) -> None:
         self.gradient(ro, tiles)
         self.apply()
+
+    def recompute_logp(self, ro: "RolloutEngine") -> None:
+        """Overwrite the rollout's log-probs with the update kernel's own forward pass (ppo_update_recompute_logp)."""
+        N = ro.T * ro.n
+        n_tiles = (N + 127) // 128
+        if getattr(self, "_all_tiles", None) is None or self._all_tiles.numel() != n_tiles:
+            self._all_tiles = torch.arange(n_tiles, dtype=torch.int32, device=self.device)
+        check(self.lib.ppo_update_recompute_logp(C.byref(self.packed.struct), _p(ro.obs), _p(ro.actions), _p(self._all_tiles), n_tiles, N,
+                                                 _p(ro.log_probs), _p(self.workspace), _stream(self.device)))
+
+    def arm_kl_stop(self, target_kl: float) -> None:
+        """(Re-)arm SB3's target_kl early stop on the device (0 = off) and clear its latch: call once per PPO.train."""
+        check(self.lib.ppo_update_kl_stop(_p(self.workspace), float(target_kl), None, None, _stream(self.device)))
+
+    def kl_stopped(self) -> tuple[bool, int]:
+        """(latched, optimiser steps skipped since arm_kl_stop)."""
+        st, sk = C.c_int32(), C.c_int32()
+        check(self.lib.ppo_update_kl_stop(_p(self.workspace), -1.0, C.byref(st), C.byref(sk), _stream(self.device)))
+        return bool(st.value), sk.value
+
+    def set_log_std_floor(self, floor: float | None) -> None:
+        check(self.lib.ppo_update_set_log_std_floor(_p(self.workspace), 0 if floor is None else 1, 0.0 if floor is None else float(floor), _stream(self.device)))
 
     def set_lr_scale(self, scale: float) -> None:
         """Learning-rate schedule: later optimiser steps (graph replays included) use learning_rate * scale."""
@@ -507,6 +546,8 @@ class PPOTrainer:
         self.sim = QuadXSim(cfg.n_envs, ecfg, seed=cfg.seed, env_id0=shard_env_ids(rank, cfg.n_envs), device=dev, task=task)
         self.rollout = RolloutEngine(self.sim, self.packed, cfg, row0=shard_env_ids(rank, cfg.n_envs))
         self.fused = FusedUpdater(self.model, self.packed, cfg, dev, world) if cfg.fused_update else None
+        if self.fused is not None and cfg.log_std_min is not None:
+            self.fused.set_log_std_floor(cfg.log_std_min)
         self.opt = None if cfg.fused_update else torch.optim.Adam(self.model.parameters(), lr=cfg.learning_rate, eps=1e-5,
                                                                    capturable=bool(cfg.graph_update and world == 1))
         self._epoch_graph = None
@@ -596,11 +637,14 @@ class PPOTrainer:
                 fu.step(ro, self._perm[s0:s0 + min(tpm, n_tiles - s0)])
 
         fu.loss_stats.zero_()
-        done_epochs = 0
+        if cfg.recompute_old_logp:
+            fu.recompute_logp(ro)
+        dev_kl = cfg.target_kl if cfg.kl_stop_per_minibatch else 0.0
+        fu.arm_kl_stop(dev_kl)
+        steps_before = fu.adam_steps
         for _ in range(cfg.n_epochs):
             self._perm.copy_(torch.randperm(n_tiles, device=self.device, generator=self.gen).to(torch.int32))
-            kl_before = float(fu.loss_stats[4]) if cfg.target_kl > 0.0 else 0.0
-            n_before = float(fu.loss_stats[5]) if cfg.target_kl > 0.0 else 0.0
+            kl_before, n_before = (float(fu.loss_stats[4]), float(fu.loss_stats[5])) if cfg.target_kl > 0.0 and not cfg.kl_stop_per_minibatch else (0.0, 0.0)
             if cfg.graph_update:
                 if self._epoch_graph is None:
                     keep = {k: v.clone() for k, v in fu.state_dict().items() if torch.is_tensor(v)}
@@ -617,12 +661,17 @@ class PPOTrainer:
                     # warm-up and capture must not count as training: restore parameters, moments, step count, statistics
                     fu.load_state_dict({**keep, "adam_steps": steps0})
                     fu.loss_stats.copy_(stats0)
+                    fu.arm_kl_stop(dev_kl)
                     self._epoch_graph = g
                 self._epoch_graph.replay()
             else:
                 epoch_body()
-            done_epochs += 1
-            if cfg.target_kl > 0.0:
+            if cfg.target_kl > 0.0 and cfg.kl_stop_per_minibatch:
+                # the stop is taken on the device, per minibatch and identically on every rank (ppo_update_kl_stop); the host only
+                # looks at the latch once per epoch to save itself the launches of the remaining epochs
+                if fu.kl_stopped()[0]:
+                    break
+            elif cfg.target_kl > 0.0:  # epoch mean of the approximate KL, one host sync per epoch
                 akl = torch.tensor([(float(fu.loss_stats[4]) - kl_before) / max(float(fu.loss_stats[5]) - n_before, 1.0)], device=self.device)
                 if self.world > 1:
                     dist.all_reduce(akl)
@@ -631,12 +680,13 @@ class PPOTrainer:
                     break
         st = fu.loss_stats.tolist()
         n = max(st[5], 1.0)
-        return {"pg": st[0] / n, "vf": st[1] / n, "kl": st[2] / n, "clipfrac": st[3] / n, "optimizer_steps": done_epochs * len(starts)}
+        return {"pg": st[0] / n, "vf": st[1] / n, "kl": st[2] / n, "clipfrac": st[3] / n, "optimizer_steps": fu.adam_steps - steps_before}
 
     def update(self) -> dict:
-        """SB3 PPO.train: n_epochs passes over the rollout in shuffled minibatches; target_kl stops the remaining epochs
-        once the mean approximate KL of an epoch exceeds 1.5 x target (SB3 checks per minibatch; per epoch here, so that
-        the check costs one host sync per epoch)."""
+        """SB3 PPO.train: n_epochs passes over the rollout in shuffled minibatches; target_kl ends the training of this rollout
+        once the approximate KL exceeds 1.5 x target: on the mean of an epoch (one host sync per epoch; the default -- measured
+        to learn faster on this task) or, with kl_stop_per_minibatch, at the first minibatch over the threshold and before its
+        optimiser step as SB3 does, decided on the device (ppo_update_kl_stop)."""
         if self.fused is not None:
             return self._update_fused()
         cfg, ro = self.cfg, self.rollout

@@ -109,6 +109,25 @@ int ppo_update_adam(float* params, const float* grad, float* exp_avg, float* exp
 /* learning-rate schedule (SB3 `learning_rate` as a callable of the remaining progress): subsequent ppo_update_adam calls --
  * captured in a CUDA graph or not -- step with lr * scale.  The factor lives in the workspace; a fresh workspace means 1. */
 int ppo_update_set_lr_scale(void* workspace, float scale, void* stream);
+/* log pi(a | s) of every row of the given 128-row tiles, by the forward arithmetic of ppo_update_minibatch (actor only, nothing
+ * else is touched).  The rollout's policy kernel and the update kernel run the same bf16 network through different tile
+ * schedules; their means differ by bf16 rounding (~1e-3), which the Gaussian log-density divides by sigma -- once the policy
+ * has narrowed to sigma ~ e^-6 that is a spurious ratio != 1 at unchanged weights (an approx-KL floor of ~1e-2) that the clipped
+ * objective and the target_kl stop would act on.  Overwriting old_logp with this pass before the first epoch makes the ratio of
+ * the first minibatch exactly 1, as in SB3 where both passes are the same fp32 module. */
+int ppo_update_recompute_logp(const PpoPolicy* p, const float* obs, const float* actions, const int32_t* tiles_dev, int32_t n_tiles,
+                              int64_t n_rows, float* logp_out, void* workspace, void* stream);
+/* SB3's `target_kl` early stop (PPO.train: the epoch loop ends at the first minibatch whose approx_kl exceeds 1.5 x target_kl,
+ * before that minibatch's optimiser step), taken on the device so that it works per minibatch inside a captured epoch.
+ * While target_kl > 0 is armed: ppo_update_minibatch appends this minibatch's sum of (ratio - 1) - log ratio and its row count to
+ * the gradient -- grad_out must then hold ppo_update_num_params() + 2 floats, and a gradient all-reduce must cover them, so
+ * every rank decides alike -- and ppo_update_adam turns into a no-op (no parameter / moment / step-count change) from the first
+ * minibatch over the threshold until the next re-arm.  target_kl >= 0 (re-)arms with that threshold (0 = off) and clears the
+ * latch; target_kl < 0 only reads.  stopped_out / skipped_out (nullable) return the latch and the number of skipped steps as
+ * they were BEFORE the re-arm. */
+int ppo_update_kl_stop(void* workspace, float target_kl, int32_t* stopped_out, int32_t* skipped_out, void* stream);
+/* optional lower bound of log_std applied by ppo_update_adam (on != 0): keeps the exploration noise from collapsing */
+int ppo_update_set_log_std_floor(void* workspace, int32_t on, float floor, void* stream);
 /* read (out != NULL) and / or set (set_to >= 0) the Adam step counter: checkpoint / resume */
 int ppo_update_step_count(void* workspace, int64_t set_to, int64_t* out, void* stream);
 

@@ -172,6 +172,12 @@ int qx_step_k(QxHandle* h, int32_t k, const float* actions_dev, float* obs_dev, 
 int qx_reset_host(QxHandle* h, const uint8_t* mask_host, float* obs_host);
 int qx_step_host(QxHandle* h, const float* actions_host, float* obs_host, float* reward_host,
                  uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host);
+/* qx_step_host with the observation element type chosen by the caller: QX_OBS_BF16 halves the bytes that cross PCIe
+ * (the call is bound by the device-to-host copy: 80 of its 86 result bytes per env-step are the observation; a bf16
+ * policy input loses nothing, tests/test_gpu_properties.py holds "bf16 obs == rounded f32 obs").  obs_host is
+ * [n_envs, obs_dim] of that type; everything else as qx_step_host.  Pinned caller buffers are written in place. */
+int qx_step_host_ex(QxHandle* h, const float* actions_host, void* obs_host, int32_t obs_dtype, float* reward_host,
+                    uint8_t* terminated_host, uint8_t* truncated_host, float* terminal_obs_host);
 
 /* Carried state as qx_state_words(h) planes of n_envs 32-bit words (layout in
  * DESIGN.md; QX_STATE_WORDS, or QX_STATE_WORDS_CASCADE when cfg.flight_mode != 0);

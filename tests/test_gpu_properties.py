@@ -137,7 +137,8 @@ def test_episode_accounting_at_scale(pkg):
 def test_chunked_host_pipeline_equals_device_path(pkg):
     """qx_step_host cuts batches >= 2^17 into 8 chunks pipelined over three streams (H2D | kernels | D2H); the results
     must be those of the plain device-buffer call, including across a mass termination (reset queue per chunk), with
-    pinned and with pageable host buffers, for a batch size that is not a multiple of anything."""
+    pinned and with pageable host buffers, for a batch size that is not a multiple of anything.  qx_step_host_ex with
+    bf16 observations (the compact wire format) must return the f32 observations rounded to nearest-even."""
     n = (1 << 17) + 37
     cfg = pkg.default_config()
     sim_h = pkg.QuadXSim(n, cfg, seed=3)
@@ -155,13 +156,24 @@ def test_chunked_host_pipeline_equals_device_path(pkg):
     L = _lib.lib()
     a_pin = torch.zeros(n, 4).pin_memory(); o_pin = torch.zeros(n, 20).pin_memory(); r_pin = torch.zeros(n).pin_memory()
     te_pin = torch.zeros(n, dtype=torch.uint8).pin_memory(); tr_pin = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    o16_pin = torch.zeros(n, 20, dtype=torch.bfloat16).pin_memory()
     g = torch.Generator().manual_seed(0)
     for k in range(34):  # zero thrust: every env terminates on its 32nd step
         a = torch.rand(n, 4, generator=g) * 0.2 - 0.1
         a[:, 3] = -1.0
         sim_d.step(a.to(d), obs, rew, te, tr)
         torch.cuda.synchronize()
-        if k % 2 == 0:  # pinned buffers, used in place
+        if k % 3 == 2:  # compact wire format: bf16 observations, pinned buffers
+            a_pin.copy_(a)
+            _lib.check(L.qx_step_host_ex(sim_h._h, C.c_void_p(a_pin.data_ptr()), C.c_void_p(o16_pin.data_ptr()), 1, C.c_void_p(r_pin.data_ptr()),
+                                         C.c_void_p(te_pin.data_ptr()), C.c_void_p(tr_pin.data_ptr()), None))
+            assert torch.equal(obs.cpu().to(torch.bfloat16), o16_pin), k
+            assert np.array_equal(rew.cpu().numpy(), r_pin.numpy()), k
+            assert np.array_equal(te.cpu().numpy(), te_pin.numpy()) and np.array_equal(tr.cpu().numpy(), tr_pin.numpy()), k
+            if k == 31:
+                assert te_pin.numpy().all()
+            continue
+        if k % 3 == 0:  # pinned buffers, used in place
             a_pin.copy_(a)
             _lib.check(L.qx_step_host(sim_h._h, C.c_void_p(a_pin.data_ptr()), C.c_void_p(o_pin.data_ptr()), C.c_void_p(r_pin.data_ptr()),
                                       C.c_void_p(te_pin.data_ptr()), C.c_void_p(tr_pin.data_ptr()), None))
@@ -172,6 +184,7 @@ def test_chunked_host_pipeline_equals_device_path(pkg):
         assert np.array_equal(te.cpu().numpy().astype(bool), te2) and np.array_equal(tr.cpu().numpy().astype(bool), tr2), k
         if k == 31:
             assert te2.all()
+    assert L.qx_step_host_ex(sim_h._h, C.c_void_p(a_pin.data_ptr()), C.c_void_p(o16_pin.data_ptr()), 7, None, None, None, None) != 0  # unknown dtype
     sa, sb = sim_h.get_state(), sim_d.get_state()
     for key in sa:
         assert np.array_equal(sa[key], sb[key]), key

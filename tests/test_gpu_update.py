@@ -151,7 +151,7 @@ def test_adam_step_matches_torch(pkg):
     g = torch.Generator(device="cuda").manual_seed(1)
     for k in range(3):
         grad = torch.randn(fu.n_params, device="cuda", generator=g) * (0.3 if k else 0.001)  # first step below the clip threshold, then above
-        fu.grad.copy_(grad)
+        fu.grad[:fu.n_params].copy_(grad)
         # the squared norm normally comes from the reduction kernel: recompute it for an injected gradient
         from fpv_drone_rl_agent_b200 import _lib
         import ctypes as C
@@ -168,6 +168,71 @@ def test_adam_step_matches_torch(pkg):
     tr.packed.refresh()
     for a, b in zip(packed_now, (tr.packed.w1, tr.packed.w2p, tr.packed.w2v, tr.packed.w3, tr.packed.b1, tr.packed.b2, tr.packed.b3, tr.packed.log_std)):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("log_std", [0.0, -6.0])
+def test_recomputed_old_logp_gives_unit_ratio(pkg, log_std):
+    """ppo_update_recompute_logp: the update kernel's own forward pass over the rollout.  At unchanged weights the ratio of the
+    following minibatch pass is exactly 1 (approx-KL 0, clip fraction 0), whatever sigma is; with the rollout kernel's
+    log-probs the same pass shows the bf16 rounding difference of the two kernels divided by sigma (printed for the record).
+    The recomputed values agree with the fp32 torch module like the rollout's do."""
+    tr = _trainer(pkg, True)
+    ro, fu = tr.rollout, tr.fused
+    with torch.no_grad():
+        tr.model.log_std.fill_(log_std)
+    tr.packed.refresh()
+    ro.collect()
+    torch.cuda.synchronize()
+    N = ro.T * ro.n
+    tiles = torch.arange((N + 127) // 128, device="cuda", dtype=torch.int32)
+    fu.loss_stats.zero_()
+    fu.gradient(ro, tiles)
+    st0 = fu.loss_stats.tolist()
+    rollout_lp = ro.log_probs.clone()
+    fu.recompute_logp(ro)
+    fu.loss_stats.zero_()
+    fu.gradient(ro, tiles)
+    torch.cuda.synchronize()
+    st1 = fu.loss_stats.tolist()
+    print(f"log_std {log_std}: approx-KL at unchanged weights {st0[4] / st0[5]:.3e} (clip fraction {st0[3] / st0[5]:.3e}) with the rollout kernel's "
+          f"log-probs, {st1[4] / st1[5]:.3e} after the recompute; max |delta logp| {float((ro.log_probs - rollout_lp).abs().max()):.3e}")
+    assert st1[5] == N and st1[4] == 0.0 and st1[3] == 0.0 and st1[2] == 0.0
+    with torch.no_grad():
+        _, lp, _ = tr.model.evaluate_actions(ro.obs.view(N, -1), ro.actions.view(N, -1))
+    tol = 0.3 if log_std == 0.0 else 0.3 * math.exp(-log_std) * 0.05
+    assert float((lp - ro.log_probs.view(-1)).abs().max()) <= tol
+
+
+def test_target_kl_stop_on_device(pkg):
+    """SB3's target_kl early stop taken inside the kernels (ppo_update_kl_stop): with a threshold far below the KL the first
+    optimiser steps produce, the latch sets at some minibatch and nothing -- parameters, moments, step count, the bf16 pack --
+    changes afterwards, inside a captured epoch as well; with a threshold far above it the run is unaffected."""
+    from fpv_drone_rl_agent_b200 import ppo
+
+    res = {}
+    for name, tkl, graph in (("off", 0.0, True), ("high", 10.0, True), ("tiny_graph", 1e-7, True), ("tiny_eager", 1e-7, False)):
+        cfg = ppo.PPOConfig(n_envs=4096, n_steps=32, seed=5, batch_size=16384, n_epochs=4, graph_update=graph, use_cuda_graph=False, target_kl=tkl, kl_stop_per_minibatch=True)
+        tr = ppo.PPOTrainer(cfg, device="cuda:0")
+        out = tr.learn_iteration()
+        torch.cuda.synchronize()
+        stopped, skipped = tr.fused.kl_stopped()
+        res[name] = (tr.fused.flat.clone(), out["optimizer_steps"], stopped, skipped, tr.fused.adam_steps)
+        if name == "tiny_graph":  # latched: further optimiser steps are no-ops
+            flat0, m0, w1_0 = tr.fused.flat.clone(), tr.fused.exp_avg.clone(), tr.packed.w1.clone()
+            tr._epoch_graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(flat0, tr.fused.flat) and torch.equal(m0, tr.fused.exp_avg) and torch.equal(w1_0, tr.packed.w1)
+            assert tr.fused.adam_steps == res[name][4]
+        tr.sim.close()
+    per_epoch = 4096 * 32 // 16384
+    assert res["off"][1] == res["high"][1] == 4 * per_epoch and not res["off"][2] and not res["high"][2] and res["high"][3] == 0
+    assert float((res["off"][0] - res["high"][0]).abs().max()) <= 5e-4
+    for name in ("tiny_graph", "tiny_eager"):
+        steps, stopped, skipped = res[name][1], res[name][2], res[name][3]
+        # the stop comes within the first epoch (the first minibatch already shows the bf16 rounding difference between the rollout's and
+        # the update's forward pass as a KL of ~1e-6), the epoch's remaining launches are no-ops, and the host does not launch another epoch
+        assert stopped and 0 <= steps < per_epoch and steps + skipped == per_epoch, (name, steps, skipped)
+    assert res["tiny_graph"][1] == res["tiny_eager"][1]
 
 
 def test_graph_replay_equals_eager_and_training_learns(pkg):

@@ -48,7 +48,7 @@ for r in sorted(rows[2:], key=lambda r: -_dur(r)):  # the longest instance of ev
         if k in hdr:
             vals[k] = r[hdr.index(k)]
             out.append(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |")
-    if "dram__bytes_read.sum" in vals and traffic is None and ("quadx_step_kernel<1" in name or "policy_forward" in name):
+    if "dram__bytes_read.sum" in vals and traffic is None and ("quadx_step_kernel<1" in name or "quadx_step_hot_kernel" in name or "policy_forward" in name):
         def tobytes(v, u):
             return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         rd = tobytes(vals["dram__bytes_read.sum"], units[hdr.index("dram__bytes_read.sum")])

@@ -31,6 +31,29 @@ CONFIGS = {
     "epochs8": dict(n_epochs=8, lr_final_frac=0.05, lr_anneal_iters=2000, log_std_init=-1.6),
     "long_rollout": dict(n_steps=128, batch_size=65536, lr_final_frac=0.05, lr_anneal_iters=1500, log_std_init=-1.6),
 }
+# round 2b: target_kl taken per minibatch on the device (ppo_update_kl_stop, SB3's semantics) instead of per epoch on the host
+G995 = dict(gamma=0.995, gae_lambda=0.97, lr_final_frac=0.05, lr_anneal_iters=3000, log_std_init=-1.6)
+for _s in range(1, 4):
+    KL = dict(kl_stop_per_minibatch=True, recompute_old_logp=False)
+    CONFIGS[f"kl_long_rollout_s{_s}"] = dict(CONFIGS["long_rollout"], seed=_s, **KL)
+    CONFIGS[f"kl_g995_s{_s}"] = dict(G995, seed=_s, **KL)
+    CONFIGS[f"kl_g995_floor_s{_s}"] = dict(G995, seed=_s, log_std_min=-5.5, **KL)
+    CONFIGS[f"kl_g995_tkl05_s{_s}"] = dict(G995, seed=_s, target_kl=0.05, **KL)
+    CONFIGS[f"kl_g995_ep8_s{_s}"] = dict(G995, seed=_s, n_epochs=8, **KL)
+# round 2c: old log-probs recomputed by the update kernel's own forward pass (ppo_update_recompute_logp; the default) vs the rollout kernel's
+for _s in range(1, 4):
+    CONFIGS[f"rc_long_rollout_s{_s}"] = dict(CONFIGS["long_rollout"], seed=_s)
+    CONFIGS[f"rc_g995_s{_s}"] = dict(G995, seed=_s)
+    CONFIGS[f"norc_long_rollout_s{_s}"] = dict(CONFIGS["long_rollout"], seed=_s, recompute_old_logp=False)
+    CONFIGS[f"rc_g995_nodecay_s{_s}"] = dict(gamma=0.995, gae_lambda=0.97, log_std_init=-1.6, seed=_s)
+# round 2d: keep exploring long enough to leave the ~165 plateau (runs that narrow to log_std < -5 within 4 s stay on it)
+for _s in range(1, 4):
+    X = dict(G995, seed=_s, recompute_old_logp=False)
+    CONFIGS[f"ex_floor45_s{_s}"] = dict(X, log_std_min=-4.5)
+    CONFIGS[f"ex_floor40_s{_s}"] = dict(X, log_std_min=-4.0)
+    CONFIGS[f"ex_ent_s{_s}"] = dict(X, ent_coef=0.003)
+    CONFIGS[f"ex_std10_floor45_s{_s}"] = dict(X, log_std_init=-1.0, log_std_min=-4.5)
+    CONFIGS[f"ex_32k_floor45_s{_s}"] = dict(X, n_envs=32768, batch_size=65536, log_std_min=-4.5)
 for _s in range(1, 6):  # run-to-run spread of the configuration bench.py's train leg uses
     CONFIGS[f"long_rollout_seed{_s}"] = dict(CONFIGS["long_rollout"], seed=_s)
     CONFIGS[f"gamma995_seed{_s}"] = dict(CONFIGS["gamma995"], seed=_s)
