@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libquadx_b200.so")
+LIB_PATH = os.environ.get("QX_LIB") or os.path.join(_HERE, "csrc", "libquadx_b200.so")  # QX_LIB: a tuning build (tools/ only)
 
 QX_TASK_HOVER, QX_TASK_YAW = 0, 1
 QX_OBS_F32, QX_OBS_BF16 = 0, 1

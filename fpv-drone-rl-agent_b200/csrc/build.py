@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, "libquadx_b200.so")
+LIB = os.environ.get("QX_LIB_OUT") or os.path.join(HERE, "libquadx_b200.so")  # QX_LIB_OUT: tuning builds (QX_NVCC_EXTRA) next to the product library
 SOURCES = ["qx_kernels.cu", "ppo_kernels.cu", "ppo_update_kernels.cu"]
 HEADERS = ["qx_model.cuh", "qx_lanes.cuh", "qx_ref_constants.cuh", "qx_internal.h", "tc05.cuh", os.path.join(ROOT, "include", "quadx_b200.h"), os.path.join(ROOT, "include", "ppo_b200.h")]
 NVCC_FLAGS = [

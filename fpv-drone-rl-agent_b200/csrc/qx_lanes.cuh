@@ -52,10 +52,6 @@ QX_DI float vcos(float a) { return __cosf(a); }
 QX_DI bool vlt(float a, float b) { return a < b; }
 QX_DI bool vgt(float a, float b) { return a > b; }
 QX_DI bool vany(bool m) { return m; }
-// does any converged lane of this warp see `m`?  A warp-uniform test around a cold block: ptxas if-converts short blocks guarded by
-// a per-thread predicate (the floor stand-in is ~24 instructions per sub-step that every warp then issues), a uniform branch it
-// cannot -- one VOTE + BRA when nobody is on the floor.  Purely a scheduling device: the guarded code still tests its own predicate.
-QX_DI bool warp_any(bool m) { return __any_sync(__activemask(), m); }
 QX_DI bool mor(bool a, bool b) { return a || b; }
 QX_DI float vsel(bool m, float a, float b) { return m ? a : b; }
 template <class T> QX_DI T splat(float s);
@@ -115,7 +111,6 @@ template <bool PK> QX_DI P2<PK> vcos(P2<PK> a) { return P2<PK>{__cosf(a.x), __co
 template <bool PK> QX_DI m2 vlt(P2<PK> a, float b) { return m2{a.x < b, a.y < b}; }
 template <bool PK> QX_DI m2 vgt(P2<PK> a, float b) { return m2{a.x > b, a.y > b}; }
 QX_DI bool vany(m2 m) { return m.x || m.y; }
-QX_DI bool warp_any(m2 m) { return __any_sync(__activemask(), m.x || m.y); }
 QX_DI m2 mor(m2 a, m2 b) { return m2{a.x || b.x, a.y || b.y}; }
 template <bool PK> QX_DI P2<PK> vsel(m2 m, P2<PK> a, P2<PK> b) { return P2<PK>{m.x ? a.x : b.x, m.y ? a.y : b.y}; }
 template <bool PK> QX_DI P2<PK> vsel(m2 m, P2<PK> a, float b) { return P2<PK>{m.x ? a.x : b, m.y ? a.y : b}; }

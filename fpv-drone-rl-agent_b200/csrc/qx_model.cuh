@@ -479,9 +479,7 @@ QX_DI void physics_substep(Core<T>& e, const DevConfig& c, const T apwm[4], cons
   e.qx = vmul(nx, inv); e.qy = vmul(ny, inv); e.qz = vmul(nzq, inv); e.qw = vmul(nw, inv);
   // floor stand-in
   const auto below = vlt(e.pz, c.floor_z);
-  if (warp_any(below)) {
-    if (vany(below)) floor_contact(e, c, below);
-  }
+  if (vany(below)) floor_contact(e, c, below);  // (ptxas if-converts this block; a warp-uniform VOTE + branch around it measured 2 % slower)
   e.contact = below;
   if (!c.state_stale) {
     const T X = e.qx, Y = e.qy, Z = e.qz, W = e.qw;
@@ -540,9 +538,9 @@ QX_DI f2 cpair(float a, float b) { return f2{a, b}; }
 // 4 x noise_ratio N(0,1) of one env as two pairs (n0, n1), (n2, n3): normal4_scaled<float> with the two Box-Muller words paired
 QX_DI void normal4_scaled_s(uint32_t w0, uint32_t w1, float noise_k, f2 n[2]) {
   const f2 u = vfma(f2{f16_lo16(w0), f16_lo16(w1)}, kBmUk, f2{kBmU0, kBmU0});
+  const f2 t = vfma(f2{f16_hi16(w0), f16_hi16(w1)}, kBmTk, f2{kBmT0, kBmT0});
   const f2 r2 = vmul(f2{__log2f(u.x), __log2f(u.y)}, noise_k);
   const float ra = fsqrt(r2.x), rb = fsqrt(r2.y);
-  const f2 t = vfma(f2{f16_hi16(w0), f16_hi16(w1)}, kBmTk, f2{kBmT0, kBmT0});
   n[0] = vmul(f2{__cosf(t.x), __sinf(t.x)}, ra);
   n[1] = vmul(f2{__cosf(t.y), __sinf(t.y)}, rb);
 }
@@ -677,7 +675,7 @@ QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], con
   }
   // floor stand-in (cold)
   const bool below = e.pz < c.floor_z;
-  if (warp_any(below) && below) {
+  if (below) {  // if-converted by ptxas (~24 predicated instructions per sub-step); a VOTE + uniform branch around it measured 2 % slower
     e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vxy = f2{0.f, 0.f};
     const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
     const float a20 = __fmul_rn(__fsub_rn(__fmul_rn(X, Z), __fmul_rn(W, Y)), 2.f), a21 = __fmul_rn(fmaf(Y, Z, __fmul_rn(W, X)), 2.f);
@@ -755,15 +753,18 @@ __device__ __forceinline__ void euler_to_quat(float roll, float pitch, float yaw
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& vis, float& cx, float& cy, float& area,
                                        float& ratio) {
+  // (every multiply-add is written as fmaf: the library is built with -fmad=false, a * b + c * d would issue three instructions)
   const float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
-  const float r00 = 1.f - 2.f * (yy + zz), r01 = 2.f * (xy - wz), r02 = 2.f * (xz + wy);
-  const float r10 = 2.f * (xy + wz), r11 = 1.f - 2.f * (xx + zz), r12 = 2.f * (yz - wx);
-  const float r20 = 2.f * (xz - wy), r21 = 2.f * (yz + wx), r22 = 1.f - 2.f * (xx + yy);
+  const float x2 = x + x, y2 = y + y, z2 = z + z;
+  const float wx = w * x2, wy = w * y2, wz = w * z2;
+  const float r00 = fmaf(-y, y2, fmaf(-z, z2, 1.f)), r11 = fmaf(-x, x2, fmaf(-z, z2, 1.f)), r22 = fmaf(-x, x2, fmaf(-y, y2, 1.f));
+  const float r01 = fmaf(x, y2, -wz), r10 = fmaf(x, y2, wz);
+  const float r02 = fmaf(x, z2, wy), r20 = fmaf(x, z2, -wy);
+  const float r12 = fmaf(y, z2, -wx), r21 = fmaf(y, z2, wx);
   // sin / cos of the roll Euler angle = (r21, r22) / cos(pitch)
   float sph = 0.f, cph = 1.f;
   if (fabsf(r20) < 0.99999f) {
-    const float inv = frsqrt(r21 * r21 + r22 * r22);
+    const float inv = frsqrt(fmaf(r21, r21, r22 * r22));
     sph = r21 * inv; cph = r22 * inv;
   }
   // camera axes in the body frame: Rx(-roll) Ry(-tilt) Rx(roll) applied to x, z
@@ -771,20 +772,20 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
   const float fx = cd, fy = sd * sph, fzz = sd * cph;
   const float ux = -sd * cph, uy = sph * cph * (cd - 1.f), uz = fmaf(sph, sph, cd * cph * cph);
   // right = fwd x up
-  const float rx = fy * uz - fzz * uy, ry = fzz * ux - fx * uz, rz = fx * uy - fy * ux;
+  const float rx = fmaf(fy, uz, -(fzz * uy)), ry = fmaf(fzz, ux, -(fx * uz)), rz = fmaf(fx, uy, -(fy * ux));
   float pxs[4], pys[4];
   bool ok = true;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float dx = c.panel[3 * k + 0] - e.px, dy = c.panel[3 * k + 1] - e.py, dz = c.panel[3 * k + 2] - e.pz;
-    const float bx = r00 * dx + r10 * dy + r20 * dz - c.cam_off[0];
-    const float by = r01 * dx + r11 * dy + r21 * dz - c.cam_off[1];
-    const float bz = r02 * dx + r12 * dy + r22 * dz - c.cam_off[2];
-    const float depth = fx * bx + fy * by + fzz * bz;
+    const float bx = fmaf(r20, dz, fmaf(r10, dy, fmaf(r00, dx, -c.cam_off[0])));
+    const float by = fmaf(r21, dz, fmaf(r11, dy, fmaf(r01, dx, -c.cam_off[1])));
+    const float bz = fmaf(r22, dz, fmaf(r12, dy, fmaf(r02, dx, -c.cam_off[2])));
+    const float depth = fmaf(fzz, bz, fmaf(fy, by, fx * bx));
     ok = ok && (depth > c.cam_near);
-    const float k1 = c.inv_tan * frcp(fmaxf(depth, 1e-9f));
-    pxs[k] = fmaf((rx * bx + ry * by + rz * bz) * k1, c.half_res, c.half_res);
-    pys[k] = fmaf(-(ux * bx + uy * by + uz * bz) * k1, c.half_res, c.half_res);
+    const float k1 = c.inv_tan * c.half_res * frcp(fmaxf(depth, 1e-9f));
+    pxs[k] = fmaf(fmaf(rz, bz, fmaf(ry, by, rx * bx)), k1, c.half_res);
+    pys[k] = fmaf(fmaf(uz, bz, fmaf(uy, by, ux * bx)), -k1, c.half_res);
   }
   const float xmin = fminf(fminf(pxs[0], pxs[1]), fminf(pxs[2], pxs[3]));
   const float xmax = fmaxf(fmaxf(pxs[0], pxs[1]), fmaxf(pxs[2], pxs[3]));
@@ -795,9 +796,9 @@ __device__ __forceinline__ void vision(const Env& e, const DevConfig& c, bool& v
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int kn = (k + 1) & 3;
-    a2 += pxs[k] * pys[kn] - pxs[kn] * pys[k];
+    a2 += fmaf(pxs[k], pys[kn], -(pxs[kn] * pys[k]));
     const float ex = pxs[kn] - pxs[k], ey = pys[kn] - pys[k];
-    per += fsqrt(ex * ex + ey * ey);
+    per += fsqrt(fmaf(ex, ex, ey * ey));
   }
   const float wpx = floorf(xmax - 0.5f) - ceilf(xmin - 0.5f) + 1.f;
   const float hpx = floorf(ymax - 0.5f) - ceilf(ymin - 0.5f) + 1.f;

@@ -302,6 +302,8 @@ class PPOConfig:
     recompute_old_logp: bool = False  # (fused update) old log-probs from the update kernel's own forward pass, see ppo_update_recompute_logp
     kl_stop_per_minibatch: bool = False  # target_kl checked per minibatch on the device (SB3) instead of on the epoch mean by the host
     log_std_min: float | None = None  # optional floor of log_std (fused update only): the exploration noise cannot collapse below exp(this)
+    log_std_min_final: float | None = None  # ... released linearly to this value between the iterations log_std_min_iters = (start, end):
+    log_std_min_iters: tuple = (0, 0)       # explore at a guaranteed noise level first, then let the policy narrow (0, 0 = constant floor)
     fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
 
 
@@ -725,6 +727,10 @@ class PPOTrainer:
         if self.fused is not None and self.cfg.lr_anneal_iters > 0:
             prog = min(1.0, self._iteration / self.cfg.lr_anneal_iters)
             self.fused.set_lr_scale(1.0 - (1.0 - self.cfg.lr_final_frac) * prog)
+        if self.fused is not None and self.cfg.log_std_min is not None and self.cfg.log_std_min_final is not None:
+            a, b = self.cfg.log_std_min_iters
+            prog = 0.0 if self._iteration <= a else (1.0 if b <= a or self._iteration >= b else (self._iteration - a) / (b - a))
+            self.fused.set_log_std_floor(self.cfg.log_std_min + (self.cfg.log_std_min_final - self.cfg.log_std_min) * prog)
         self._iteration += 1
         with torch.cuda.nvtx.range("ppo_collect_rollouts"):
             self.rollout.collect()

@@ -110,11 +110,11 @@ int ppo_update_adam(float* params, const float* grad, float* exp_avg, float* exp
  * captured in a CUDA graph or not -- step with lr * scale.  The factor lives in the workspace; a fresh workspace means 1. */
 int ppo_update_set_lr_scale(void* workspace, float scale, void* stream);
 /* log pi(a | s) of every row of the given 128-row tiles, by the forward arithmetic of ppo_update_minibatch (actor only, nothing
- * else is touched).  The rollout's policy kernel and the update kernel run the same bf16 network through different tile
- * schedules; their means differ by bf16 rounding (~1e-3), which the Gaussian log-density divides by sigma -- once the policy
- * has narrowed to sigma ~ e^-6 that is a spurious ratio != 1 at unchanged weights (an approx-KL floor of ~1e-2) that the clipped
- * objective and the target_kl stop would act on.  Overwriting old_logp with this pass before the first epoch makes the ratio of
- * the first minibatch exactly 1, as in SB3 where both passes are the same fp32 module. */
+ * else is touched): the counterpart of SB3's policy.evaluate_actions on a stored rollout.  Overwriting old_logp with it makes
+ * the ratio of a following minibatch pass exactly 1 at unchanged weights (tests/test_gpu_update.py).  Measured: the rollout's
+ * policy kernel and this pass -- the same bf16 network through different tile schedules -- agree to 4e-6 in log pi even at
+ * sigma = e^-6 (approx-KL < 1e-9), so the trainer does not need it (PPOConfig.recompute_old_logp = False); it is there for
+ * rollouts whose log-probs came from somewhere else (an imported SB3 policy, a replayed buffer). */
 int ppo_update_recompute_logp(const PpoPolicy* p, const float* obs, const float* actions, const int32_t* tiles_dev, int32_t n_tiles,
                               int64_t n_rows, float* logp_out, void* workspace, void* stream);
 /* SB3's `target_kl` early stop (PPO.train: the epoch loop ends at the first minibatch whose approx_kl exceeds 1.5 x target_kl,

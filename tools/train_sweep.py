@@ -54,6 +54,19 @@ for _s in range(1, 4):
     CONFIGS[f"ex_ent_s{_s}"] = dict(X, ent_coef=0.003)
     CONFIGS[f"ex_std10_floor45_s{_s}"] = dict(X, log_std_init=-1.0, log_std_min=-4.5)
     CONFIGS[f"ex_32k_floor45_s{_s}"] = dict(X, n_envs=32768, batch_size=65536, log_std_min=-4.5)
+# round 2e: the entropy bonus is what leaves the plateau (ex_ent reached 188-190); how much, and how repeatable
+for _s in range(1, 6):
+    X = dict(G995, seed=_s)
+    CONFIGS[f"ent2_s{_s}"] = dict(X, ent_coef=0.002)
+    CONFIGS[f"ent3_s{_s}"] = dict(X, ent_coef=0.003)
+    CONFIGS[f"ent5_s{_s}"] = dict(X, ent_coef=0.005)
+    CONFIGS[f"ent10_s{_s}"] = dict(X, ent_coef=0.01)
+# round 2f: a floor under log_std while exploring (every seed reaches the ~190 mode, 178 with the noise of the floor), then released
+for _s in range(1, 6):
+    X = dict(G995, seed=_s)
+    CONFIGS[f"fs_a_s{_s}"] = dict(X, log_std_min=-4.5, log_std_min_final=-7.0, log_std_min_iters=(400, 1200))
+    CONFIGS[f"fs_b_s{_s}"] = dict(X, log_std_min=-4.5, log_std_min_final=-7.0, log_std_min_iters=(200, 800))
+    CONFIGS[f"fs_ent_s{_s}"] = dict(X, ent_coef=0.003, log_std_min=-4.5, log_std_min_final=-7.0, log_std_min_iters=(300, 900))
 for _s in range(1, 6):  # run-to-run spread of the configuration bench.py's train leg uses
     CONFIGS[f"long_rollout_seed{_s}"] = dict(CONFIGS["long_rollout"], seed=_s)
     CONFIGS[f"gamma995_seed{_s}"] = dict(CONFIGS["gamma995"], seed=_s)
