@@ -47,6 +47,9 @@ def main():
     ap.add_argument("--gae-lambda", type=float, default=0.95)
     ap.add_argument("--lr-final-frac", type=float, default=1.0, help="linear learning-rate decay to this fraction ...")
     ap.add_argument("--lr-anneal-iters", type=int, default=0, help="... over this many iterations (0 = constant)")
+    ap.add_argument("--log-std-min", type=float, default=None, help="floor under log_std while exploring ...")
+    ap.add_argument("--log-std-min-final", type=float, default=None, help="... released linearly to this value ...")
+    ap.add_argument("--log-std-min-iters", type=int, nargs=2, default=(0, 0), help="... between these iterations")
     ap.add_argument("--json", default="", help="write the per-iteration log here")
     args = ap.parse_args()
 
@@ -67,7 +70,8 @@ def main():
 
     cfg = ppo.PPOConfig(n_envs=args.envs, n_steps=args.steps, n_epochs=args.epochs, batch_size=args.batch, learning_rate=args.lr, seed=args.seed,
                         ent_coef=args.ent_coef, gamma=args.gamma, target_kl=args.target_kl, log_std_init=args.log_std_init, gae_lambda=args.gae_lambda,
-                        lr_final_frac=args.lr_final_frac, lr_anneal_iters=args.lr_anneal_iters)
+                        lr_final_frac=args.lr_final_frac, lr_anneal_iters=args.lr_anneal_iters, log_std_min=args.log_std_min,
+                        log_std_min_final=args.log_std_min_final, log_std_min_iters=tuple(args.log_std_min_iters))
     trainer = ppo.PPOTrainer(cfg, device=f"cuda:{local}", rank=rank, world=world)
     writer = None
     if args.tensorboard and rank == 0:
