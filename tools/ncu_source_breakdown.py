@@ -54,7 +54,7 @@ def main():
         subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=d, capture_output=True)
         cubin = os.path.join(d, "qx_kernels.sm_100a.cubin")
         elf = subprocess.run(["cuobjdump", "-elf", cubin], capture_output=True, text=True).stdout
-        idx = next(l.split()[0] for l in elf.split("\n") if l.rstrip().endswith(mangled) or (mangled in l and " 0x12 " in l))
+        idx = next(l.split()[0] for l in elf.split("\n") if l.split() and l.split()[-1] == mangled and l.split()[0].startswith("0x"))
         dis = subprocess.run(["nvdisasm", "-g", "-fun", idx, cubin], capture_output=True, text=True, errors="ignore").stdout
     ins, cur = [], None
     for line in dis.split("\n"):
@@ -62,12 +62,15 @@ def main():
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"^\s+/\*[0-9a-f]{4,}\*/\s+\S", line):
+        if re.match(r"^\s+/\*[0-9a-f]{4,}\*/\s+.*?;", line):
             ins.append(cur)
     n = min(len(R), len(ins))
     counts = [int(R[k][iI]) for k in range(n)]
     tot = sum(counts)
-    base = min(c for c in counts if c > 0 and counts.count(c) > 50)  # warps of the launch = executions of a once-per-launch instruction
+    from collections import Counter
+
+    freq = Counter(c for c in counts if c > 0)
+    base = min(c for c, k in freq.items() if k >= 200)  # warps of the launch = executions of a once-per-launch instruction
     print(f"{n} SASS instructions, {tot} warp-instructions executed, {base} warps")
     cls = defaultdict(lambda: [0, 0])
     for c in counts:
