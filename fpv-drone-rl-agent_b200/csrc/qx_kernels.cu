@@ -1294,10 +1294,14 @@ static int step_host_impl(QxHandle* h, const float* actions_host, void* obs_host
   float* dst_rew = reward_host ? (p_rew ? reward_host : h->h_rew) : nullptr;
   // the handle's own copy of the flags is only needed to unpack pageable buffers and to pick the terminal observations
   const bool own_flags = terminal_obs_host || (terminated_host && !p_te) || (truncated_host && !p_tr);
-  const int chunks = n >= (1 << 17) ? 8 : 1;
-  const int64_t per = ((n + chunks - 1) / chunks + qx::kBlock - 1) / qx::kBlock * qx::kBlock;
+  // 8 chunks, the first cut in two again: the D2H engine -- what bounds the call -- idles until the first chunk has gone
+  // through H2D and the kernels, so that chunk is kept small
+  const int chunks = n >= (1 << 17) ? 9 : 1;
+  const int64_t per = chunks == 1 ? n : ((n + 7) / 8 + 2 * qx::kBlock - 1) / (2 * qx::kBlock) * (2 * qx::kBlock);
   for (int k = 0; k < chunks; ++k) {
-    const int64_t b = k * per, cnt = (b + per <= n ? per : n - b);
+    const int64_t b = chunks == 1 ? 0 : (k == 0 ? 0 : (k == 1 ? per / 2 : (k - 1) * per));
+    const int64_t want = chunks == 1 ? n : (k < 2 ? per / 2 : per);
+    const int64_t cnt = b >= n ? 0 : (b + want <= n ? want : n - b);
     if (cnt <= 0) break;
     QX_CUDA(cudaMemcpyAsync(h->d_act + b * ad, src + b * ad, sizeof(float) * cnt * ad, cudaMemcpyHostToDevice, h->h2d_stream));
     QX_CUDA(cudaEventRecord(h->ev_h2d[k], h->h2d_stream));
