@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-o", LIB, *srcs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    log_path = os.path.join(HERE, "build.log") if not os.environ.get("QX_LIB_OUT") else LIB + ".log"  # a tuning build keeps the product's log intact
+    with open(log_path, "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + log)

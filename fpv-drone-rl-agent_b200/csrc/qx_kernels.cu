@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <new>
 
 #include "../../include/quadx_b200.h"
@@ -469,7 +470,15 @@ template <> struct HotShape<0> { static constexpr int kBlock = 128, kMinBlocks =
 template <> struct HotShape<3> { static constexpr int kBlock = 128, kMinBlocks = 4; };  // 128
 template <> struct HotShape<4> { static constexpr int kBlock = 128, kMinBlocks = 5; };  // 96
 template <> struct HotShape<5> { static constexpr int kBlock = 128, kMinBlocks = 6; };  // 80
+#ifdef QX_EXTRA_SHAPES  // tuning builds: small blocks (finer-grained block turnover, 21-23 warps per SM), S1 lanes only
+template <> struct HotShape<6> { static constexpr int kBlock = 64, kMinBlocks = 11; };  // 88 registers, 22 warps
+template <> struct HotShape<7> { static constexpr int kBlock = 32, kMinBlocks = 23; };  // 88 registers, 23 warps
+template <> struct HotShape<8> { static constexpr int kBlock = 64, kMinBlocks = 10; };  // 96 registers, 20 warps
+template <> struct HotShape<9> { static constexpr int kBlock = 32, kMinBlocks = 21; };  // 96 registers, 21 warps
+constexpr int kHotShapes = 10;
+#else
 constexpr int kHotShapes = 6;
+#endif
 
 template <bool REF>
 __device__ __noinline__ void run_env_cold(const DevConfig& cparam, const StepArgs& a, const int64_t i) {
@@ -571,12 +580,22 @@ QX_DI void hot_substeps(const DevConfig& c, Env& e0, Env& e1, const float4 av0, 
   if (kLanes == 2) unpack_lane<1>(e1, p);
 }
 
-// the paired sub-step loop: nsub sub-steps (even) towards a fixed setpoint, noise stream `stream`
-QX_DI void substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float spz, const float thrust, const int nsub, const uint32_t stream, const int64_t i0) {
+#ifndef QX_SWP
+#define QX_SWP 0
+#endif
+#ifndef QX_DIAG
+#define QX_DIAG 0
+#endif
+// the paired sub-step loop: nsub sub-steps (even) towards a fixed setpoint, noise stream `stream`.  FLOOR = false is the
+// speculative loop without the floor stand-in (physics_substep_s); returns the lowest pz it saw (+inf with FLOOR = true).
+template <bool FLOOR = true>
+QX_DI float substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float spz, const float thrust, const int nsub, const uint32_t stream, const int64_t i0) {
   CoreS p;
   pack_core_s(p, e0);
+  float minz = __int_as_float(0x7f800000);
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i0);
   const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
+#if QX_SWP == 0
 #pragma unroll 1
   for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call, two physics sub-steps
     f2 apwm[2];
@@ -584,14 +603,70 @@ QX_DI void substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float sp
     f2 nz[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
     uint4 b = make_uint4(0u, 0u, 0u, 0u);
     if (c.noise) {
+#if QX_DIAG == 2  // diagnostic build (timing only, wrong numbers): no Philox
+      b = make_uint4(k0 + j, k1 ^ j, e0.rng_ctr * 0x9E3779B9u + j, k0 * 0x85EBCA6Bu + j);
+#else
       b = env_philox(make_uint4((uint32_t)j >> 1, stream, e0.rng_ctr, 0u), k0, k1);
+#endif
+#if QX_DIAG == 1  // diagnostic build (timing only, wrong numbers): no Box-Muller
+      nz[0] = vmul(f2{__uint_as_float(0x3f800000u | (b.x >> 9)) - 1.5f, __uint_as_float(0x3f800000u | (b.x << 14 >> 9)) - 1.5f}, 0.02f);
+      nz[1] = vmul(f2{__uint_as_float(0x3f800000u | (b.y >> 9)) - 1.5f, __uint_as_float(0x3f800000u | (b.y << 14 >> 9)) - 1.5f}, 0.02f);
+#else
       normal4_scaled_s(b.x, b.y, c.noise_k, nz);
+#endif
     }
-    physics_substep_s(p, c, apwm, nz, false);
+    physics_substep_s<FLOOR>(p, c, apwm, nz, false, minz);
+#if QX_DIAG == 1
+    if (c.noise) {
+      nz[0] = vmul(f2{__uint_as_float(0x3f800000u | (b.z >> 9)) - 1.5f, __uint_as_float(0x3f800000u | (b.z << 14 >> 9)) - 1.5f}, 0.02f);
+      nz[1] = vmul(f2{__uint_as_float(0x3f800000u | (b.w >> 9)) - 1.5f, __uint_as_float(0x3f800000u | (b.w << 14 >> 9)) - 1.5f}, 0.02f);
+    }
+#else
     if (c.noise) normal4_scaled_s(b.z, b.w, c.noise_k, nz);
-    physics_substep_s(p, c, apwm, nz, j + 2 == nsub);
+#endif
+    physics_substep_s<FLOOR>(p, c, apwm, nz, j + 2 == nsub, minz);
   }
+#elif QX_SWP == 1
+  // software-pipelined noise: the Philox call of Aviary.step j + 1 is issued at the top of step j, where nothing depends on it,
+  // so that its ~7 x 3 dependent integer operations fill the stalls of the control / physics chain instead of heading it
+  uint4 b = make_uint4(0u, 0u, 0u, 0u);
+  if (c.noise) b = env_philox(make_uint4(0u, stream, e0.rng_ctr, 0u), k0, k1);
+#pragma unroll 1
+  for (int j = 0; j < nsub; j += 2) {
+    const uint4 bc = b;
+    if (c.noise && j + 2 < nsub) b = env_philox(make_uint4(((uint32_t)j >> 1) + 1u, stream, e0.rng_ctr, 0u), k0, k1);
+    f2 apwm[2];
+    control_update_s(p, c, spxy, spz, thrust, apwm);
+    f2 nz[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+    if (c.noise) normal4_scaled_s(bc.x, bc.y, c.noise_k, nz);
+    physics_substep_s<FLOOR>(p, c, apwm, nz, false, minz);
+    if (c.noise) normal4_scaled_s(bc.z, bc.w, c.noise_k, nz);
+    physics_substep_s<FLOOR>(p, c, apwm, nz, j + 2 == nsub, minz);
+  }
+#else
+  // ... and the Box-Muller transform with it: the 8 scaled normals of step j + 1 are ready before step j ends
+  f2 na[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}}, nb[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
+  if (c.noise) {
+    const uint4 b = env_philox(make_uint4(0u, stream, e0.rng_ctr, 0u), k0, k1);
+    normal4_scaled_s(b.x, b.y, c.noise_k, na);
+    normal4_scaled_s(b.z, b.w, c.noise_k, nb);
+  }
+#pragma unroll 1
+  for (int j = 0; j < nsub; j += 2) {
+    const f2 ca[2] = {na[0], na[1]}, cb[2] = {nb[0], nb[1]};
+    if (c.noise && j + 2 < nsub) {
+      const uint4 b = env_philox(make_uint4(((uint32_t)j >> 1) + 1u, stream, e0.rng_ctr, 0u), k0, k1);
+      normal4_scaled_s(b.x, b.y, c.noise_k, na);
+      normal4_scaled_s(b.z, b.w, c.noise_k, nb);
+    }
+    f2 apwm[2];
+    control_update_s(p, c, spxy, spz, thrust, apwm);
+    physics_substep_s<FLOOR>(p, c, apwm, ca, false, minz);
+    physics_substep_s<FLOOR>(p, c, apwm, cb, j + 2 == nsub, minz);
+  }
+#endif
   unpack_core_s(e0, p);
+  return minz;
 }
 // hot_substeps for V = S1: one env per thread with its own components paired (qx_model.cuh, CoreS)
 template <>
@@ -600,6 +675,34 @@ QX_DI void hot_substeps<S1>(const DevConfig& c, Env& e0, Env&, const float4 av0,
   const float spz = __fmul_rn(av0.z, c.act_scale[2]);
   const float thrust = __saturatef(fmaf(av0.w, c.thrust_scale, c.thrust_bias));  // QuadX.update_control clips the mode-0 thrust command to [0, 1]
   substeps_s(c, e0, spxy, spz, thrust, c.n_sub_step, STREAM_STEP, i0);
+}
+#ifndef QX_SPEC_FLOOR
+#define QX_SPEC_FLOOR 1
+#endif
+#ifndef QX_PREFETCH_TAIL
+#define QX_PREFETCH_TAIL 1
+#endif
+// The same with the floor stand-in speculated away (QX_SPEC_FLOOR): a warp none of whose envs rests on the floor or is predicted
+// to come near it within this agent step runs the loop without the stand-in and checks afterwards that no pz went below
+// floor_z; an env that fails the check (rare: the predictor is generous) reloads its loop planes -- nothing has been stored yet
+// -- and runs the full loop.  Every other warp runs the full loop as before.  Bitwise equal to hot_substeps<S1> by construction;
+// tests/test_gpu_properties.py holds it against the generic kernels.
+QX_DI void hot_substeps_spec(const DevConfig& c, Env& e0, const StepArgs& a, const float4 av0, const int64_t i0) {
+  const f2 spxy = vmul(f2{av0.x, av0.y}, cpair(c.act_scale[0], c.act_scale[1]));
+  const float spz = __fmul_rn(av0.z, c.act_scale[2]);
+  const float thrust = __saturatef(fmaf(av0.w, c.thrust_scale, c.thrust_bias));
+  // predictor: where pz would be after this agent step at the current vertical speed, less 2 g T^2 / 2 (T = n_sub_step h)
+  const float T = __fmul_rn((float)c.n_sub_step, c.h);
+  const float reach = fmaf(fminf(e0.vz, 0.f), T, e0.pz) - __fmul_rn(__fmul_rn(c.g, T), T);
+  const bool risky = e0.contact || !(reach > c.floor_z);
+  const bool slow = __any_sync(__activemask(), risky);
+  float minz = __int_as_float(0x7f800000);
+  if (!slow) minz = substeps_s<false>(c, e0, spxy, spz, thrust, c.n_sub_step, STREAM_STEP, i0);
+  const bool redo = minz < c.floor_z;
+  if (slow || redo) {
+    if (redo) load_env_loop(e0, a.state, a.n, i0);
+    substeps_s<true>(c, e0, spxy, spz, thrust, c.n_sub_step, STREAM_STEP, i0);
+  }
 }
 
 // reset() of one queued env on the paired code (hover.py:72-113: respawn, the idle Aviary.step()s with a zero setpoint, first
@@ -634,6 +737,10 @@ template <bool REF, class V>
 QX_DI void hot_task(const DevConfig& c, const DevConfig& cparam, const StepArgs& a, const int64_t i0, const int64_t i1, const bool has1) {
   constexpr int kLanes = Lane<V>::N;
   Env e0, e1;
+  // the action is requested together with the state planes: loaded after the finished-env test below it cost every warp a second,
+  // serialised trip to HBM (4.5 % of the warp's lifetime in the ncu stall samples of profiles/k1_r2k.md)
+  const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0);
+  const float4 av1 = kLanes == 2 ? __ldg(reinterpret_cast<const float4*>(a.actions) + i1) : av0;
   load_env_loop(e0, a.state, a.n, i0);
   if (kLanes == 2) load_env_loop(e1, a.state, a.n, i1);
   if ((e0.flags | (kLanes == 2 ? e1.flags : 0u)) & (F_TERM | F_TRUNC)) {  // cold: a finished env does not step (hover.py:347-348)
@@ -641,9 +748,13 @@ QX_DI void hot_task(const DevConfig& c, const DevConfig& cparam, const StepArgs&
     if (has1) run_env_cold<REF>(cparam, a, i1);
     return;
   }
-  const float4 av0 = __ldg(reinterpret_cast<const float4*>(a.actions) + i0);
-  const float4 av1 = kLanes == 2 ? __ldg(reinterpret_cast<const float4*>(a.actions) + i1) : av0;
-  hot_substeps<V>(c, e0, e1, av0, av1, i0, i1);
+#if QX_PREFETCH_TAIL
+  // the epilogue planes are loaded after the loop (no registers across it); ask L2 for them now
+#pragma unroll
+  for (int p = kLoopPlanes; p < 11; ++p) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state + (int64_t)p * a.n + i0));
+#endif
+  if constexpr (QX_SPEC_FLOOR && std::is_same<V, S1>::value) hot_substeps_spec(c, e0, a, av0, i0);
+  else hot_substeps<V>(c, e0, e1, av0, av1, i0, i1);
   hot_epilogue<REF>(e0, c, a, i0, av0);
   if (has1) hot_epilogue<REF>(e1, c, a, i1, av1);
 }
@@ -1108,6 +1219,16 @@ static int launch_hot(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   a.paired_reset = h->paired_reset;
   if (a.merged) a.queue = h->queue;
   cudaError_t e;
+#ifdef QX_EXTRA_SHAPES
+  if (h->hot_lanes == 4 && h->hot_shape >= 6) {
+    switch (h->hot_shape) {
+      case 6: e = launch_hot_one<6, qx::S1>(h, a, s); break;
+      case 7: e = launch_hot_one<7, qx::S1>(h, a, s); break;
+      case 8: e = launch_hot_one<8, qx::S1>(h, a, s); break;
+      default: e = launch_hot_one<9, qx::S1>(h, a, s); break;
+    }
+  } else
+#endif
   if (h->hot_lanes == 2) e = launch_hot_shape<qx::P2<true>>(h, a, s);
   else if (h->hot_lanes == 4) e = launch_hot_shape<qx::S1>(h, a, s);
   else e = launch_hot_shape<float>(h, a, s);

@@ -589,7 +589,12 @@ QX_DI void control_update_s(CoreS& e, const DevConfig& c, const f2 spxy, const f
   apwm[1] = vmul(f2{pwm[2], pwm[3]}, c.lag_alpha);
 }
 
-QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], const f2 nz[2], const bool last) {
+// FLOOR = false: the speculative variant for an env that is not resting on the floor and is expected to stay clear of it --
+// the floor stand-in (~24 predicated instructions per sub-step, issued by every warp) is replaced by one FMNMX that tracks the
+// lowest pz; the caller re-runs the step with FLOOR = true when that dips below floor_z.  Until it does the two variants go
+// through the same operations, so a step that passes the check is bitwise what FLOOR = true computes.
+template <bool FLOOR = true>
+QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], const f2 nz[2], const bool last, float& minz) {
   // motors: first-order lag, multiplicative noise, thrust and torques
   f2 t01 = vfma(e.thr01, c.one_m_alpha, apwm[0]), t23 = vfma(e.thr23, c.one_m_alpha, apwm[1]);
   t01 = vfma(nz[0], t01, t01); t23 = vfma(nz[1], t23, t23);
@@ -614,7 +619,7 @@ QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], con
   const float fby = __fmul_rn(vabsmul(e.svb[1], c.ndrag_c), e.svb[1]);
   const float fbz = fmaf(vabsmul(e.svb[2], c.ndrag_c), e.svb[2], fz);
   {
-    const float dq = e.contact ? 0.f : c.ndrag_pqr;  // no angular drag while resting on the floor
+    const float dq = (FLOOR && e.contact) ? 0.f : c.ndrag_pqr;  // no angular drag while resting on the floor
     tx = fmaf(vabsmul(e.swbxy.x, dq), e.swbxy.x, tx);
     ty = fmaf(vabsmul(e.swbxy.y, dq), e.swbxy.y, ty);
     tz = fmaf(vabsmul(e.swbz, dq), e.swbz, tz);
@@ -674,16 +679,20 @@ QX_DI void physics_substep_s(CoreS& e, const DevConfig& c, const f2 apwm[2], con
     e.qxy = vmul(nxy, inv); e.qzw = vmul(nzw, inv);
   }
   // floor stand-in (cold)
-  const bool below = e.pz < c.floor_z;
-  if (below) {  // if-converted by ptxas (~24 predicated instructions per sub-step); a VOTE + uniform branch around it measured 2 % slower
-    e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vxy = f2{0.f, 0.f};
-    const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
-    const float a20 = __fmul_rn(__fsub_rn(__fmul_rn(X, Z), __fmul_rn(W, Y)), 2.f), a21 = __fmul_rn(fmaf(Y, Z, __fmul_rn(W, X)), 2.f);
-    const float a22 = __fsub_rn(1.f, __fmul_rn(fmaf(X, X, __fmul_rn(Y, Y)), 2.f));
-    const float wzw = fmaf(a22, e.wz, fmaf(a21, e.wxy.y, __fmul_rn(a20, e.wxy.x)));  // world yaw rate survives
-    e.wxy = f2{__fmul_rn(a20, wzw), __fmul_rn(a21, wzw)}; e.wz = __fmul_rn(a22, wzw);
+  if constexpr (FLOOR) {
+    const bool below = e.pz < c.floor_z;
+    if (below) {  // if-converted by ptxas (~24 predicated instructions per sub-step); a VOTE + uniform branch around it measured 2 % slower
+      e.pz = c.floor_z; e.vz = fmaxf(e.vz, 0.f); e.vxy = f2{0.f, 0.f};
+      const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
+      const float a20 = __fmul_rn(__fsub_rn(__fmul_rn(X, Z), __fmul_rn(W, Y)), 2.f), a21 = __fmul_rn(fmaf(Y, Z, __fmul_rn(W, X)), 2.f);
+      const float a22 = __fsub_rn(1.f, __fmul_rn(fmaf(X, X, __fmul_rn(Y, Y)), 2.f));
+      const float wzw = fmaf(a22, e.wz, fmaf(a21, e.wxy.y, __fmul_rn(a20, e.wxy.x)));  // world yaw rate survives
+      e.wxy = f2{__fmul_rn(a20, wzw), __fmul_rn(a21, wzw)}; e.wz = __fmul_rn(a22, wzw);
+    }
+    e.contact = below;
+  } else {
+    minz = fminf(minz, e.pz);  // pz < floor_z in any sub-step <=> min pz < floor_z (a NaN pz fails both tests alike)
   }
-  e.contact = below;
   if (!c.state_stale) {
     const float X = e.qxy.x, Y = e.qxy.y, Z = e.qzw.x, W = e.qzw.y;
     const float X2 = X + X, Y2 = Y + Y, Z2 = Z + Z;

@@ -42,19 +42,34 @@ def _stream(dev):
 class ActorCritic(nn.Module):
     """SB3 ``MlpPolicy`` with ``net_arch=[128, 128]`` (train_hover.py:57): separate
     tanh MLPs for the actor and the critic, state-independent ``log_std``,
-    orthogonal init (gain sqrt 2; 0.01 on the action head; 1 on the value head)."""
+    orthogonal init (gain sqrt 2; 0.01 on the action head; 1 on the value head).
 
-    def __init__(self, obs_dim: int = 20, act_dim: int = 4, log_std_init: float = 0.0):
+    ``hidden`` < 128 (SB3's default ``net_arch=[64, 64]``, what the yaw config of SURVEY 8d C3 would train) is held as an
+    exact embedding in the 128-wide layers the kernels are tiled for: the extra rows / columns and biases are zero, so the
+    extra units output tanh(0) = 0, receive a zero back-propagated signal (their outgoing weights are zero) and a zero weight
+    gradient (their activations are zero) -- Adam never moves them and the global gradient norm does not see them.  Forward,
+    gradients and the trajectory of training are those of the narrow network (``tests/test_gpu_update.py``)."""
+
+    def __init__(self, obs_dim: int = 20, act_dim: int = 4, log_std_init: float = 0.0, hidden: int = HID):
         super().__init__()
-        assert obs_dim <= IN_PAD and act_dim <= 4
-        self.obs_dim, self.act_dim = obs_dim, act_dim
+        assert obs_dim <= IN_PAD and act_dim <= 4 and 0 < hidden <= HID
+        self.obs_dim, self.act_dim, self.hidden = obs_dim, act_dim, hidden
         self.pi1, self.pi2, self.mu = nn.Linear(obs_dim, HID), nn.Linear(HID, HID), nn.Linear(HID, act_dim)
         self.vf1, self.vf2, self.v = nn.Linear(obs_dim, HID), nn.Linear(HID, HID), nn.Linear(HID, 1)
         self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
-        for lin, gain in ((self.pi1, math.sqrt(2)), (self.pi2, math.sqrt(2)), (self.vf1, math.sqrt(2)), (self.vf2, math.sqrt(2)),
-                          (self.mu, 0.01), (self.v, 1.0)):
-            nn.init.orthogonal_(lin.weight, gain=gain)
+        h = hidden
+        for lin, gain, rows, cols in ((self.pi1, math.sqrt(2), h, obs_dim), (self.pi2, math.sqrt(2), h, h), (self.vf1, math.sqrt(2), h, obs_dim),
+                                      (self.vf2, math.sqrt(2), h, h), (self.mu, 0.01, act_dim, h), (self.v, 1.0, 1, h)):
+            w = torch.empty(rows, cols)
+            nn.init.orthogonal_(w, gain=gain)
+            with torch.no_grad():
+                lin.weight.zero_()
+                lin.weight[:rows, :cols].copy_(w)
             nn.init.zeros_(lin.bias)
+
+    def num_effective_params(self) -> int:
+        h, od, ad = self.hidden, self.obs_dim, self.act_dim
+        return 2 * (od * h + h + h * h + h) + (h * ad + ad) + (h + 1) + ad
 
     def forward(self, obs: torch.Tensor):
         hp = torch.tanh(self.pi2(torch.tanh(self.pi1(obs))))
@@ -83,10 +98,14 @@ def export_sb3_state_dict(model: "ActorCritic") -> dict:
     counterpart of `model.save` in train_hover.py:26,62 for users who play the policy back with SB3
     (test_hover.py:8-21)."""
     sd = {"log_std": model.log_std.detach().cpu().clone()}
+    h = getattr(model, "hidden", HID)
     for sb3, mine in SB3_KEYS.items():
         lin = getattr(model, mine)
-        sd[f"{sb3}.weight"] = lin.weight.detach().cpu().clone()
-        sd[f"{sb3}.bias"] = lin.bias.detach().cpu().clone()
+        w, b = lin.weight.detach().cpu(), lin.bias.detach().cpu()
+        rows = h if w.shape[0] == HID else w.shape[0]  # a narrow net_arch lives in the top-left block of the 128-wide layers
+        cols = h if w.shape[1] == HID else w.shape[1]
+        sd[f"{sb3}.weight"] = w[:rows, :cols].clone()
+        sd[f"{sb3}.bias"] = b[:rows].clone()
     return sd
 
 
@@ -94,8 +113,10 @@ def import_sb3_state_dict(model: "ActorCritic", sd: dict) -> None:
     with torch.no_grad():
         model.log_std.copy_(sd["log_std"])
         for sb3, mine in SB3_KEYS.items():
-            getattr(model, mine).weight.copy_(sd[f"{sb3}.weight"])
-            getattr(model, mine).bias.copy_(sd[f"{sb3}.bias"])
+            lin, w, b = getattr(model, mine), sd[f"{sb3}.weight"], sd[f"{sb3}.bias"]
+            lin.weight.zero_(); lin.bias.zero_()
+            lin.weight[:w.shape[0], :w.shape[1]].copy_(w)
+            lin.bias[:b.shape[0]].copy_(b)
 
 
 def export_vecnormalize(obs_stats: "RunningStats", ret_stats: "RunningStats", cfg: "PPOConfig") -> dict:
@@ -127,7 +148,7 @@ def export_sb3_zip(model: "ActorCritic", path: str, vecnormalize: dict | None = 
 
     hyper = dict(hyper or {})
     data = {"policy_class": "stable_baselines3.common.policies.ActorCriticPolicy", "algorithm": "PPO",
-            "policy_kwargs": {"net_arch": [HID, HID], "log_std_init": float(hyper.pop("log_std_init", 0.0)), "activation_fn": "torch.nn.Tanh"},
+            "policy_kwargs": {"net_arch": [getattr(model, "hidden", HID)] * 2, "log_std_init": float(hyper.pop("log_std_init", 0.0)), "activation_fn": "torch.nn.Tanh"},
             "observation_space": {"type": "Box", "shape": [model.obs_dim], "low": "-inf", "high": "inf", "dtype": "float64"},  # hover.py:67-70
             "action_space": {"type": "Box", "shape": [model.act_dim], "low": -1.0, "high": 1.0, "dtype": "float64"},           # hover.py:59-61
             "learning_rate": 3e-4, "n_steps": 2048, "batch_size": 64, "gamma": 0.99, "gae_lambda": 0.95, "clip_range": 0.2, "ent_coef": 0.0,
@@ -305,6 +326,7 @@ class PPOConfig:
     log_std_min_final: float | None = None  # ... released linearly to this value between the iterations log_std_min_iters = (start, end):
     log_std_min_iters: tuple = (0, 0)       # explore at a guaranteed noise level first, then let the policy narrow (0, 0 = constant floor)
     fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
+    net_arch: int = HID  # hidden width of both MLPs: 128 = train_hover.py:57, 64 = SB3's default; < 128 runs zero-padded (ActorCritic)
 
 
 class RolloutEngine:
@@ -539,7 +561,8 @@ class PPOTrainer:
         if cfg.tf32_update:
             torch.backends.cuda.matmul.allow_tf32 = True
         torch.manual_seed(cfg.seed)  # identical initial weights on every rank
-        self.model = (ActorCritic(log_std_init=cfg.log_std_init) if task == 0 else ActorCritic(12, 1, log_std_init=cfg.log_std_init)).to(dev)
+        self.model = (ActorCritic(log_std_init=cfg.log_std_init, hidden=cfg.net_arch) if task == 0
+                      else ActorCritic(12, 1, log_std_init=cfg.log_std_init, hidden=cfg.net_arch)).to(dev)
         self.packed = PackedPolicy(self.model, dev)
         from ._lib import default_config
 

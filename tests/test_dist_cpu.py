@@ -90,6 +90,44 @@ def test_reference_arm_rank_handling():
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
+def test_narrow_net_arch_is_an_exact_embedding():
+    """net_arch=[64, 64] (SB3's default) is held zero-padded in the 128-wide layers the kernels are tiled for: the
+    forward pass and the gradients are those of a genuine 64-wide network, the padded entries get exactly zero gradient, and the
+    SB3 export has the narrow shapes."""
+    sys.path.insert(0, ROOT)
+    from fpv_drone_rl_agent_b200 import ppo
+
+    torch.manual_seed(11)
+    m = ppo.ActorCritic(12, 1, log_std_init=-0.5, hidden=64)
+    sd = ppo.export_sb3_state_dict(m)
+    assert sd["mlp_extractor.policy_net.0.weight"].shape == (64, 12) and sd["mlp_extractor.policy_net.2.weight"].shape == (64, 64)
+    assert sd["action_net.weight"].shape == (1, 64) and sd["value_net.weight"].shape == (1, 64)
+    assert sum(v.numel() for v in sd.values()) == m.num_effective_params() == 2 * (12 * 64 + 64 + 64 * 64 + 64) + 64 + 1 + 64 + 1 + 1
+    # a genuine 64-wide torch network with the exported weights
+    pi = torch.nn.Sequential(torch.nn.Linear(12, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1))
+    vf = torch.nn.Sequential(torch.nn.Linear(12, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1))
+    with torch.no_grad():
+        for net, names in ((pi, ("mlp_extractor.policy_net.0", "mlp_extractor.policy_net.2", "action_net")),
+                           (vf, ("mlp_extractor.value_net.0", "mlp_extractor.value_net.2", "value_net"))):
+            for k, name in zip((0, 2, 4), names):
+                net[k].weight.copy_(sd[name + ".weight"]); net[k].bias.copy_(sd[name + ".bias"])
+    x, a = torch.randn(64, 12), torch.randn(64, 1)
+    mean, value = m(x)
+    assert torch.allclose(mean, pi(x), atol=1e-6) and torch.allclose(value, vf(x).squeeze(-1), atol=1e-6)
+    v, logp, _ = m.evaluate_actions(x, a)
+    (logp.mean() + (v ** 2).mean()).backward()
+    z = (a - pi(x)) / m.log_std.detach().exp()
+    ((-0.5 * z * z - m.log_std.detach() - 0.5 * np.log(2 * np.pi)).sum(-1).mean() + (vf(x).squeeze(-1) ** 2).mean()).backward()
+    assert torch.allclose(m.pi2.weight.grad[:64, :64], pi[2].weight.grad, atol=1e-6) and torch.allclose(m.vf1.weight.grad[:64], vf[0].weight.grad, atol=1e-6)
+    for lin in (m.pi1, m.pi2, m.vf1, m.vf2):
+        assert float(lin.weight.grad[64:].abs().max()) == 0.0 and float(lin.bias.grad[64:].abs().max()) == 0.0
+    for lin in (m.pi2, m.vf2, m.mu, m.v):
+        assert float(lin.weight.grad[:, 64:].abs().max()) == 0.0
+    m2 = ppo.ActorCritic(12, 1, hidden=64)
+    ppo.import_sb3_state_dict(m2, sd)
+    assert torch.equal(m2(x)[0], mean.detach()) and m2.pi2.weight[64:].abs().max() == 0
+
+
 def test_sb3_compatible_export_roundtrip():
     """train_hover.py:26-27,62-63 save an SB3 zip + VecNormalize pkl; the export uses SB3's parameter names."""
     sys.path.insert(0, ROOT)

@@ -265,6 +265,40 @@ def test_graph_replay_equals_eager_and_training_learns(pkg):
     tr.sim.close()
 
 
+def test_narrow_net_arch_trains_inside_the_padding(pkg):
+    """net_arch = 64 (SB3's default MlpPolicy; ppo.ActorCritic holds it zero-padded in the 128-wide kernel layout): after real
+    optimiser steps of the hand-written update on the yaw task the padded rows / columns are still exactly zero -- their
+    activations, back-propagated signals and Adam moments never leave zero -- while the 64-wide block has moved, and the
+    rollout's tcgen05 forward equals the fp32 torch forward of the exported 64-wide weights."""
+    from fpv_drone_rl_agent_b200 import ppo
+
+    cfg = ppo.PPOConfig(n_envs=4096, n_steps=32, seed=2, batch_size=16384, n_epochs=2, net_arch=64)
+    tr = ppo.PPOTrainer(cfg, device="cuda:0", task=1)
+    w0 = tr.model.pi2.weight.detach().clone()
+    for _ in range(2):
+        st = tr.learn_iteration()
+    torch.cuda.synchronize()
+    assert np.isfinite(list(st.values())).all()
+    m = tr.model
+    for lin in (m.pi1, m.pi2, m.vf1, m.vf2):
+        assert float(lin.weight[64:].abs().max()) == 0.0 and float(lin.bias[64:].abs().max()) == 0.0
+    for lin in (m.pi2, m.vf2, m.mu, m.v):
+        assert float(lin.weight[:, 64:].abs().max()) == 0.0
+    assert float((m.pi2.weight[:64, :64] - w0[:64, :64]).abs().max()) > 1e-4, "the narrow block did not train"
+    assert float(tr.fused.exp_avg_sq.abs().sum()) > 0
+    sd = ppo.export_sb3_state_dict(m)
+    assert sd["mlp_extractor.policy_net.2.weight"].shape == (64, 64)
+    ro = tr.rollout
+    ro.collect()
+    torch.cuda.synchronize()
+    x = ro.obs.view(-1, 12)[:4096]
+    h = torch.tanh(x @ sd["mlp_extractor.value_net.0.weight"].to(x).T + sd["mlp_extractor.value_net.0.bias"].to(x))
+    h = torch.tanh(h @ sd["mlp_extractor.value_net.2.weight"].to(x).T + sd["mlp_extractor.value_net.2.bias"].to(x))
+    v = (h @ sd["value_net.weight"].to(x).T + sd["value_net.bias"].to(x)).squeeze(-1)
+    assert float((v - ro.values.view(-1)[:4096]).abs().max()) < 5e-2
+    tr.sim.close()
+
+
 @pytest.mark.parametrize("fused", [True, False])
 def test_checkpoint_resume(pkg, fused, tmp_path):
     """PPOTrainer.save / load: a run resumed from a checkpoint continues like the uninterrupted one (policy, optimiser
