@@ -123,7 +123,21 @@ struct FwdArgs {
   const uint8_t* boot_tr;
   float boot_gamma;
   int32_t grid;                   // CTAs of this launch (= gridDim.x), as a parameter so that the tile walk needs no register for it
+  // fused VecNormalize update (ppo_policy_forward_stats): the launch first merges the raw rows of `obs` into the running
+  // statistics {mean, var, count} (fp64) and refreshes the fp32 (mean, inv_std) it then normalises with -- see the kernel
+  double* fs_stats;               // null = off (obs_mean / obs_inv_std are read as given)
+  double* fs_scratch;             // per-CTA partial sums + ticket / flag words (ppo_running_stats_scratch_bytes)
+  float fs_eps;
+  float* fs_mean_out;             // == obs_mean, writable
+  float* fs_inv_out;              // == obs_inv_std, writable
 };
+
+// (defined with the K4 kernels below)
+constexpr int kStatMaxDim = 32;
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket);
+__device__ __forceinline__ void welford_merge_block(const double* part, int nblocks, int64_t n, int dim, double* __restrict__ stats, float eps,
+                                                    float* __restrict__ mean_f32, float* __restrict__ inv_std_f32);
+__device__ __forceinline__ unsigned int* stat_words(double* scratch);
 
 __device__ __forceinline__ uint32_t tanh_pack_bf16x2(float lo, float hi) {
 #ifdef PPO_TANH_BF16X2
@@ -212,6 +226,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   K2_TRACE(127);
   // gather mode (time-limit bootstrap): most steps have no truncated env at all -- leave before staging 88 KB of weights
   if (a.gather_idx && (int64_t)blockIdx.x * 128 >= (int64_t)*a.gather_count) return;  // (slot-major tile order: this CTA's first tile is blockIdx.x)
+  // ---- fused VecNormalize update, first half: this CTA's share of the rows -> fp64 column sums (lane = column, the 24 warps
+  // stride over the rows, 16 row loads in flight per lane), combined through the still unused slot buffers, left in the scratch
+  // buffer; the CTA that arrives last merges all of them into the running statistics (RunningMeanStd.update_from_moments),
+  // refreshes the fp32 (mean, inv_std) and raises the flag every CTA waits for after it has staged its weights -- the merge and
+  // the other CTAs' staging overlap, and the separate statistics launch (12 us at 131 072 rows, a latency chain) is gone.
+  // All CTAs of the launch are resident together (grid <= SM count, one CTA per SM), so the wait cannot starve anyone.
+  if (a.fs_stats) {
+    double* sh = reinterpret_cast<double*>(smem + kSmSlot);
+    const int w = (int)(tid >> 5);
+    const int64_t warp_id = (int64_t)blockIdx.x * (kFwdThreads / 32) + w, n_warps = (int64_t)gridDim.x * (kFwdThreads / 32);
+    double s = 0.0, q = 0.0;
+    if ((int)lane < obs_dim) {
+      for (int64_t i = warp_id; i < a.n; i += 16 * n_warps) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int64_t r = i + k * n_warps;
+          v[k] = r < a.n ? __ldg(a.obs + r * a.obs_stride + lane) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          s += (double)v[k] + (double)v[k + 1];
+          q += (double)v[k] * v[k] + (double)v[k + 1] * v[k + 1];
+        }
+      }
+    }
+    sh[w * 2 * kStatMaxDim + lane] = s; sh[w * 2 * kStatMaxDim + kStatMaxDim + lane] = q;
+    __syncthreads();
+    if (tid < 2 * kStatMaxDim) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < kFwdThreads / 32; ++k) acc += sh[k * 2 * kStatMaxDim + tid];
+      a.fs_scratch[(size_t)blockIdx.x * 2 * kStatMaxDim + tid] = acc;
+    }
+    unsigned int* words = stat_words(a.fs_scratch);  // [0] ticket, [2] flag, [4] CTAs past the flag
+    if (last_block_done(words)) {
+      welford_merge_block(a.fs_scratch, (int)gridDim.x, a.n, obs_dim, a.fs_stats, a.fs_eps, a.fs_mean_out, a.fs_inv_out);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(words + 2), "r"(1u) : "memory");
+    }
+    __syncthreads();  // the slot buffers are free again
+  }
   // ---- one-time: weights, biases, normalisation constants -> smem; TMEM; barriers
   stage_weight(smem + kSmW1, (const __nv_bfloat16*)a.p.w1, 2 * kHid, kIn, tid, kFwdThreads);
   stage_weight(smem + kSmW2p, (const __nv_bfloat16*)a.p.w2p, kHid, kHid, tid, kFwdThreads);
@@ -225,9 +282,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
   float* sInv = sMean + kIn;
   if (tid < 2 * kHid) { sB1[tid] = a.p.b1[tid]; sB2[tid] = a.p.b2[tid]; }
   if (tid < kHead) sB3[tid] = a.p.b3[tid];
+  if (a.fs_stats) {  // fused statistics, second half: wait for the merged (mean, inv_std); the last CTA through re-arms the words
+    unsigned int* words = stat_words(a.fs_scratch);
+    if (tid == 0) {
+      unsigned int v, ns = 32u;
+      while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(words + 2) : "memory");
+        if (v != 0u) break;
+        __nanosleep(ns);
+        if (ns < 256u) ns += ns;
+      }
+      if (atomicAdd(words + 4, 1u) == gridDim.x - 1) { words[4] = 0u; __threadfence(); words[2] = 0u; }
+    }
+    __syncthreads();
+  }
   if (tid < kIn) {
-    sMean[tid] = (a.obs_mean && (int)tid < obs_dim) ? a.obs_mean[tid] : 0.f;
-    sInv[tid] = (a.obs_inv_std && (int)tid < obs_dim) ? a.obs_inv_std[tid] : 1.f;
+    sMean[tid] = (a.obs_mean && (int)tid < obs_dim) ? __ldcg(a.obs_mean + tid) : 0.f;
+    sInv[tid] = (a.obs_inv_std && (int)tid < obs_dim) ? __ldcg(a.obs_inv_std + tid) : 1.f;
   }
   if (tid < 32) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
@@ -548,8 +619,10 @@ __global__ void __launch_bounds__(1024) gae_warpscan_kernel(const float* __restr
 // and does the parallel-Welford merge into {mean[dim], var[dim], count}, and
 // refreshes the fp32 mean / inv_std the policy kernel reads.
 // ---------------------------------------------------------------------------
-constexpr int kStatBlocks = 148, kStatThreads = 1024, kRetThreads = 1024, kStatMaxDim = 32;  // one wave of full-SM blocks
+constexpr int kStatBlocks = 148, kStatThreads = 1024, kRetThreads = 1024;  // one wave of full-SM blocks (kStatMaxDim = 32: above)
 constexpr size_t kStatTicketOffset = (size_t)kStatBlocks * 2 * kStatMaxDim;  // in doubles
+// the 16 32-bit words behind the partial sums: [0] last-block ticket; the fused policy launch also uses [2] and [4]
+__device__ __forceinline__ unsigned int* stat_words(double* scratch) { return reinterpret_cast<unsigned int*>(scratch + kStatTicketOffset); }
 
 // true in exactly one block per launch: the last one to arrive; it re-arms the ticket for the next launch / graph replay
 __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
@@ -726,6 +799,21 @@ extern "C" int ppo_policy_forward(const PpoPolicy* p, const float* obs, int64_t 
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.row0 = row0; a.step = step; a.step_base = step_base_dev;
   a.deterministic = deterministic; a.actions = actions; a.env_actions = env_actions; a.values = values; a.log_probs = log_probs;
   a.obs_norm_out = obs_norm_out;
+  return launch_forward(a, n, stream);
+}
+
+extern "C" int ppo_policy_forward_stats(const PpoPolicy* p, const float* obs, int64_t obs_stride, int64_t n, double* obs_stats, float eps,
+                                        void* stats_scratch, float* obs_mean, float* obs_inv_std, float obs_clip, uint64_t seed, uint64_t row0,
+                                        uint64_t step, const uint64_t* step_base_dev, int32_t deterministic, float* actions, float* env_actions,
+                                        float* values, float* log_probs, float* obs_norm_out, void* stream) {
+  if (!policy_ok(p) || !obs || n <= 0 || obs_stride < p->obs_dim || !obs_stats || !stats_scratch || !obs_mean || !obs_inv_std)
+    return pfail(QX_EINVAL, "ppo_policy_forward_stats: bad arguments");
+  ppo::FwdArgs a{};
+  a.p = *p; a.obs = obs; a.obs_stride = obs_stride; a.n = n; a.obs_mean = obs_mean; a.obs_inv_std = obs_inv_std; a.obs_clip = obs_clip;
+  a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.row0 = row0; a.step = step; a.step_base = step_base_dev;
+  a.deterministic = deterministic; a.actions = actions; a.env_actions = env_actions; a.values = values; a.log_probs = log_probs;
+  a.obs_norm_out = obs_norm_out;
+  a.fs_stats = obs_stats; a.fs_scratch = (double*)stats_scratch; a.fs_eps = eps; a.fs_mean_out = obs_mean; a.fs_inv_out = obs_inv_std;
   return launch_forward(a, n, stream);
 }
 

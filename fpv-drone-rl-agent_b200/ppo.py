@@ -256,11 +256,21 @@ class RunningStats:
 
 def policy_forward(pol: PackedPolicy, obs: torch.Tensor, *, obs_stats: RunningStats | None = None, obs_clip: float = 10.0, seed: int = 0,
                    row0: int = 0, step: int = 0, step_base: torch.Tensor | None = None, deterministic: bool = False,
-                   actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None, norm: tuple | None = None) -> None:
-    """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward).  norm = (mean, inv_std) overrides obs_stats' buffers."""
+                   actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None, norm: tuple | None = None,
+                   update_stats: bool = False) -> None:
+    """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward).  norm = (mean, inv_std) overrides obs_stats' buffers.
+    update_stats: the same launch first merges `obs` into obs_stats and refreshes (mean, inv_std) -- VecNormalize's
+    ``obs_rms.update`` + ``normalize_obs`` of one env step in one kernel (ppo_policy_forward_stats)."""
     n = obs.shape[0]
     assert obs.dtype == torch.float32 and obs.stride(1) == 1
     mean, inv_std = norm if norm is not None else ((obs_stats.mean, obs_stats.inv_std) if obs_stats else (None, None))
+    if update_stats:
+        assert obs_stats is not None and mean is not None
+        check(_lib.lib().ppo_policy_forward_stats(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(obs_stats.stats), obs_stats.eps,
+                                                  _p(obs_stats.scratch), _p(mean), _p(inv_std), obs_clip, seed, row0, step, _p(step_base),
+                                                  int(deterministic), _p(actions), _p(env_actions), _p(values), _p(log_probs), _p(obs_norm),
+                                                  _stream(pol.device)))
+        return
     check(_lib.lib().ppo_policy_forward(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(mean),
                                         _p(inv_std), obs_clip, seed, row0, step, _p(step_base),
                                         int(deterministic), _p(actions), _p(env_actions), _p(values), _p(log_probs), _p(obs_norm),
@@ -326,6 +336,9 @@ class PPOConfig:
     log_std_min_final: float | None = None  # ... released linearly to this value between the iterations log_std_min_iters = (start, end):
     log_std_min_iters: tuple = (0, 0)       # explore at a guaranteed noise level first, then let the policy narrow (0, 0 = constant floor)
     fused_update: bool = True  # the hand-written update kernels (ppo_update_*); False: torch autograd + torch.optim.Adam (reference)
+    fuse_obs_stats: bool = False  # VecNormalize's obs statistics update inside the policy-forward launch (ppo_policy_forward_stats): one launch
+                                  # fewer per env step, but measured SLOWER inside the two-branch rollout graph (3.30 vs 3.16 ms per 131 072 x 32
+                                  # rollout): the in-kernel wait for the last CTA makes every CTA wait for the SMs the side branch still holds
     net_arch: int = HID  # hidden width of both MLPs: 128 = train_hover.py:57, 64 = SB3's default; < 128 runs zero-padded (ActorCritic)
 
 
@@ -385,11 +398,12 @@ class RolloutEngine:
         cfg, sim, L, s = self.cfg, self.sim, self.lib, _stream(self.device)
         stats = self.obs_stats if cfg.norm_obs else None
         norm = (self._snap_mean[t & 1], self._snap_inv[t & 1]) if cfg.norm_obs else None
-        if cfg.norm_obs:
+        fuse = cfg.norm_obs and cfg.fuse_obs_stats
+        if cfg.norm_obs and not fuse:
             self.obs_stats.update(self.cur_obs, out=norm)
         policy_forward(self.pol, self.cur_obs, obs_stats=stats, norm=norm, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
                        step_base=self.step_base, actions=self.actions[t], env_actions=self.env_actions, values=self.values[t],
-                       log_probs=self.log_probs[t], obs_norm=self.obs[t])
+                       log_probs=self.log_probs[t], obs_norm=self.obs[t], update_stats=fuse)
         main = torch.cuda.current_stream(self.device)
         if t > 0:
             main.wait_stream(self._side)  # join the side branch of step t - 1 (the rollout ends with a join, so there is none at t = 0)
@@ -441,7 +455,7 @@ class RolloutEngine:
 
     @property
     def launches_per_rollout(self) -> int:
-        per_step = (1 if self.cfg.norm_obs else 0) + 1 + 2 + 1 + 2  # obs stats, forward, env step/reset, bootstrap, reward path
+        per_step = (1 if self.cfg.norm_obs and not self.cfg.fuse_obs_stats else 0) + 1 + 2 + 1 + 2  # obs stats, forward, env step/reset, bootstrap, reward path
         return self.T * per_step + 3
 
 

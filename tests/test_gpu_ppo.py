@@ -186,6 +186,36 @@ def test_running_stats_and_reward_normalisation(env):
         assert np.array_equal(dn.cpu().numpy(), te | tr)
 
 
+@pytest.mark.parametrize("n", [1000, 131072, 200_001])
+def test_fused_statistics_forward_equals_the_two_launches(env, n):
+    """ppo_policy_forward_stats (VecNormalize's obs_rms.update + normalize_obs + the policy forward in one launch) against
+    ppo_running_stats_update followed by ppo_policy_forward: the running statistics agree to fp64 rounding (the per-CTA partial
+    sums are grouped differently), the fp32 (mean, inv_std) to one ulp, and the outputs to what one ulp of the normalisation
+    moves them.  Three successive batches through the same buffers check that the in-kernel ticket / flag words re-arm."""
+    pkg, _lib, ppo = env
+    m = _model(ppo, seed=3)
+    pol = ppo.PackedPolicy(m, "cuda:0")
+    a_stats, b_stats = ppo.RunningStats(20, "cuda:0"), ppo.RunningStats(20, "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(n)
+    for rep in range(3):
+        x = torch.randn(n, 20, device="cuda", generator=g) * (1.0 + rep) + torch.linspace(-2, 2, 20, device="cuda")
+        out_a = [torch.zeros(n, 4, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, 20, device="cuda")]
+        out_b = [torch.zeros_like(t) for t in out_a]
+        a_stats.update(x)
+        ppo.policy_forward(pol, x, obs_stats=a_stats, obs_clip=10.0, seed=5, step=rep, actions=out_a[0], values=out_a[1], log_probs=out_a[2], obs_norm=out_a[3])
+        ppo.policy_forward(pol, x, obs_stats=b_stats, obs_clip=10.0, seed=5, step=rep, actions=out_b[0], values=out_b[1], log_probs=out_b[2], obs_norm=out_b[3],
+                           update_stats=True)
+        torch.cuda.synchronize()
+        assert torch.allclose(a_stats.stats, b_stats.stats, rtol=1e-12, atol=1e-12), (a_stats.stats - b_stats.stats).abs().max()
+        assert float(b_stats.stats[40]) == pytest.approx(1e-4 + (rep + 1) * n)
+        assert torch.allclose(a_stats.mean, b_stats.mean, rtol=3e-7, atol=1e-7) and torch.allclose(a_stats.inv_std, b_stats.inv_std, rtol=3e-7)
+        assert (out_a[3] - out_b[3]).abs().max().item() < 1e-5
+        assert (out_a[1] - out_b[1]).abs().max().item() < 2e-2 and (out_a[0] - out_b[0]).abs().max().item() < 2e-2  # bf16 staging of a 1-ulp-different input
+        assert (out_a[1] - out_b[1]).abs().mean().item() < 1e-4
+    # numpy restatement of the merged moments
+    assert torch.isfinite(b_stats.stats).all()
+
+
 def test_time_limit_bootstrap(env):
     """Envs that hover into the 402-step limit get reward += gamma * V(terminal_obs) (SB3 collect_rollouts)."""
     pkg, _lib, ppo = env

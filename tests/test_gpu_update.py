@@ -278,7 +278,7 @@ def test_narrow_net_arch_trains_inside_the_padding(pkg):
     for _ in range(2):
         st = tr.learn_iteration()
     torch.cuda.synchronize()
-    assert np.isfinite(list(st.values())).all()
+    assert all(np.isfinite(st[k]) for k in ("pg", "vf", "kl", "clipfrac")), st  # (the episode means are NaN until a yaw episode has ended)
     m = tr.model
     for lin in (m.pi1, m.pi2, m.vf1, m.vf2):
         assert float(lin.weight[64:].abs().max()) == 0.0 and float(lin.bias[64:].abs().max()) == 0.0
