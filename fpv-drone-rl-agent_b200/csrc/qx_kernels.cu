@@ -877,6 +877,8 @@ struct QxHandle {
   int stream_stores;   // QX_STREAM_STORES: 0 plain stores, 1 evict-first for obs / reward / flags, 2 also for the state planes
   int merged;          // QX_MERGED: 1 (default) the hot kernel also drains the reset queue (one launch per step), 0 separate reset launch
   int sm_count;
+  int host_chunks;     // QX_HOST_CHUNKS: pieces the *_host calls cut a large batch into (the first one is halved again)
+  int host_one_d2h;    // QX_HOST_ONE_D2H: the small result arrays share the observation's D2H stream
   int hot_grid;        // blocks of one resident wave of the merged launch (SMs x blocks per SM from the occupancy calculator), 0 = not computed yet
   float4* state;
   qx::Stats* stats;
@@ -1065,6 +1067,9 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   h->hot_shape = env_int("QX_SHAPE", h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2);
   if (h->hot_shape < 0 || h->hot_shape >= qx::kHotShapes || h->hot_shape == 1 || h->hot_shape == 2) h->hot_shape = h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2;
   h->paired_reset = (h->hot_ok && (h->dev.n_sub_reset & 1) == 0 && cfg->spawn_throttle >= 0.f && cfg->pwm_idle >= 0.f && env_int("QX_PAIRED_RESET", 1)) ? 1 : 0;
+  h->host_chunks = env_int("QX_HOST_CHUNKS", 8);
+  if (h->host_chunks < 1 || h->host_chunks > 15) h->host_chunks = 8;
+  h->host_one_d2h = env_int("QX_HOST_ONE_D2H", 0);
   h->merged = env_int("QX_MERGED", 0);  // measured: saves the second launch (~5 us) when nothing finishes, loses ~13 us when the queue is not empty
   h->sm_count = prop.multiProcessorCount;
   h->stream_stores = env_int("QX_STREAM_STORES", 0);
@@ -1417,8 +1422,9 @@ static int step_host_impl(QxHandle* h, const float* actions_host, void* obs_host
   const bool own_flags = terminal_obs_host || (terminated_host && !p_te) || (truncated_host && !p_tr);
   // 8 chunks, the first cut in two again: the D2H engine -- what bounds the call -- idles until the first chunk has gone
   // through H2D and the kernels, so that chunk is kept small
-  const int chunks = n >= (1 << 17) ? 9 : 1;
-  const int64_t per = chunks == 1 ? n : ((n + 7) / 8 + 2 * qx::kBlock - 1) / (2 * qx::kBlock) * (2 * qx::kBlock);
+  const int nc = h->host_chunks;  // QX_HOST_CHUNKS (default 8, at most 15)
+  const int chunks = n >= (1 << 17) ? nc + 1 : 1;
+  const int64_t per = chunks == 1 ? n : ((n + nc - 1) / nc + 2 * qx::kBlock - 1) / (2 * qx::kBlock) * (2 * qx::kBlock);
   for (int k = 0; k < chunks; ++k) {
     const int64_t b = chunks == 1 ? 0 : (k == 0 ? 0 : (k == 1 ? per / 2 : (k - 1) * per));
     const int64_t want = chunks == 1 ? n : (k < 2 ? per / 2 : per);
@@ -1443,7 +1449,7 @@ static int step_host_impl(QxHandle* h, const float* actions_host, void* obs_host
     QX_CUDA(cudaStreamWaitEvent(h->d2h_stream, h->ev_k[k], 0));
     QX_CUDA(cudaStreamWaitEvent(h->d2h2_stream, h->ev_k[k], 0));
     if (dst_obs) QX_CUDA(cudaMemcpyAsync(dst_obs + b * od * osz, (const char*)h->d_obs + b * od * osz, osz * cnt * od, cudaMemcpyDeviceToHost, h->d2h_stream));
-    cudaStream_t s2 = h->d2h2_stream;
+    cudaStream_t s2 = h->host_one_d2h ? h->d2h_stream : h->d2h2_stream;
     if (dst_rew) QX_CUDA(cudaMemcpyAsync(dst_rew + b, h->d_rew + b, sizeof(float) * cnt, cudaMemcpyDeviceToHost, s2));
     if (own_flags) {
       QX_CUDA(cudaMemcpyAsync(h->h_flags + b, h->d_flags + b, cnt, cudaMemcpyDeviceToHost, s2));
