@@ -335,15 +335,19 @@ def main_ours(args):
     te = torch.zeros(E, dtype=torch.uint8, device=dev)
     tr = torch.zeros(E, dtype=torch.uint8, device=dev)
     sim.reset(obs)
-    for k in range(args.warmup):
-        sim.step(acts[k % 8], obs, rew, te, tr)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)  # (before the warm-up, not after it: a quarter of a second of idling lets the GPU leave its working clocks)
+    if world > 1:
+        dist.barrier()
+    for k in range(args.warmup):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+    torch.cuda.synchronize()
+    if os.environ.get("BENCH_IDLE_BEFORE_TIMING"):  # diagnostic: the round-1 / early round-2 order (idle gap between warm-up and timing)
         time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.lib().qx_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -450,6 +454,7 @@ def main_ours(args):
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
         }
         line["roofline"]["step_ms_first8_min"] = min(per[:8]) if len(per) >= 8 else None
+        line["roofline"]["step_ms_each"] = [round(x, 4) for x in per[:64]]
         if world == 1 and not args.no_small:
             line["hover_4096"] = small_config(pkg, dev)
         if world == 1 and not args.no_small:

@@ -785,6 +785,7 @@ template <bool REF, int SHAPE, class V, bool MERGED>
 __global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMinBlocks) quadx_step_hot_kernel(const __grid_constant__ DevConfig cparam,
                                                                                                                  const __grid_constant__ StepArgs a) {
   constexpr int kB = HotShape<SHAPE>::kBlock, kLanes = Lane<V>::N, kWarps = kB / 32, kTask = 32 * kLanes;
+  if constexpr (!MERGED) asm volatile("griddepcontrol.launch_dependents;");  // the reset-queue launch may be scheduled once the last wave has started
   DevConfig cref = cparam;
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
@@ -839,6 +840,9 @@ __global__ void __launch_bounds__(128, 4) quadx_reset_hot_kernel(const __grid_co
   DevConfig cref = cparam;
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
+  // launched as a programmatic dependent of the step launch (qx_step): the blocks are already on the SMs when the step grid
+  // retires and wait here for its memory; a no-op in a plain launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned int cnt = *reinterpret_cast<volatile unsigned int*>(&a.queue->count);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -877,6 +881,8 @@ struct QxHandle {
   int stream_stores;   // QX_STREAM_STORES: 0 plain stores, 1 evict-first for obs / reward / flags, 2 also for the state planes
   int merged;          // QX_MERGED: 1 (default) the hot kernel also drains the reset queue (one launch per step), 0 separate reset launch
   int sm_count;
+  int pdl;             // QX_PDL (default 1): qx_step launches the reset-queue kernel as a programmatic dependent of the step kernel
+  int pdl_armed;       // set by qx_step around qx_step_end
   int host_chunks;     // QX_HOST_CHUNKS: 0 (default) = the geometric piece schedule of the *_host calls, k > 0 = k equal pieces, the first halved again
   int host_one_d2h;    // QX_HOST_ONE_D2H: the small result arrays share the observation's D2H stream
   int hot_grid;        // blocks of one resident wave of the merged launch (SMs x blocks per SM from the occupancy calculator), 0 = not computed yet
@@ -1067,6 +1073,8 @@ extern "C" int qx_create(const QxConfig* cfg, int64_t n_envs, uint64_t seed, uin
   h->hot_shape = env_int("QX_SHAPE", h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2);
   if (h->hot_shape < 0 || h->hot_shape >= qx::kHotShapes || h->hot_shape == 1 || h->hot_shape == 2) h->hot_shape = h->hot_lanes != 2 ? kDefaultShape1 : kDefaultShape2;
   h->paired_reset = (h->hot_ok && (h->dev.n_sub_reset & 1) == 0 && cfg->spawn_throttle >= 0.f && cfg->pwm_idle >= 0.f && env_int("QX_PAIRED_RESET", 1)) ? 1 : 0;
+  h->pdl = env_int("QX_PDL", 1);
+  h->pdl_armed = 0;
   h->host_chunks = env_int("QX_HOST_CHUNKS", 0);
   if (h->host_chunks < -8 || h->host_chunks > 15 || h->host_chunks == -1) h->host_chunks = 0;
   h->host_one_d2h = env_int("QX_HOST_ONE_D2H", 0);
@@ -1257,7 +1265,16 @@ static int launch(QxHandle* h, int mode, qx::StepArgs a, cudaStream_t s) {
   if (mode == qx::MODE_RESET_QUEUE && use_hot(h) && h->paired_reset) {
     const unsigned blocks = (unsigned)((a.env_count + 127) / 128);
     const unsigned g = blocks < (unsigned)qx::kResetQueueBlocks ? blocks : (unsigned)qx::kResetQueueBlocks;
-    if (h->ref_constants) qx::quadx_reset_hot_kernel<true><<<g, 128, 0, s>>>(h->dev, a);
+    if (h->pdl && h->pdl_armed) {  // directly behind the step launch on the same stream (qx_step): programmatic dependent launch
+      cudaLaunchConfig_t lc{};
+      lc.gridDim = dim3(g); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 0; lc.stream = s;
+      cudaLaunchAttribute at{};
+      at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at.val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = &at; lc.numAttrs = 1;
+      QX_CUDA(h->ref_constants ? cudaLaunchKernelEx(&lc, qx::quadx_reset_hot_kernel<true>, h->dev, a)
+                               : cudaLaunchKernelEx(&lc, qx::quadx_reset_hot_kernel<false>, h->dev, a));
+    } else if (h->ref_constants) qx::quadx_reset_hot_kernel<true><<<g, 128, 0, s>>>(h->dev, a);
     else qx::quadx_reset_hot_kernel<false><<<g, 128, 0, s>>>(h->dev, a);
     ++g_launches;
     QX_CUDA(cudaGetLastError());
@@ -1332,7 +1349,10 @@ extern "C" int qx_step(QxHandle* h, const float* actions_dev, void* obs_dev, int
   }
   int rc = qx_step_begin(h, actions_dev, obs_dev, obs_dtype, obs_stride, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, stream);
   if (rc) return rc;
-  return qx_step_end(h, obs_dev, obs_dtype, obs_stride, stream);
+  h->pdl_armed = 1;  // nothing was enqueued between the two launches
+  rc = qx_step_end(h, obs_dev, obs_dtype, obs_stride, stream);
+  h->pdl_armed = 0;
+  return rc;
 }
 
 // debug hook (not in the public header): out_dev[0] = clock64 of one SM, out_dev[1] = globaltimer ns, enqueued on `stream`
