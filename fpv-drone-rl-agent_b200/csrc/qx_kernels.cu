@@ -586,16 +586,19 @@ QX_DI void hot_substeps(const DevConfig& c, Env& e0, Env& e1, const float4 av0, 
 #ifndef QX_DIAG
 #define QX_DIAG 0
 #endif
+#ifndef QX_RESET_SWP
+#define QX_RESET_SWP 0
+#endif
 // the paired sub-step loop: nsub sub-steps (even) towards a fixed setpoint, noise stream `stream`.  FLOOR = false is the
 // speculative loop without the floor stand-in (physics_substep_s); returns the lowest pz it saw (+inf with FLOOR = true).
-template <bool FLOOR = true>
+template <bool FLOOR = true, int SWP = QX_SWP>
 QX_DI float substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float spz, const float thrust, const int nsub, const uint32_t stream, const int64_t i0) {
   CoreS p;
   pack_core_s(p, e0);
   float minz = __int_as_float(0x7f800000);
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i0);
   const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i0) >> 32));
-#if QX_SWP == 0
+  if constexpr (SWP == 0) {
 #pragma unroll 1
   for (int j = 0; j < nsub; j += 2) {  // one Aviary.step(): rate PID, one Philox call, two physics sub-steps
     f2 apwm[2];
@@ -626,7 +629,7 @@ QX_DI float substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float s
 #endif
     physics_substep_s<FLOOR>(p, c, apwm, nz, j + 2 == nsub, minz);
   }
-#elif QX_SWP == 1
+  } else if constexpr (SWP == 1) {
   // software-pipelined noise: the Philox call of Aviary.step j + 1 is issued at the top of step j, where nothing depends on it,
   // so that its ~7 x 3 dependent integer operations fill the stalls of the control / physics chain instead of heading it
   uint4 b = make_uint4(0u, 0u, 0u, 0u);
@@ -643,7 +646,7 @@ QX_DI float substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float s
     if (c.noise) normal4_scaled_s(bc.z, bc.w, c.noise_k, nz);
     physics_substep_s<FLOOR>(p, c, apwm, nz, j + 2 == nsub, minz);
   }
-#else
+  } else {
   // ... and the Box-Muller transform with it: the 8 scaled normals of step j + 1 are ready before step j ends
   f2 na[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}}, nb[2] = {f2{0.f, 0.f}, f2{0.f, 0.f}};
   if (c.noise) {
@@ -664,7 +667,7 @@ QX_DI float substeps_s(const DevConfig& c, Env& e0, const f2 spxy, const float s
     physics_substep_s<FLOOR>(p, c, apwm, ca, false, minz);
     physics_substep_s<FLOOR>(p, c, apwm, cb, j + 2 == nsub, minz);
   }
-#endif
+  }
   unpack_core_s(e0, p);
   return minz;
 }
@@ -716,7 +719,9 @@ QX_DI void hot_reset_env(const DevConfig& c, const StepArgs& a, const int64_t i)
   const uint32_t k0 = c.seed_lo ^ (c.env_lo + (uint32_t)i);
   const uint32_t k1 = c.seed_hi ^ (c.env_hi + (uint32_t)(((uint64_t)c.env_lo + (uint64_t)i) >> 32));
   respawn(e, c, k0, k1);
-  substeps_s(c, e, f2{0.f, 0.f}, 0.f, 0.f, c.n_sub_reset, STREAM_RESET, i);  // set_mode(0): zero setpoint
+  // set_mode(0): zero setpoint.  The reset-queue launch is a latency chain of a few warps (~7 us for the 20 idle sub-steps, 0.3
+  // instructions per clock); generating the noise of Aviary.step j + 1 during step j (QX_RESET_SWP = 2) measured no shorter
+  substeps_s<true, QX_RESET_SWP>(c, e, f2{0.f, 0.f}, 0.f, 0.f, c.n_sub_reset, STREAM_RESET, i);
   const float act[4] = {0.f, 0.f, 0.f, 0.f};  // hover.py:101
   float obs[OBS_DIM];
   ObsAux x;
