@@ -422,10 +422,16 @@ def main_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         kern_ms = statistics.mean(per)
         achieved = E * ALG_BYTES_PER_ENV_STEP / (kern_ms * 1e-3) / 1e9
-        traffic, compute_side = None, None
+        traffic, compute_side, traffic_stale = None, None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
+            import hashlib
+
+            hsh = hashlib.sha256()
+            for f in ("qx_kernels.cu", "qx_model.cuh", "qx_lanes.cuh", "qx_ref_constants.cuh"):
+                hsh.update(open(os.path.join(ROOT, "fpv-drone-rl-agent_b200", "csrc", f), "rb").read())
+            traffic_stale = tj.get("kernel_sources_sha16") != hsh.hexdigest()[:16]  # the capture was taken from other kernel sources
             if tj.get("envs") == E:
                 traffic = tj.get("dram_bytes_per_launch")
                 if "thread_instructions_per_env_step" in tj:
@@ -435,7 +441,7 @@ def main_ours(args):
                     cap = 148 * 4 * 32 * 1.965e9 / ipe
                     compute_side = {"thread_instructions_per_env_step": ipe, "issue_active_pct_ncu": tj.get("issue_active_pct"),
                                     "issue_bound_env_steps_per_s": cap, "issue_bound_as_frac_of_hbm_roofline": cap * ALG_BYTES_PER_ENV_STEP / (peak * 1e9),
-                                    "source": tj.get("source")}
+                                    "source": tj.get("source"), "capture_is_of_these_sources": not traffic_stale}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -449,7 +455,8 @@ def main_ours(args):
             "clocks": clocks,
             "kernels": ("reference-constant instantiation (model constants of the reference's own parameter set as literals)"
                         if sim.lib.qx_uses_reference_constants(sim._h) else "generic (every constant read from the config)"),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "compute_side": compute_side,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_capture_is_of_these_sources": (None if traffic_stale is None else not traffic_stale),
+                         "compute_side": compute_side,
                          "kernel": "qx::quadx_step_hot_kernel<REF, SHAPE 4, S1> (one env per thread, paired FFMA2 / FMUL2 / FADD2) + qx::quadx_reset_hot_kernel, both launches inside the step time", "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP,
                          "kernel_ms": kern_ms, "kernel_ms_min": min(per), "peak_source": peak_src},
         }

@@ -73,5 +73,11 @@ if os.path.exists(launches):
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", f"{prefix}_{tag}.md"), "w").write("\n".join(out) + "\n")
 if traffic and "quadx" in traffic["kernel"]:
+    import hashlib
+
+    hsh = hashlib.sha256()
+    for f in ("qx_kernels.cu", "qx_model.cuh", "qx_lanes.cuh", "qx_ref_constants.cuh"):  # bench.py compares this with the sources it runs
+        hsh.update(open(os.path.join(ROOT, "fpv-drone-rl-agent_b200", "csrc", f), "rb").read())
+    traffic["kernel_sources_sha16"] = hsh.hexdigest()[:16]
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "k1_traffic.json"), "w"), indent=1)
 print("\n".join(out[:60]))
