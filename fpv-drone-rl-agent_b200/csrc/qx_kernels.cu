@@ -147,6 +147,12 @@ __device__ __forceinline__ void publish_queue_length(ResetQueue* q) {
 // REF: the model constants are the reference's literals (qx_ref_constants.cuh) instead of kernel parameters
 template <int MODE, int TASK, bool CASC = false, bool REF = false>
 __global__ void __launch_bounds__(kBlock, QX_MIN_BLOCKS) quadx_step_kernel(const __grid_constant__ DevConfig cparam, const __grid_constant__ StepArgs a) {
+  if (MODE == MODE_STEP_INLINE) {
+    // launched as a programmatic dependent of whatever kernel precedes it on the stream (launch_task): wait for that grid and its
+    // memory, then let the next launch of the chain be scheduled while this one runs (small batches are launch-latency-bound)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+  }
   DevConfig cref = cparam;  // scalar-replaced by the compiler: untouched fields stay parameter reads
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
@@ -1183,7 +1189,19 @@ template <int TASK, bool CASC, bool REF>
 static void launch_task(QxHandle* h, int mode, const qx::StepArgs& a, cudaStream_t s) {
   const unsigned grid = (unsigned)((a.env_count + qx::kBlock - 1) / qx::kBlock);
   switch (mode) {
-    case qx::MODE_STEP_INLINE: qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
+    case qx::MODE_STEP_INLINE:
+      if (h->pdl) {  // one launch per agent step: consecutive steps chain as programmatic dependents (the kernel waits for its predecessor at its top)
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(qx::kBlock); lc.dynamicSmemBytes = 0; lc.stream = s;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = &at; lc.numAttrs = 1;
+        cudaLaunchKernelEx(&lc, qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC, REF>, h->dev, a);
+      } else {
+        qx::quadx_step_kernel<qx::MODE_STEP_INLINE, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a);
+      }
+      break;
     case qx::MODE_STEP_DEFER: qx::quadx_step_kernel<qx::MODE_STEP_DEFER, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     case qx::MODE_RESET_MASK: qx::quadx_step_kernel<qx::MODE_RESET_MASK, TASK, CASC, REF><<<grid, qx::kBlock, 0, s>>>(h->dev, a); break;
     default: {
