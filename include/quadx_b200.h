@@ -214,6 +214,20 @@ int64_t qx_sizeof_config(void);
 const char* qx_last_error(void);
 int32_t qx_version(void);
 
+/* Environment variables read once at qx_create (tuning and A/B measurements; every setting computes the same results, and the
+ * defaults are what measured fastest on B200 -- profiles/k1_r2_variants.md):
+ *   QX_FORCE_GENERIC=1   generic kernels even when the configuration equals the reference's constants
+ *   QX_HOT=0|1           never / always the lean one-step hover kernel (default: batches of >= 32 768 envs)
+ *   QX_LANES=1|2|4       hot kernel: scalar lanes / two envs per thread on f32x2 / one env per thread, own components paired (default 4)
+ *   QX_SHAPE=0|3|4|5     hot kernel launch shape (resident blocks per SM; default 4 = 5 blocks of 128 threads, 96 registers)
+ *   QX_MERGED=1          hot kernel also drains the reset queue (one launch per step; default 0: two launches)
+ *   QX_PAIRED_RESET=0    queued envs re-created by the generic code instead of the paired one
+ *   QX_STREAM_STORES=1|2 evict-first stores for the outputs / the state planes too (default 0)
+ *   QX_PDL=0             no programmatic dependent launches (default 1: the reset-queue kernel of qx_step, and consecutive
+ *                        single-launch steps, are scheduled while their predecessor still runs and wait for it on the device)
+ *   QX_HOST_CHUNKS=k     *_host calls: k equal pieces (the first halved again), k < 0: -k geometric pieces (default: 5 geometric)
+ *   QX_HOST_ONE_D2H=1    *_host calls: the small result arrays share the observation's device-to-host stream */
+
 #ifdef __cplusplus
 }
 #endif
