@@ -225,15 +225,23 @@ def hover_leg(pkg, dev, envs: int, rank: int, world: int, steps: int, warmup: in
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for k in range(steps):
-        if flush is not None:
+    if flush is None:  # one event pair around the window: an event record between two steps would end the programmatic launch chain
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            sim.step(acts[k % 8], obs, rew, te, tr)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
             flush.zero_()
-        ev[k][0].record()
-        sim.step(acts[k % 8], obs, rew, te, tr)
-        ev[k][1].record()
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+            ev[k][0].record()
+            sim.step(acts[k % 8], obs, rew, te, tr)
+            ev[k][1].record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,18 +358,33 @@ def main_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _lib.lib().qx_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    # the timed region: K steps between two events on the launching stream.  No event between the steps: a tight loop of qx_step is
+    # a chain of programmatic dependent launches (step -> reset queue -> next step), which an event record in between would cut
+    # (tools/step_ab.py: 139.0 us per step against 142.9 with one event per step); the per-step times of the line come from a
+    # second, diagnostic pass over the same window below
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ev[0].record()
+    ev0.record()
     for k in range(args.steps):
         sim.step(acts[k % 8], obs, rew, te, tr)
-        ev[k + 1].record()
+    ev1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     if world > 1:
         dist.barrier()
     launches = _lib.lib().qx_launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = ev0.elapsed_time(ev1)
+    # diagnostic pass (not part of `value`): the same window again from a fresh reset, one event per step
+    sim.reset(obs)
+    for k in range(args.warmup):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        sim.step(acts[k % 8], obs, rew, te, tr)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
     per = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -420,7 +443,7 @@ def main_ours(args):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        kern_ms = statistics.mean(per)
+        kern_ms = total_ms / args.steps  # this rank's timed region (the line's ms_per_step is the slowest rank's)
         achieved = E * ALG_BYTES_PER_ENV_STEP / (kern_ms * 1e-3) / 1e9
         traffic, compute_side, traffic_stale = None, None, None
         tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -462,6 +485,7 @@ def main_ours(args):
         }
         line["roofline"]["step_ms_first8_min"] = min(per[:8]) if len(per) >= 8 else None
         line["roofline"]["step_ms_each"] = [round(x, 4) for x in per[:64]]
+        line["roofline"]["step_ms_each_note"] = "diagnostic second pass over the same window with one event per step (costs ~3 us per step: the event record ends the programmatic launch chain); not what `value` was timed on"
         if world == 1 and not args.no_small:
             line["hover_4096"] = small_config(pkg, dev)
         if world == 1 and not args.no_small:

@@ -796,7 +796,12 @@ template <bool REF, int SHAPE, class V, bool MERGED>
 __global__ void __launch_bounds__(HotShape<SHAPE>::kBlock, HotShape<SHAPE>::kMinBlocks) quadx_step_hot_kernel(const __grid_constant__ DevConfig cparam,
                                                                                                                  const __grid_constant__ StepArgs a) {
   constexpr int kB = HotShape<SHAPE>::kBlock, kLanes = Lane<V>::N, kWarps = kB / 32, kTask = 32 * kLanes;
-  if constexpr (!MERGED) asm volatile("griddepcontrol.launch_dependents;");  // the reset-queue launch may be scheduled once the last wave has started
+  if constexpr (!MERGED) {
+    // launched as a programmatic dependent of the kernel before it on the stream (launch_hot_kernel): wait for that grid and its
+    // memory; then the reset-queue launch that follows may be scheduled as soon as the last wave of this grid has started
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+  }
   DevConfig cref = cparam;
   if (REF) apply_ref_constants(cref);
   const DevConfig& c = REF ? cref : cparam;
@@ -854,6 +859,7 @@ __global__ void __launch_bounds__(128, 4) quadx_reset_hot_kernel(const __grid_co
   // launched as a programmatic dependent of the step launch (qx_step): the blocks are already on the SMs when the step grid
   // retires and wait here for its memory; a no-op in a plain launch
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");  // the next step launch of a tight loop (it waits at its own top)
   const unsigned int cnt = *reinterpret_cast<volatile unsigned int*>(&a.queue->count);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1228,6 +1234,15 @@ static cudaError_t launch_hot_kernel(QxHandle* h, const qx::StepArgs& a, cudaStr
     am.drainers = (uint32_t)h->hot_grid;
     qx::quadx_step_hot_kernel<REF, SHAPE, V, true><<<grid, B, 0, s>>>(h->dev, am);
     return cudaSuccess;
+  }
+  if (h->pdl) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(B); lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = &at; lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, qx::quadx_step_hot_kernel<REF, SHAPE, V, false>, h->dev, a);
   }
   qx::quadx_step_hot_kernel<REF, SHAPE, V, false><<<grid, B, 0, s>>>(h->dev, a);
   return cudaSuccess;

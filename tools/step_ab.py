@@ -42,6 +42,21 @@ for name, rate in (("tumble", 0.3), ("gentle", 0.02)):
         torch.cuda.synchronize()
         per = [ev[k].elapsed_time(ev[k + 1]) * 1e3 for k in range(K)]
         res.append((round(statistics.median(per[3:15]), 1), round(statistics.mean(per[5:25]), 1)))
+    # the same window without an event between the steps (an event record between two kernels ends a programmatic launch chain)
+    tot = []
+    for rep in range(3):
+        sim.reset(obs)
+        for k in range(5):
+            sim.step(acts[k % 8], obs, rew, te, tr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(5, 25):
+            sim.step(acts[k % 8], obs, rew, te, tr)
+        e1.record()
+        torch.cuda.synchronize()
+        tot.append(round(e0.elapsed_time(e1) * 1e3 / 20, 1))
     out[name] = res
+    out[name + "_steps5to24_no_inner_events"] = tot
     sim.close()
 print(json.dumps({"QX_PDL": os.environ.get("QX_PDL", "1"), **out}))
