@@ -130,6 +130,7 @@ struct FwdArgs {
   float fs_eps;
   float* fs_mean_out;             // == obs_mean, writable
   float* fs_inv_out;              // == obs_inv_std, writable
+  int32_t pdl_wait;               // launched as a programmatic dependent of the statistics kernel: wait for it before reading its results
 };
 
 // (defined with the K4 kernels below)
@@ -296,6 +297,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
     }
     __syncthreads();
   }
+  // two-launch form of ppo_policy_forward_stats: this grid was scheduled while the statistics kernel was still merging; everything
+  // above (weights, biases) does not depend on it, everything below (mean / inv_std, the observations) does
+  if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (tid < kIn) {
     sMean[tid] = (a.obs_mean && (int)tid < obs_dim) ? __ldcg(a.obs_mean + tid) : 0.f;
     sInv[tid] = (a.obs_inv_std && (int)tid < obs_dim) ? __ldcg(a.obs_inv_std + tid) : 1.f;
@@ -681,6 +685,7 @@ __global__ void __launch_bounds__(kStatThreads) running_stats_kernel(const float
                                                                     double* __restrict__ scratch, double* __restrict__ stats, float eps,
                                                                     float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
   __shared__ double sh[kStatThreads / 32][2 * kStatMaxDim];
+  asm volatile("griddepcontrol.launch_dependents;");  // a policy-forward launch chained behind this one may take the SMs as the blocks leave
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t warp_id = (int64_t)blockIdx.x * (kStatThreads / 32) + w, n_warps = (int64_t)gridDim.x * (kStatThreads / 32);
   double s = 0.0, q = 0.0;
@@ -780,6 +785,16 @@ static int launch_forward(ppo::FwdArgs& a, int64_t max_rows, void* stream) {
   const int64_t tiles = (max_rows + 127) / 128;
   const unsigned grid = (unsigned)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);  // small batches: one tile per SM before a second slot is used
   a.grid = (int32_t)grid;
+  if (a.pdl_wait) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(ppo::kFwdThreads); lc.dynamicSmemBytes = ppo::kSmTotal; lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = &at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, ppo::policy_forward_kernel, a) != cudaSuccess) return pfail(QX_ECUDA, "ppo_policy_forward: launch failed");
+    return QX_OK;
+  }
   ppo::policy_forward_kernel<<<grid, ppo::kFwdThreads, ppo::kSmTotal, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_policy_forward: launch failed");
 }
@@ -805,7 +820,7 @@ extern "C" int ppo_policy_forward(const PpoPolicy* p, const float* obs, int64_t 
 extern "C" int ppo_policy_forward_stats(const PpoPolicy* p, const float* obs, int64_t obs_stride, int64_t n, double* obs_stats, float eps,
                                         void* stats_scratch, float* obs_mean, float* obs_inv_std, float obs_clip, uint64_t seed, uint64_t row0,
                                         uint64_t step, const uint64_t* step_base_dev, int32_t deterministic, float* actions, float* env_actions,
-                                        float* values, float* log_probs, float* obs_norm_out, void* stream) {
+                                        float* values, float* log_probs, float* obs_norm_out, int32_t fused, void* stream) {
   if (!policy_ok(p) || !obs || n <= 0 || obs_stride < p->obs_dim || !obs_stats || !stats_scratch || !obs_mean || !obs_inv_std)
     return pfail(QX_EINVAL, "ppo_policy_forward_stats: bad arguments");
   ppo::FwdArgs a{};
@@ -813,7 +828,15 @@ extern "C" int ppo_policy_forward_stats(const PpoPolicy* p, const float* obs, in
   a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32); a.row0 = row0; a.step = step; a.step_base = step_base_dev;
   a.deterministic = deterministic; a.actions = actions; a.env_actions = env_actions; a.values = values; a.log_probs = log_probs;
   a.obs_norm_out = obs_norm_out;
-  a.fs_stats = obs_stats; a.fs_scratch = (double*)stats_scratch; a.fs_eps = eps; a.fs_mean_out = obs_mean; a.fs_inv_out = obs_inv_std;
+  if (fused) {
+    a.fs_stats = obs_stats; a.fs_scratch = (double*)stats_scratch; a.fs_eps = eps; a.fs_mean_out = obs_mean; a.fs_inv_out = obs_inv_std;
+    return launch_forward(a, n, stream);
+  }
+  // two launches, the second a programmatic dependent of the first: the policy kernel stages its weights while the statistics
+  // kernel's last block still merges, and waits on the device before it reads (mean, inv_std)
+  int rc = ppo_running_stats_update(obs, obs_stride, n, p->obs_dim, obs_stats, eps, obs_mean, obs_inv_std, stats_scratch, stream);
+  if (rc) return rc;
+  a.pdl_wait = 1;
   return launch_forward(a, n, stream);
 }
 

@@ -257,10 +257,11 @@ class RunningStats:
 def policy_forward(pol: PackedPolicy, obs: torch.Tensor, *, obs_stats: RunningStats | None = None, obs_clip: float = 10.0, seed: int = 0,
                    row0: int = 0, step: int = 0, step_base: torch.Tensor | None = None, deterministic: bool = False,
                    actions=None, env_actions=None, values=None, log_probs=None, obs_norm=None, norm: tuple | None = None,
-                   update_stats: bool = False) -> None:
+                   update_stats: bool = False, fused_stats: bool = False) -> None:
     """``ActorCriticPolicy.forward`` on the tensor cores (ppo_policy_forward).  norm = (mean, inv_std) overrides obs_stats' buffers.
-    update_stats: the same launch first merges `obs` into obs_stats and refreshes (mean, inv_std) -- VecNormalize's
-    ``obs_rms.update`` + ``normalize_obs`` of one env step in one kernel (ppo_policy_forward_stats)."""
+    update_stats: `obs` is first merged into obs_stats and (mean, inv_std) refreshed -- VecNormalize's ``obs_rms.update`` +
+    ``normalize_obs`` of one env step in one call (ppo_policy_forward_stats): two launches chained as programmatic dependents, or,
+    with fused_stats, one launch with the merge inside the policy kernel."""
     n = obs.shape[0]
     assert obs.dtype == torch.float32 and obs.stride(1) == 1
     mean, inv_std = norm if norm is not None else ((obs_stats.mean, obs_stats.inv_std) if obs_stats else (None, None))
@@ -269,7 +270,7 @@ def policy_forward(pol: PackedPolicy, obs: torch.Tensor, *, obs_stats: RunningSt
         check(_lib.lib().ppo_policy_forward_stats(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(obs_stats.stats), obs_stats.eps,
                                                   _p(obs_stats.scratch), _p(mean), _p(inv_std), obs_clip, seed, row0, step, _p(step_base),
                                                   int(deterministic), _p(actions), _p(env_actions), _p(values), _p(log_probs), _p(obs_norm),
-                                                  _stream(pol.device)))
+                                                  int(fused_stats), _stream(pol.device)))
         return
     check(_lib.lib().ppo_policy_forward(C.byref(pol.struct), _p(obs), obs.stride(0), n, _p(mean),
                                         _p(inv_std), obs_clip, seed, row0, step, _p(step_base),
@@ -339,6 +340,11 @@ class PPOConfig:
     fuse_obs_stats: bool = False  # VecNormalize's obs statistics update inside the policy-forward launch (ppo_policy_forward_stats): one launch
                                   # fewer per env step, but measured SLOWER inside the two-branch rollout graph (3.30 vs 3.16 ms per 131 072 x 32
                                   # rollout): the in-kernel wait for the last CTA makes every CTA wait for the SMs the side branch still holds
+    chain_obs_stats: bool | None = None  # the statistics launch and the policy-forward launch of a rollout step as programmatic dependents
+                                         # (ppo_policy_forward_stats, fused = 0).  None = where it measured faster: the hover task
+                                         # (131 072 envs x 32: 3.14 -> 3.03 ms per rollout), not the yaw task (65 536 x 128: 6.46 -> 6.75 ms --
+                                         # its env step + reset are shorter than the side branch of the step before, whose bootstrap launch
+                                         # then finds every SM taken by a policy CTA that is waiting on the device, and joins late)
     net_arch: int = HID  # hidden width of both MLPs: 128 = train_hover.py:57, 64 = SB3's default; < 128 runs zero-padded (ActorCritic)
 
 
@@ -398,12 +404,13 @@ class RolloutEngine:
         cfg, sim, L, s = self.cfg, self.sim, self.lib, _stream(self.device)
         stats = self.obs_stats if cfg.norm_obs else None
         norm = (self._snap_mean[t & 1], self._snap_inv[t & 1]) if cfg.norm_obs else None
-        fuse = cfg.norm_obs and cfg.fuse_obs_stats
-        if cfg.norm_obs and not fuse:
+        chain_cfg = cfg.chain_obs_stats if cfg.chain_obs_stats is not None else (sim.obs_dim == 20)  # hover: 20-D observation
+        chain = cfg.norm_obs and (cfg.fuse_obs_stats or chain_cfg)
+        if cfg.norm_obs and not chain:
             self.obs_stats.update(self.cur_obs, out=norm)
         policy_forward(self.pol, self.cur_obs, obs_stats=stats, norm=norm, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
                        step_base=self.step_base, actions=self.actions[t], env_actions=self.env_actions, values=self.values[t],
-                       log_probs=self.log_probs[t], obs_norm=self.obs[t], update_stats=fuse)
+                       log_probs=self.log_probs[t], obs_norm=self.obs[t], update_stats=chain, fused_stats=cfg.fuse_obs_stats)
         main = torch.cuda.current_stream(self.device)
         if t > 0:
             main.wait_stream(self._side)  # join the side branch of step t - 1 (the rollout ends with a join, so there is none at t = 0)

@@ -57,12 +57,15 @@ int ppo_policy_forward(const PpoPolicy* p, const float* obs, int64_t obs_stride,
  * n raw rows of obs into the running statistics obs_stats = {mean[obs_dim], var[obs_dim], count} (fp64, as
  * ppo_running_stats_update does), writes the refreshed fp32 obs_mean / obs_inv_std = 1 / sqrt(var + eps), and then runs
  * ppo_policy_forward with them.  stats_scratch: ppo_running_stats_scratch_bytes bytes, zeroed once, private to this stream.
- * The launch waits inside the kernel for its own last CTA (grid <= SM count, one CTA per SM: all resident together); do not run
- * two of these on one device at the same time from different streams. */
+ * fused != 0: the launch waits inside the kernel for its own last CTA (grid <= SM count, one CTA per SM: all resident together); do
+ * not run two of these on one device at the same time from different streams.
+ * fused == 0: ppo_running_stats_update followed by ppo_policy_forward as its programmatic dependent launch -- the policy kernel
+ * is scheduled as the statistics blocks leave the SMs, stages its weights while the last block merges, and waits on the device
+ * (griddepcontrol.wait) before it reads the statistics; same results as the two separate calls, what the rollout uses. */
 int ppo_policy_forward_stats(const PpoPolicy* p, const float* obs, int64_t obs_stride, int64_t n, double* obs_stats, float eps,
                              void* stats_scratch, float* obs_mean, float* obs_inv_std, float obs_clip, uint64_t seed, uint64_t row0,
                              uint64_t step, const uint64_t* step_base_dev, int32_t deterministic, float* actions, float* env_actions,
-                             float* values, float* log_probs, float* obs_norm_out, void* stream);
+                             float* values, float* log_probs, float* obs_norm_out, int32_t fused, void* stream);
 
 /* SB3 collect_rollouts time-limit bootstrap: for the envs listed in the done queue of the step just taken
  * (qx_done_queue) that were truncated but not terminated, reward += gamma * V(terminal_obs). */

@@ -186,8 +186,9 @@ def test_running_stats_and_reward_normalisation(env):
         assert np.array_equal(dn.cpu().numpy(), te | tr)
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("n", [1000, 131072, 200_001])
-def test_fused_statistics_forward_equals_the_two_launches(env, n):
+def test_fused_statistics_forward_equals_the_two_launches(env, n, fused):
     """ppo_policy_forward_stats (VecNormalize's obs_rms.update + normalize_obs + the policy forward in one launch) against
     ppo_running_stats_update followed by ppo_policy_forward: the running statistics agree to fp64 rounding (the per-CTA partial
     sums are grouped differently), the fp32 (mean, inv_std) to one ulp, and the outputs to what one ulp of the normalisation
@@ -204,7 +205,7 @@ def test_fused_statistics_forward_equals_the_two_launches(env, n):
         a_stats.update(x)
         ppo.policy_forward(pol, x, obs_stats=a_stats, obs_clip=10.0, seed=5, step=rep, actions=out_a[0], values=out_a[1], log_probs=out_a[2], obs_norm=out_a[3])
         ppo.policy_forward(pol, x, obs_stats=b_stats, obs_clip=10.0, seed=5, step=rep, actions=out_b[0], values=out_b[1], log_probs=out_b[2], obs_norm=out_b[3],
-                           update_stats=True)
+                           update_stats=True, fused_stats=fused)  # fused: one launch; not fused: two launches chained as programmatic dependents
         torch.cuda.synchronize()
         assert torch.allclose(a_stats.stats, b_stats.stats, rtol=1e-12, atol=1e-12), (a_stats.stats - b_stats.stats).abs().max()
         assert float(b_stats.stats[40]) == pytest.approx(1e-4 + (rep + 1) * n)
