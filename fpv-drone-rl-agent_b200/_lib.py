@@ -112,10 +112,12 @@ def lib() -> C.CDLL:
         "ppo_policy_forward": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, vp, f32, u64, u64, u64, vp, i32, vp, vp, vp, vp, vp, vp]),
         "ppo_policy_forward_stats": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, f32, vp, vp, vp, f32, u64, u64, u64, vp, i32, vp, vp, vp, vp, vp, i32, vp]),
         "ppo_bootstrap_truncated": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, vp, f32, vp, vp, vp, vp, f32, vp, vp]),
+        "ppo_bootstrap_truncated_first": (C.c_int, [C.POINTER(PpoPolicy), vp, i64, i64, vp, vp, f32, vp, vp, vp, vp, f32, vp, vp]),
         "ppo_gae": (C.c_int, [vp, vp, vp, vp, i32, i64, f32, f32, vp, vp, vp]),
         "ppo_running_stats_update": (C.c_int, [vp, i64, i64, i32, vp, f32, vp, vp, vp, vp]),
         "ppo_running_stats_scratch_bytes": (i64, [i32]),
         "ppo_reward_normalize": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp]),
+        "ppo_reward_normalize_add": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp]),
         "ppo_test_gemm": (C.c_int, [vp, vp, vp, i32, i32, vp]),
         "ppo_test_gemm_mn": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
         "ppo_update_num_params": (i32, [i32, i32]),
@@ -144,7 +146,7 @@ EXPORTED = [
     "qx_get_state", "qx_set_state", "qx_get_flags", "qx_episode_stats", "qx_nonfinite_count", "qx_num_envs", "qx_obs_dim", "qx_act_dim", "qx_state_ptr", "qx_state_words", "qx_uses_reference_constants", "qx_config_matches_reference_constants",
     "qx_launch_count", "qx_sizeof_config", "qx_last_error", "qx_version",
 ]
-PPO_EXPORTED = ["ppo_policy_forward", "ppo_policy_forward_stats", "ppo_bootstrap_truncated", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
+PPO_EXPORTED = ["ppo_policy_forward", "ppo_policy_forward_stats", "ppo_bootstrap_truncated", "ppo_bootstrap_truncated_first", "ppo_reward_normalize_add", "ppo_gae", "ppo_running_stats_update", "ppo_running_stats_scratch_bytes",
                 "ppo_reward_normalize", "ppo_test_gemm", "ppo_test_gemm_mn", "ppo_update_num_params", "ppo_update_workspace_bytes",
                 "ppo_update_minibatch", "ppo_update_grad_norm", "ppo_update_adam", "ppo_update_step_count", "ppo_update_set_lr_scale", "ppo_update_kl_stop", "ppo_update_set_log_std_floor", "ppo_update_recompute_logp"]
 

@@ -131,6 +131,7 @@ struct FwdArgs {
   float* fs_mean_out;             // == obs_mean, writable
   float* fs_inv_out;              // == obs_inv_std, writable
   int32_t pdl_wait;               // launched as a programmatic dependent of the statistics kernel: wait for it before reading its results
+  int32_t boot_store;             // bootstrap: reward[row] = gamma V (the reward-normalisation launch that follows adds its result) instead of +=
 };
 
 // (defined with the K4 kernels below)
@@ -415,7 +416,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) policy_forward_kernel(const Fw
     }
     if (a.values) a.values[row] = value;
     if (a.log_probs) a.log_probs[row] = logp;
-    if (a.boot_reward && a.boot_tr[row] && !a.boot_te[row]) a.boot_reward[row] = fmaf(a.boot_gamma, value, a.boot_reward[row]);
+    if (a.boot_reward && a.boot_tr[row] && !a.boot_te[row])
+      a.boot_reward[row] = a.boot_store ? a.boot_gamma * value : fmaf(a.boot_gamma, value, a.boot_reward[row]);
   };
   auto issue_l1p = [&]() {
 #pragma unroll
@@ -742,12 +744,14 @@ __global__ void __launch_bounds__(kRetThreads) returns_stats_kernel(const float*
 }
 
 __global__ void __launch_bounds__(256) reward_norm_kernel(const float* __restrict__ r, const uint8_t* __restrict__ te, const uint8_t* __restrict__ tr, float* __restrict__ acc,
-                                                          int64_t n, float clip, float eps, const double* __restrict__ ret_stats, float* __restrict__ out,
-                                                          uint8_t* __restrict__ done_out) {
+                                                          int64_t n, float clip, float eps, const double* __restrict__ ret_stats, float* out,
+                                                          uint8_t* __restrict__ done_out, int add_boot) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float inv = ret_stats ? (float)(1.0 / sqrt(ret_stats[1] + (double)eps)) : 1.f;
-  out[i] = fminf(fmaxf(r[i] * inv, -clip), clip);
+  // add_boot: the time-limit bootstrap ran first and left gamma V(terminal_obs) in out[i] for the truncated rows
+  const float boot = (add_boot && tr[i] && !te[i]) ? out[i] : 0.f;
+  out[i] = fminf(fmaxf(r[i] * inv, -clip), clip) + boot;
   const uint8_t d = te[i] | tr[i];
   if (d && acc) acc[i] = 0.f;
   if (done_out) done_out[i] = d;
@@ -852,6 +856,18 @@ extern "C" int ppo_bootstrap_truncated(const PpoPolicy* p, const float* terminal
   return launch_forward(a, n, stream);
 }
 
+extern "C" int ppo_bootstrap_truncated_first(const PpoPolicy* p, const float* terminal_obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                                             const float* obs_inv_std, float obs_clip, const uint32_t* done_count_dev, const uint32_t* done_idx_dev,
+                                             const uint8_t* terminated, const uint8_t* truncated, float gamma, float* reward_out, void* stream) {
+  if (!policy_ok(p) || !terminal_obs || n <= 0 || !done_count_dev || !done_idx_dev || !terminated || !truncated || !reward_out)
+    return pfail(QX_EINVAL, "ppo_bootstrap_truncated_first: bad arguments");
+  ppo::FwdArgs a{};
+  a.p = *p; a.obs = terminal_obs; a.obs_stride = obs_stride; a.n = n; a.obs_mean = obs_mean; a.obs_inv_std = obs_inv_std; a.obs_clip = obs_clip;
+  a.deterministic = 1; a.gather_idx = done_idx_dev; a.gather_count = done_count_dev; a.boot_reward = reward_out; a.boot_te = terminated;
+  a.boot_tr = truncated; a.boot_gamma = gamma; a.boot_store = 1;
+  return launch_forward(a, n, stream);
+}
+
 extern "C" int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int32_t T, int64_t n,
                        float gamma, float lam, float* advantages, float* returns, void* stream) {
   if (!rewards || !values || !dones || !last_values || !advantages || !returns || T <= 0 || n <= 0) return pfail(QX_EINVAL, "ppo_gae: bad arguments");
@@ -878,16 +894,28 @@ extern "C" int ppo_running_stats_update(const float* x, int64_t stride, int64_t 
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_running_stats_update: launch failed");
 }
 
-extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
-                                    float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream) {
+static int reward_normalize_impl(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                                 float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream,
+                                 int add_boot) {
   if (!reward || !terminated || !truncated || !returns_acc || !ret_stats || !reward_out || !scratch || n <= 0)
     return pfail(QX_EINVAL, "ppo_reward_normalize: bad arguments");
   const unsigned grid = (unsigned)((n + 255) / 256);
   int64_t want = (n + ppo::kRetThreads - 1) / ppo::kRetThreads;
   const int blocks = (int)(want < ppo::kStatBlocks ? want : ppo::kStatBlocks);
   ppo::returns_stats_kernel<<<blocks, ppo::kRetThreads, 0, (cudaStream_t)stream>>>(reward, returns_acc, n, gamma, (double*)scratch, ret_stats, eps);
-  ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out);
+  ppo::reward_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, truncated, returns_acc, n, clip, eps, ret_stats, reward_out, done_out, add_boot);
   return cudaGetLastError() == cudaSuccess ? QX_OK : pfail(QX_ECUDA, "ppo_reward_normalize: launch failed");
+}
+
+extern "C" int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                                    float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream) {
+  return reward_normalize_impl(reward, terminated, truncated, returns_acc, n, gamma, clip, eps, ret_stats, reward_out, done_out, scratch, stream, 0);
+}
+
+extern "C" int ppo_reward_normalize_add(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                                        float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch,
+                                        void* stream) {
+  return reward_normalize_impl(reward, terminated, truncated, returns_acc, n, gamma, clip, eps, ret_stats, reward_out, done_out, scratch, stream, 1);
 }
 
 // debug / tuning hook (not part of the public header): device buffer of 8 x 16 int64 clock stamps, or NULL to switch off

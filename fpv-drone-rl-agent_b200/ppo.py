@@ -340,11 +340,12 @@ class PPOConfig:
     fuse_obs_stats: bool = False  # VecNormalize's obs statistics update inside the policy-forward launch (ppo_policy_forward_stats): one launch
                                   # fewer per env step, but measured SLOWER inside the two-branch rollout graph (3.30 vs 3.16 ms per 131 072 x 32
                                   # rollout): the in-kernel wait for the last CTA makes every CTA wait for the SMs the side branch still holds
-    chain_obs_stats: bool | None = None  # the statistics launch and the policy-forward launch of a rollout step as programmatic dependents
-                                         # (ppo_policy_forward_stats, fused = 0).  None = where it measured faster: the hover task
-                                         # (131 072 envs x 32: 3.14 -> 3.03 ms per rollout), not the yaw task (65 536 x 128: 6.46 -> 6.75 ms --
-                                         # its env step + reset are shorter than the side branch of the step before, whose bootstrap launch
-                                         # then finds every SM taken by a policy CTA that is waiting on the device, and joins late)
+    chain_obs_stats: bool = True  # the statistics launch and the policy-forward launch of a rollout step as programmatic dependents
+                                  # (ppo_policy_forward_stats, fused = 0): hover 131 072 x 32: 3.14 -> 3.02 ms per rollout
+    bootstrap_first: bool | None = None  # side branch: time-limit bootstrap before the reward normalisation (ppo_bootstrap_truncated_first +
+                                         # ppo_reward_normalize_add).  None = where it measured faster: the yaw task, whose env step + reset are
+                                         # shorter than the side branch (65 536 x 128 with the chain: 6.73 -> 6.06 ms; without either: 6.51 ms),
+                                         # not the hover task (3.02 -> 3.07 ms)
     net_arch: int = HID  # hidden width of both MLPs: 128 = train_hover.py:57, 64 = SB3's default; < 128 runs zero-padded (ActorCritic)
 
 
@@ -404,8 +405,7 @@ class RolloutEngine:
         cfg, sim, L, s = self.cfg, self.sim, self.lib, _stream(self.device)
         stats = self.obs_stats if cfg.norm_obs else None
         norm = (self._snap_mean[t & 1], self._snap_inv[t & 1]) if cfg.norm_obs else None
-        chain_cfg = cfg.chain_obs_stats if cfg.chain_obs_stats is not None else (sim.obs_dim == 20)  # hover: 20-D observation
-        chain = cfg.norm_obs and (cfg.fuse_obs_stats or chain_cfg)
+        chain = cfg.norm_obs and (cfg.fuse_obs_stats or cfg.chain_obs_stats)
         if cfg.norm_obs and not chain:
             self.obs_stats.update(self.cur_obs, out=norm)
         policy_forward(self.pol, self.cur_obs, obs_stats=stats, norm=norm, obs_clip=cfg.clip_obs, seed=cfg.seed, row0=self.row0, step=t,
@@ -419,17 +419,25 @@ class RolloutEngine:
         self._side.wait_stream(main)  # fork
         with torch.cuda.stream(self._side):
             ss = _stream(self.device)
-            if cfg.norm_reward:
-                check(L.ppo_reward_normalize(_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
-                                             self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]),
-                                             _p(self.ret_stats.scratch), ss))
+            boot_args = (C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
+                         _p(norm[0]) if norm else None, _p(norm[1]) if norm else None, cfg.clip_obs,
+                         self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), ss)
+            norm_args = (_p(self.raw_reward), _p(self.te), _p(self.tr), _p(self.returns_acc), self.n, cfg.gamma, cfg.clip_reward,
+                         self.ret_stats.eps, _p(self.ret_stats.stats), _p(self.rewards[t]), _p(self.dones[t]), _p(self.ret_stats.scratch), ss)
+            boot_first = cfg.bootstrap_first if cfg.bootstrap_first is not None else (sim.obs_dim != 20)  # yaw: 12-D observation
+            if cfg.norm_reward and boot_first:
+                # the bootstrap launch needs a whole SM's shared memory per CTA even to find the done queue empty: issued first it runs
+                # while the main branch is still in the reset / statistics launches, not after the policy CTAs have taken the SMs
+                check(L.ppo_bootstrap_truncated_first(*boot_args))
+                check(L.ppo_reward_normalize_add(*norm_args))
             else:
-                self.rewards[t].copy_(self.raw_reward)
-                torch.bitwise_or(self.te, self.tr, out=self.dones[t])
-            # SB3: rewards[idx] += gamma * V(terminal_obs) when the time limit, not the task, ended the episode
-            check(L.ppo_bootstrap_truncated(C.byref(self.pol.struct), _p(self.terminal_obs), self.terminal_obs.stride(0), self.n,
-                                            _p(norm[0]) if norm else None, _p(norm[1]) if norm else None, cfg.clip_obs,
-                                            self._q_count, self._q_idx, _p(self.te), _p(self.tr), cfg.gamma, _p(self.rewards[t]), ss))
+                if cfg.norm_reward:
+                    check(L.ppo_reward_normalize(*norm_args))
+                else:
+                    self.rewards[t].copy_(self.raw_reward)
+                    torch.bitwise_or(self.te, self.tr, out=self.dones[t])
+                # SB3: rewards[idx] += gamma * V(terminal_obs) when the time limit, not the task, ended the episode
+                check(L.ppo_bootstrap_truncated(*boot_args))
         check(L.qx_step_end(sim._h, _p(self.cur_obs), 0, self.cur_obs.stride(0), s))
 
     def _rollout_body(self) -> None:

@@ -73,6 +73,14 @@ int ppo_bootstrap_truncated(const PpoPolicy* p, const float* terminal_obs, int64
                             const float* obs_inv_std, float obs_clip, const uint32_t* done_count_dev, const uint32_t* done_idx_dev,
                             const uint8_t* terminated, const uint8_t* truncated, float gamma, float* reward_inout, void* stream);
 
+/* The same two operations in the other order, for a rollout whose side branch must not wait for a free SM late:
+ * ppo_bootstrap_truncated_first STORES gamma * V(terminal_obs) into reward_out[row] for the truncated, not terminated envs of
+ * the done queue; ppo_reward_normalize_add (below) then writes clip(r / sigma) + that value for exactly those rows and
+ * clip(r / sigma) for all others.  Result = ppo_reward_normalize followed by ppo_bootstrap_truncated up to one rounding. */
+int ppo_bootstrap_truncated_first(const PpoPolicy* p, const float* terminal_obs, int64_t obs_stride, int64_t n, const float* obs_mean,
+                                  const float* obs_inv_std, float obs_clip, const uint32_t* done_count_dev, const uint32_t* done_idx_dev,
+                                  const uint8_t* terminated, const uint8_t* truncated, float gamma, float* reward_out, void* stream);
+
 /* RolloutBuffer.compute_returns_and_advantage: rewards, values, dones [T, n] (dones[t] = episode ended AT step t),
  * last_values [n]; writes advantages, returns [T, n]. */
 int ppo_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int32_t T, int64_t n,
@@ -92,6 +100,9 @@ int64_t ppo_running_stats_scratch_bytes(int32_t dim);
  * ret = 0 where done; done_out [n] (nullable) = terminated | truncated.  `returns_acc` [n] is the per-env discounted return accumulator. */
 int ppo_reward_normalize(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
                          float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch, void* stream);
+int ppo_reward_normalize_add(const float* reward, const uint8_t* terminated, const uint8_t* truncated, float* returns_acc, int64_t n,
+                             float gamma, float clip, float eps, double* ret_stats, float* reward_out, uint8_t* done_out, void* scratch,
+                             void* stream);
 
 /* ---- the PPO update (SB3 PPO.train, reached by train_hover.py:60 `model.learn`) --------------------------------------
  * Flat fp32 parameter vector, in the module order of SB3's ActorCriticPolicy(net_arch=[128,128]) with separate pi / vf

@@ -249,6 +249,24 @@ def test_time_limit_bootstrap(env):
         exp = before + 0.99 * v * trunc_only
         assert (rew - exp)[trunc_only].abs().max().item() < 3e-2 if trunc_only.any() else True
         assert torch.equal(rew[~trunc_only], before[~trunc_only])
+        # the other order (ppo_bootstrap_truncated_first + ppo_reward_normalize_add) gives the same rewards as
+        # ppo_reward_normalize + ppo_bootstrap_truncated, up to the one rounding of fma(gamma, V, r) vs gamma V + r
+        outs = []
+        for first in (False, True):
+            st, acc = ppo.RunningStats(1, "cuda"), torch.zeros(n, device="cuda")
+            st.stats[1] = 4.0  # a return variance that is not 1
+            out, dn = torch.full((n,), 123.0, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+            boot = (C.byref(pol.struct), tobs.data_ptr(), 20, n, None, None, 0.0, cnt, idx, te.data_ptr(), tr.data_ptr(), 0.99, out.data_ptr(), None)
+            nrm = (before.data_ptr(), te.data_ptr(), tr.data_ptr(), acc.data_ptr(), n, 0.99, 10.0, st.eps, st.stats.data_ptr(), out.data_ptr(), dn.data_ptr(),
+                   st.scratch.data_ptr(), None)
+            if first:
+                assert L.ppo_bootstrap_truncated_first(*boot) == 0 and L.ppo_reward_normalize_add(*nrm) == 0
+            else:
+                assert L.ppo_reward_normalize(*nrm) == 0 and L.ppo_bootstrap_truncated(*boot) == 0
+            torch.cuda.synchronize()
+            outs.append((out.clone(), dn.clone(), acc.clone(), st.stats.clone()))
+        assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 and torch.equal(outs[0][1], outs[1][1])
+        assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
         seen_trunc += int(trunc_only.sum()); seen_term += int(te.sum())
     assert seen_trunc > 0 and seen_term > 0
 

@@ -35,7 +35,8 @@ def measure(envs: int = 131072, steps: int = 32, reps: int = 5, rank: int = 0, w
     tflops_peak = peaks.get("bf16_tflops", 1590.0)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     cfg = ppo.PPOConfig(n_envs=envs, n_steps=steps, seed=0, use_cuda_graph=True,
-                        chain_obs_stats={"0": False, "1": True}.get(os.environ.get("PPO_CHAIN_OBS_STATS", ""), None))  # (A/B switch for tools runs)
+                        chain_obs_stats=os.environ.get("PPO_CHAIN_OBS_STATS", "1") != "0",  # (A/B switches for tools runs)
+                        bootstrap_first={"0": False, "1": True}.get(os.environ.get("PPO_BOOTSTRAP_FIRST", ""), None))
     tr = ppo.PPOTrainer(cfg, device=dev, rank=rank, world=world, task=task)
     ro = tr.rollout
 
